@@ -1,0 +1,578 @@
+// C ABI of the emg3d_b200 library (see include/emg3d_b200.h).
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/emg3d_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace emg;
+
+namespace emg {
+long long g_launch_count = 0;
+}
+
+static thread_local std::string g_err;
+static cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+static double* g_dot_scratch = nullptr;   // partials for dot products
+static double* g_dot_out = nullptr;       // 2 doubles
+static int64_t g_dot_scratch_n = 0;
+
+static int fail(const char* where, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_err = buf;
+    return (int)e ? (int)e : -1;
+}
+static int fail_msg(const char* msg) {
+    g_err = msg;
+    return -1;
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t _e = (call);                          \
+        if (_e != cudaSuccess) return fail(#call, _e);    \
+    } while (0)
+#define CK_LAUNCH(name)                                   \
+    do {                                                  \
+        cudaError_t _e = cudaPeekAtLastError();           \
+        if (_e != cudaSuccess) {                          \
+            cudaGetLastError();                           \
+            return fail(name, _e);                        \
+        }                                                 \
+    } while (0)
+#define NEED_INIT()                                                              \
+    do {                                                                         \
+        if (!g_stream) return fail_msg("emg3d_b200_init() has not been called"); \
+    } while (0)
+
+struct emg3d_b200_level {
+    Dims d;
+    double* h[3];        // device
+    double* rh[3];       // device
+    int cplx;            // -1 until a model is set
+    const void* eta[3];
+    const double* zeta;
+    void* fac[3];        // cached line factorisations (device), per direction
+    double* scratch;     // residual-norm partials
+    double* norm2;       // device scalar
+    // link to the parent (fine) level
+    Dims fine;
+    int linked;
+    int cflag[3];
+    double* w[9];        // device weights
+    int* lo[3];
+    double* fr[3];
+};
+
+template <typename T>
+static Model<T> model_of(const emg3d_b200_level* lv) {
+    Model<T> m;
+    m.d = lv->d;
+    for (int a = 0; a < 3; ++a) {
+        m.eta[a] = (const T*)lv->eta[a];
+        m.h[a] = lv->h[a];
+        m.rh[a] = lv->rh[a];
+    }
+    m.zeta = lv->zeta;
+    return m;
+}
+
+extern "C" {
+
+int emg3d_b200_abi_version(void) { return 1; }
+
+const char* emg3d_b200_last_error(void) { return g_err.c_str(); }
+
+int emg3d_b200_device_count(int* count) {
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int emg3d_b200_init(int device) {
+    if (g_stream && device == g_device) return 0;
+    if (g_stream) return fail_msg("emg3d_b200_init: already initialised on another device");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    g_dot_scratch_n = dot_scratch_doubles((int64_t)1 << 40);
+    CK(cudaMalloc(&g_dot_scratch, sizeof(double) * g_dot_scratch_n));
+    CK(cudaMalloc(&g_dot_out, sizeof(double) * 2));
+    return 0;
+}
+
+int emg3d_b200_device_name(char* buf, int buflen) {
+    NEED_INIT();
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, g_device));
+    snprintf(buf, buflen, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
+    return 0;
+}
+
+int emg3d_b200_mem_info(size_t* free_bytes, size_t* total_bytes) {
+    NEED_INIT();
+    CK(cudaMemGetInfo(free_bytes, total_bytes));
+    return 0;
+}
+
+int emg3d_b200_sync(void) {
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int emg3d_b200_launch_count(long long* count) {
+    *count = emg::g_launch_count;
+    return 0;
+}
+
+// ---- memory ------------------------------------------------------------------
+int emg3d_b200_malloc(void** dptr, size_t nbytes) {
+    NEED_INIT();
+    *dptr = nullptr;
+    CK(cudaMalloc(dptr, nbytes ? nbytes : 16));
+    return 0;
+}
+int emg3d_b200_free(void* dptr) {
+    if (!dptr) return 0;
+    CK(cudaFree(dptr));
+    return 0;
+}
+int emg3d_b200_memset(void* dptr, int byte, size_t nbytes) {
+    NEED_INIT();
+    CK(cudaMemsetAsync(dptr, byte, nbytes, g_stream));
+    return 0;
+}
+int emg3d_b200_h2d(void* dst, const void* src, size_t nbytes) {
+    NEED_INIT();
+    CK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int emg3d_b200_d2h(void* dst, const void* src, size_t nbytes) {
+    NEED_INIT();
+    CK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int emg3d_b200_d2d(void* dst, const void* src, size_t nbytes) {
+    NEED_INIT();
+    CK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, g_stream));
+    return 0;
+}
+int emg3d_b200_host_alloc(void** hptr, size_t nbytes) {
+    CK(cudaMallocHost(hptr, nbytes ? nbytes : 16));
+    return 0;
+}
+int emg3d_b200_host_free(void* hptr) {
+    if (!hptr) return 0;
+    CK(cudaFreeHost(hptr));
+    return 0;
+}
+
+// ---- events / graphs ---------------------------------------------------------
+int emg3d_b200_event_create(void** ev) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    *ev = (void*)e;
+    return 0;
+}
+int emg3d_b200_event_record(void* ev) {
+    NEED_INIT();
+    CK(cudaEventRecord((cudaEvent_t)ev, g_stream));
+    return 0;
+}
+int emg3d_b200_event_elapsed_ms(void* a, void* b, float* ms) {
+    CK(cudaEventSynchronize((cudaEvent_t)b));
+    CK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return 0;
+}
+int emg3d_b200_event_destroy(void* ev) {
+    CK(cudaEventDestroy((cudaEvent_t)ev));
+    return 0;
+}
+int emg3d_b200_graph_begin(void) {
+    NEED_INIT();
+    CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+int emg3d_b200_graph_end(void** graph_exec) {
+    NEED_INIT();
+    cudaGraph_t g;
+    CK(cudaStreamEndCapture(g_stream, &g));
+    cudaGraphExec_t ge;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate", e);
+    *graph_exec = (void*)ge;
+    return 0;
+}
+int emg3d_b200_graph_launch(void* graph_exec) {
+    NEED_INIT();
+    CK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, g_stream));
+    return 0;
+}
+int emg3d_b200_graph_destroy(void* graph_exec) {
+    CK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return 0;
+}
+
+// ---- levels ------------------------------------------------------------------
+int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz, const double* hx,
+                            const double* hy, const double* hz) {
+    NEED_INIT();
+    if (nx < 2 || ny < 2 || nz < 2) return fail_msg("level_create: need at least 2 cells per axis");
+    emg3d_b200_level* lv = new emg3d_b200_level();
+    memset(lv, 0, sizeof *lv);
+    lv->d.n[0] = nx; lv->d.n[1] = ny; lv->d.n[2] = nz;
+    lv->cplx = -1;
+    const double* hh[3] = {hx, hy, hz};
+    for (int a = 0; a < 3; ++a) {
+        const int n = lv->d.n[a];
+        std::vector<double> r(n);
+        for (int i = 0; i < n; ++i) r[i] = 1.0 / hh[a][i];
+        CK(cudaMalloc(&lv->h[a], sizeof(double) * n));
+        CK(cudaMalloc(&lv->rh[a], sizeof(double) * n));
+        CK(cudaMemcpyAsync(lv->h[a], hh[a], sizeof(double) * n, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(lv->rh[a], r.data(), sizeof(double) * n, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+    }
+    CK(cudaMalloc(&lv->scratch, sizeof(double) * residual_scratch_doubles(lv->d)));
+    CK(cudaMalloc(&lv->norm2, sizeof(double) * 2));
+    *out = lv;
+    return 0;
+}
+
+int emg3d_b200_level_drop_factors(emg3d_b200_level* lv) {
+    for (int a = 0; a < 3; ++a) {
+        if (lv->fac[a]) cudaFree(lv->fac[a]);
+        lv->fac[a] = nullptr;
+    }
+    return 0;
+}
+
+int emg3d_b200_level_destroy(emg3d_b200_level* lv) {
+    if (!lv) return 0;
+    emg3d_b200_level_drop_factors(lv);
+    for (int a = 0; a < 3; ++a) {
+        cudaFree(lv->h[a]);
+        cudaFree(lv->rh[a]);
+        cudaFree(lv->lo[a]);
+        cudaFree(lv->fr[a]);
+    }
+    for (int k = 0; k < 9; ++k) cudaFree(lv->w[k]);
+    cudaFree(lv->scratch);
+    cudaFree(lv->norm2);
+    delete lv;
+    return 0;
+}
+
+int emg3d_b200_level_set_model(emg3d_b200_level* lv, int cplx, const void* eta_x, const void* eta_y,
+                               const void* eta_z, const double* zeta) {
+    NEED_INIT();
+    emg3d_b200_level_drop_factors(lv);
+    lv->cplx = cplx ? 1 : 0;
+    lv->eta[0] = eta_x; lv->eta[1] = eta_y; lv->eta[2] = eta_z;
+    lv->zeta = zeta;
+    return 0;
+}
+
+int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes) {
+    if (ldir < 1 || ldir > 3) return fail_msg("level_factor_bytes: ldir must be 1, 2 or 3");
+    const size_t el = lv->cplx == 0 ? sizeof(double) : sizeof(cplx);
+    *nbytes = (size_t)line_factor_elems(lv->d, ldir - 1) * el;
+    return 0;
+}
+
+int emg3d_b200_level_link(emg3d_b200_level* c, const emg3d_b200_level* f, const int* cflag,
+                          const double* const* weights, const int* const* lo,
+                          const double* const* frac) {
+    NEED_INIT();
+    for (int a = 0; a < 3; ++a) {
+        const int expect = cflag[a] ? f->d.n[a] / 2 : f->d.n[a];
+        if (cflag[a] && (f->d.n[a] % 2)) return fail_msg("level_link: odd cell count cannot be coarsened");
+        if (c->d.n[a] != expect) return fail_msg("level_link: coarse shape does not match fine shape and cflag");
+    }
+    c->fine = f->d;
+    for (int a = 0; a < 3; ++a) {
+        c->cflag[a] = cflag[a] ? 1 : 0;
+        const int ncn = c->d.n[a] + 1, nfn = f->d.n[a] + 1;
+        for (int k = 0; k < 3; ++k) {
+            cudaFree(c->w[3 * a + k]);
+            c->w[3 * a + k] = nullptr;
+            if (cflag[a]) {
+                if (!weights || !weights[3 * a + k]) return fail_msg("level_link: missing restriction weights");
+                CK(cudaMalloc(&c->w[3 * a + k], sizeof(double) * ncn));
+                CK(cudaMemcpyAsync(c->w[3 * a + k], weights[3 * a + k], sizeof(double) * ncn,
+                                   cudaMemcpyHostToDevice, g_stream));
+            }
+        }
+        cudaFree(c->lo[a]);
+        cudaFree(c->fr[a]);
+        CK(cudaMalloc(&c->lo[a], sizeof(int) * nfn));
+        CK(cudaMalloc(&c->fr[a], sizeof(double) * nfn));
+        CK(cudaMemcpyAsync(c->lo[a], lo[a], sizeof(int) * nfn, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(c->fr[a], frac[a], sizeof(double) * nfn, cudaMemcpyHostToDevice, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    c->linked = 1;
+    return 0;
+}
+
+// ---- kernels -------------------------------------------------------------------
+#define NEED_MODEL(lv)                                                            \
+    do {                                                                          \
+        NEED_INIT();                                                              \
+        if ((lv)->cplx < 0) return fail_msg("level has no model (level_set_model)"); \
+    } while (0)
+
+static int residual_impl(emg3d_b200_level* lv, const void* s, const void* e, void* r, double* norm2_dev,
+                         int apply_only) {
+    NEED_MODEL(lv);
+    if (lv->cplx)
+        launch_residual<cplx>(model_of<cplx>(lv), (const cplx*)s, (const cplx*)e, (cplx*)r, norm2_dev,
+                              lv->scratch, apply_only, g_stream);
+    else
+        launch_residual<double>(model_of<double>(lv), (const double*)s, (const double*)e, (double*)r,
+                                norm2_dev, lv->scratch, apply_only, g_stream);
+    CK_LAUNCH("residual");
+    return 0;
+}
+
+int emg3d_b200_residual(emg3d_b200_level* lv, const void* s, const void* e, void* r, double* norm2_dev) {
+    return residual_impl(lv, s, e, r, norm2_dev, 0);
+}
+
+int emg3d_b200_apply(emg3d_b200_level* lv, const void* e, void* out) {
+    return residual_impl(lv, nullptr, e, out, nullptr, 1);
+}
+
+int emg3d_b200_amat_x(emg3d_b200_level* lv, void* r, const void* e) {
+    return emg3d_b200_residual(lv, r, e, r, nullptr);
+}
+
+int emg3d_b200_residual_norm(emg3d_b200_level* lv, const void* s, const void* e, void* r, double* norm_host) {
+    int rc = emg3d_b200_residual(lv, s, e, r, lv->norm2);
+    if (rc) return rc;
+    double v = 0.0;
+    CK(cudaMemcpyAsync(&v, lv->norm2, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *norm_host = sqrt(v);
+    return 0;
+}
+
+int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu, int ldir, int order) {
+    NEED_MODEL(lv);
+    if (ldir < 0 || ldir > 3) return fail_msg("gauss_seidel: ldir must be 0..3");
+    if (order != ORDER_LEX && order != ORDER_COLOR) return fail_msg("gauss_seidel: unknown order");
+    if (nu <= 0) return 0;
+    if (ldir == 0) {
+        if (lv->cplx)
+            launch_gs_point<cplx>(model_of<cplx>(lv), (cplx*)e, (const cplx*)s, nu, order, g_stream);
+        else
+            launch_gs_point<double>(model_of<double>(lv), (double*)e, (const double*)s, nu, order, g_stream);
+        CK_LAUNCH("gauss_seidel");
+        return 0;
+    }
+    const int dir = ldir - 1;
+    if (!lv->fac[dir]) {
+        size_t nbytes;
+        emg3d_b200_level_factor_bytes(lv, ldir, &nbytes);
+        if (nbytes == 0) return 0;
+        CK(cudaMalloc(&lv->fac[dir], nbytes));
+        if (lv->cplx)
+            launch_line_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac[dir], g_stream);
+        else
+            launch_line_factor<double>(model_of<double>(lv), dir, (double*)lv->fac[dir], g_stream);
+        CK_LAUNCH("line_factor");
+    }
+    if (lv->cplx)
+        launch_gs_line<cplx>(model_of<cplx>(lv), dir, (const cplx*)lv->fac[dir], (cplx*)e, (const cplx*)s,
+                             nu, order, g_stream);
+    else
+        launch_gs_line<double>(model_of<double>(lv), dir, (const double*)lv->fac[dir], (double*)e,
+                               (const double*)s, nu, order, g_stream);
+    CK_LAUNCH("gauss_seidel_line");
+    return 0;
+}
+
+int emg3d_b200_restrict(emg3d_b200_level* c, const void* r_fine, void* s_coarse) {
+    NEED_INIT();
+    if (!c->linked) return fail_msg("restrict: coarse level is not linked to a fine level");
+    if (c->cplx < 0) return fail_msg("restrict: coarse level has no model (dtype unknown)");
+    const double* wl[3] = {c->w[0], c->w[3], c->w[6]};
+    const double* w0[3] = {c->w[1], c->w[4], c->w[7]};
+    const double* wr[3] = {c->w[2], c->w[5], c->w[8]};
+    if (c->cplx)
+        launch_restrict<cplx>(c->fine, c->cflag, (const cplx*)r_fine, (cplx*)s_coarse, wl, w0, wr, g_stream);
+    else
+        launch_restrict<double>(c->fine, c->cflag, (const double*)r_fine, (double*)s_coarse, wl, w0, wr, g_stream);
+    CK_LAUNCH("restrict");
+    return 0;
+}
+
+int emg3d_b200_prolong(emg3d_b200_level* c, void* e_fine, const void* e_coarse) {
+    NEED_INIT();
+    if (!c->linked) return fail_msg("prolong: coarse level is not linked to a fine level");
+    if (c->cplx < 0) return fail_msg("prolong: coarse level has no model (dtype unknown)");
+    if (c->cplx)
+        launch_prolong<cplx>(c->fine, c->cflag, (cplx*)e_fine, (const cplx*)e_coarse, c->lo, c->fr, g_stream);
+    else
+        launch_prolong<double>(c->fine, c->cflag, (double*)e_fine, (const double*)e_coarse, c->lo, c->fr, g_stream);
+    CK_LAUNCH("prolong");
+    return 0;
+}
+
+int emg3d_b200_restrict_cells(emg3d_b200_level* c, int is_cplx, const void* p_fine, void* p_coarse) {
+    NEED_INIT();
+    if (!c->linked) return fail_msg("restrict_cells: coarse level is not linked to a fine level");
+    if (is_cplx)
+        launch_restrict_cells<cplx>(c->fine, c->cflag, (const cplx*)p_fine, (cplx*)p_coarse, g_stream);
+    else
+        launch_restrict_cells<double>(c->fine, c->cflag, (const double*)p_fine, (double*)p_coarse, g_stream);
+    CK_LAUNCH("restrict_cells");
+    return 0;
+}
+
+int emg3d_b200_pec_zero(emg3d_b200_level* lv, void* e) {
+    NEED_MODEL(lv);
+    if (lv->cplx) launch_pec_zero<cplx>(lv->d, (cplx*)e, g_stream);
+    else launch_pec_zero<double>(lv->d, (double*)e, g_stream);
+    CK_LAUNCH("pec_zero");
+    return 0;
+}
+
+// ---- vector helpers --------------------------------------------------------------
+int emg3d_b200_dot(int is_cplx, long long n, const void* x, const void* y, int conj_x, double* dot2_dev) {
+    NEED_INIT();
+    if (is_cplx) launch_dot<cplx>(n, (const cplx*)x, (const cplx*)y, conj_x, dot2_dev, g_dot_scratch, g_stream);
+    else launch_dot<double>(n, (const double*)x, (const double*)y, 0, dot2_dev, g_dot_scratch, g_stream);
+    CK_LAUNCH("dot");
+    return 0;
+}
+
+int emg3d_b200_dot_host(int is_cplx, long long n, const void* x, const void* y, int conj_x, double* dot2_host) {
+    int rc = emg3d_b200_dot(is_cplx, n, x, y, conj_x, g_dot_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dot2_host, g_dot_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (!is_cplx) dot2_host[1] = 0.0;
+    return 0;
+}
+
+int emg3d_b200_axpby(int is_cplx, long long n, double a_re, double a_im, const void* x, double b_re,
+                     double b_im, void* y) {
+    NEED_INIT();
+    if (is_cplx) launch_axpby<cplx>(n, make_c(a_re, a_im), (const cplx*)x, make_c(b_re, b_im), (cplx*)y, g_stream);
+    else launch_axpby<double>(n, a_re, (const double*)x, b_re, (double*)y, g_stream);
+    CK_LAUNCH("axpby");
+    return 0;
+}
+
+// ---- host-array entry points -------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 16) == cudaSuccess ? 0 : -1; }
+};
+
+struct HostCall {
+    emg3d_b200_level* lv = nullptr;
+    DevBuf eta[3], zeta;
+    ~HostCall() { emg3d_b200_level_destroy(lv); }
+    int setup(int is_cplx, int nx, int ny, int nz, const void* ex_, const void* ey_, const void* ez_,
+              const double* zt, const double* hx, const double* hy, const double* hz) {
+        int rc = emg3d_b200_level_create(&lv, nx, ny, nz, hx, hy, hz);
+        if (rc) return rc;
+        const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+        const size_t nc = (size_t)nx * ny * nz;
+        const void* src[3] = {ex_, ey_, ez_};
+        const void* dev[3];
+        for (int a = 0; a < 3; ++a) {
+            int same = -1;
+            for (int b = 0; b < a; ++b) if (src[b] == src[a]) same = b;
+            if (same >= 0) { dev[a] = dev[same]; continue; }
+            if (eta[a].alloc(nc * el)) return fail_msg("host call: out of device memory");
+            rc = emg3d_b200_h2d(eta[a].p, src[a], nc * el);
+            if (rc) return rc;
+            dev[a] = eta[a].p;
+        }
+        if (zeta.alloc(nc * sizeof(double))) return fail_msg("host call: out of device memory");
+        rc = emg3d_b200_h2d(zeta.p, zt, nc * sizeof(double));
+        if (rc) return rc;
+        return emg3d_b200_level_set_model(lv, is_cplx, dev[0], dev[1], dev[2], (const double*)zeta.p);
+    }
+};
+
+int field_io(bool up, int is_cplx, const Dims& d, void* dev, void* x, void* y, void* z) {
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    void* host[3] = {x, y, z};
+    for (int c = 0; c < 3; ++c) {
+        char* dp = (char*)dev + comp_offset(d, c) * el;
+        const size_t nb = comp_size(d, c) * el;
+        int rc = up ? emg3d_b200_h2d(dp, host[c], nb) : emg3d_b200_d2h(host[c], dp, nb);
+        if (rc) return rc;
+    }
+    return 0;
+}
+}  // namespace
+
+int emg3d_b200_host_amat_x(int is_cplx, int nx, int ny, int nz, void* rx, void* ry, void* rz, const void* ex,
+                           const void* ey, const void* ez, const void* eta_x, const void* eta_y,
+                           const void* eta_z, const double* zeta, const double* hx, const double* hy,
+                           const double* hz) {
+    NEED_INIT();
+    HostCall hc;
+    int rc = hc.setup(is_cplx, nx, ny, nz, eta_x, eta_y, eta_z, zeta, hx, hy, hz);
+    if (rc) return rc;
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    const size_t nb = (size_t)n_edges(hc.lv->d) * el;
+    DevBuf r, e;
+    if (r.alloc(nb) || e.alloc(nb)) return fail_msg("host_amat_x: out of device memory");
+    if ((rc = field_io(true, is_cplx, hc.lv->d, r.p, rx, ry, rz))) return rc;
+    if ((rc = field_io(true, is_cplx, hc.lv->d, e.p, (void*)ex, (void*)ey, (void*)ez))) return rc;
+    if ((rc = emg3d_b200_amat_x(hc.lv, r.p, e.p))) return rc;
+    return field_io(false, is_cplx, hc.lv->d, r.p, rx, ry, rz);
+}
+
+int emg3d_b200_host_solve(int is_cplx, int n, void* amat, void* bvec) {
+    NEED_INIT();
+    if (n < 1) return fail_msg("host_solve: n must be positive");
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    DevBuf a, b;
+    if (a.alloc(6 * (size_t)n * el) || b.alloc((size_t)n * el)) return fail_msg("host_solve: out of device memory");
+    int rc;
+    if ((rc = emg3d_b200_h2d(a.p, amat, 6 * (size_t)n * el))) return rc;
+    if ((rc = emg3d_b200_h2d(b.p, bvec, (size_t)n * el))) return rc;
+    if (is_cplx) launch_band_solve<cplx>(n, (cplx*)a.p, (cplx*)b.p, g_stream);
+    else launch_band_solve<double>(n, (double*)a.p, (double*)b.p, g_stream);
+    CK_LAUNCH("band_solve");
+    if ((rc = emg3d_b200_d2h(amat, a.p, 6 * (size_t)n * el))) return rc;
+    return emg3d_b200_d2h(bvec, b.p, (size_t)n * el);
+}
+
+int emg3d_b200_host_gauss_seidel(int is_cplx, int ldir, int order, int nx, int ny, int nz, void* ex, void* ey,
+                                 void* ez, const void* sx, const void* sy, const void* sz,
+                                 const void* eta_x, const void* eta_y, const void* eta_z,
+                                 const double* zeta, const double* hx, const double* hy, const double* hz,
+                                 int nu) {
+    NEED_INIT();
+    HostCall hc;
+    int rc = hc.setup(is_cplx, nx, ny, nz, eta_x, eta_y, eta_z, zeta, hx, hy, hz);
+    if (rc) return rc;
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    const size_t nb = (size_t)n_edges(hc.lv->d) * el;
+    DevBuf s, e;
+    if (s.alloc(nb) || e.alloc(nb)) return fail_msg("host_gauss_seidel: out of device memory");
+    if ((rc = field_io(true, is_cplx, hc.lv->d, e.p, ex, ey, ez))) return rc;
+    if ((rc = field_io(true, is_cplx, hc.lv->d, s.p, (void*)sx, (void*)sy, (void*)sz))) return rc;
+    if ((rc = emg3d_b200_gauss_seidel(hc.lv, e.p, s.p, nu, ldir, order))) return rc;
+    return field_io(false, is_cplx, hc.lv->d, e.p, ex, ey, ez);
+}
+
+}  // extern "C"

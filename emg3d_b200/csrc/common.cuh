@@ -1,0 +1,114 @@
+// emg3d_b200 -- shared device helpers for the multigrid hot path (sm_100a).
+//
+// Data layout in HBM (identical to the reference's host layout, so transfers
+// are plain copies): a field is one array [fx | fy | fz], fx (nx, ny+1, nz+1),
+// fy (nx+1, ny, nz+1), fz (nx+1, ny+1, nz), all x-fastest; eta_x/y/z and zeta
+// are (nx, ny, nz) x-fastest.  Fields and eta are complex128 (16-byte aligned
+// re,im pairs -> one LDG.128 per value) in the frequency domain and float64 in
+// the Laplace domain; zeta and the widths are always float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace emg {
+
+// ---- scalar types ---------------------------------------------------------
+struct __align__(16) cplx {
+    double re, im;
+};
+
+__host__ __device__ __forceinline__ cplx make_c(double re, double im) { cplx r; r.re = re; r.im = im; return r; }
+__host__ __device__ __forceinline__ cplx operator+(cplx a, cplx b) { return make_c(a.re + b.re, a.im + b.im); }
+__host__ __device__ __forceinline__ cplx operator-(cplx a, cplx b) { return make_c(a.re - b.re, a.im - b.im); }
+__host__ __device__ __forceinline__ cplx operator-(cplx a) { return make_c(-a.re, -a.im); }
+__host__ __device__ __forceinline__ cplx operator*(cplx a, cplx b) {
+    return make_c(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+__host__ __device__ __forceinline__ cplx operator*(double a, cplx b) { return make_c(a * b.re, a * b.im); }
+__host__ __device__ __forceinline__ cplx operator*(cplx b, double a) { return make_c(a * b.re, a * b.im); }
+__host__ __device__ __forceinline__ cplx& operator+=(cplx& a, cplx b) { a.re += b.re; a.im += b.im; return a; }
+__host__ __device__ __forceinline__ cplx& operator-=(cplx& a, cplx b) { a.re -= b.re; a.im -= b.im; return a; }
+__host__ __device__ __forceinline__ cplx& operator*=(cplx& a, cplx b) { a = a * b; return a; }
+__host__ __device__ __forceinline__ cplx& operator*=(cplx& a, double b) { a.re *= b; a.im *= b; return a; }
+
+// reciprocal of a pivot
+__host__ __device__ __forceinline__ double rcp(double a) { return 1.0 / a; }
+__host__ __device__ __forceinline__ cplx rcp(cplx a) {
+    double d = 1.0 / (a.re * a.re + a.im * a.im);
+    return make_c(a.re * d, -a.im * d);
+}
+__host__ __device__ __forceinline__ double abs2(double a) { return a * a; }
+__host__ __device__ __forceinline__ double abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+__host__ __device__ __forceinline__ double conj_(double a) { return a; }
+__host__ __device__ __forceinline__ cplx conj_(cplx a) { return make_c(a.re, -a.im); }
+
+__host__ __device__ __forceinline__ void add_real(double& a, double v) { a += v; }
+__host__ __device__ __forceinline__ void add_real(cplx& a, double v) { a.re += v; }
+
+template <typename T> __host__ __device__ __forceinline__ T zero_();
+template <> __host__ __device__ __forceinline__ double zero_<double>() { return 0.0; }
+template <> __host__ __device__ __forceinline__ cplx zero_<cplx>() { return make_c(0.0, 0.0); }
+
+// read-only (non-coherent) loads
+__device__ __forceinline__ double ldg(const double* p) { return __ldg(p); }
+__device__ __forceinline__ int ldg(const int* p) { return __ldg(p); }
+__device__ __forceinline__ cplx ldg(const cplx* p) {
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return make_c(v.x, v.y);
+}
+
+// ---- grid / model description passed by value to kernels -------------------
+struct Dims {
+    int n[3];          // cells per axis
+};
+
+template <typename T>
+struct Model {
+    Dims d;
+    const T* eta[3];       // eta_x, eta_y, eta_z (may alias)
+    const double* zeta;
+    const double* h[3];    // widths
+    const double* rh[3];   // 1 / widths
+};
+
+// F-order extents of the three field components
+__host__ __device__ __forceinline__ int64_t comp_d0(const Dims& d, int c) { return d.n[0] + (c != 0); }
+__host__ __device__ __forceinline__ int64_t comp_d1(const Dims& d, int c) { return d.n[1] + (c != 1); }
+__host__ __device__ __forceinline__ int64_t comp_d2(const Dims& d, int c) { return d.n[2] + (c != 2); }
+__host__ __device__ __forceinline__ int64_t comp_size(const Dims& d, int c) {
+    return comp_d0(d, c) * comp_d1(d, c) * comp_d2(d, c);
+}
+__host__ __device__ __forceinline__ int64_t comp_offset(const Dims& d, int c) {
+    int64_t o = 0;
+    for (int k = 0; k < c; ++k) o += comp_size(d, k);
+    return o;
+}
+__host__ __device__ __forceinline__ int64_t n_edges(const Dims& d) { return comp_offset(d, 3); }
+__host__ __device__ __forceinline__ int64_t n_cells(const Dims& d) {
+    return (int64_t)d.n[0] * d.n[1] * d.n[2];
+}
+
+// Strides of component c and of the cell arrays, and pointers to components.
+template <typename T>
+struct FieldView {
+    T* p[3];
+    int64_t s1[3], s2[3];   // stride of index 1 and 2 (stride of index 0 is 1)
+    __host__ __device__ FieldView() {}
+    __host__ __device__ FieldView(T* base, const Dims& d) {
+        int64_t o = 0;
+        for (int c = 0; c < 3; ++c) {
+            p[c] = base ? base + o : nullptr;
+            s1[c] = comp_d0(d, c);
+            s2[c] = comp_d0(d, c) * comp_d1(d, c);
+            o += comp_size(d, c);
+        }
+    }
+    __host__ __device__ __forceinline__ int64_t idx(int c, int i, int j, int k) const {
+        return i + s1[c] * j + s2[c] * k;
+    }
+    __host__ __device__ __forceinline__ int64_t idx(int c, const int* q) const {
+        return q[0] + s1[c] * q[1] + s2[c] * q[2];
+    }
+};
+
+}  // namespace emg

@@ -1,0 +1,269 @@
+// Point-block Gauss-Seidel smoother: for every interior node, solve
+// simultaneously for the six edges meeting at it (what emg3d/core.py:210-503
+// `gauss_seidel` computes).
+//
+// Local system of node (ix, iy, iz), unknown order as in the reference
+// [ex(ix-1), ex(ix), ey(iy-1), ey(iy), ez(iz-1), ez(iz)]:
+//   - the 12 faces containing the node each hold two local and two outer
+//     edges; a face in the plane of axes (p, q) at cells (cp, cq) has the curl
+//     stencil  e_p(q-node cq): +1/h_q, e_p(cq+1): -1/h_q,
+//              e_q(p-node cp+1): +1/h_p, e_q(cp): -1/h_p
+//     (only products of stencil entries matter, so one global sign is free);
+//   - matrix  += 1/2 M_f c_loc c_loc^T,  rhs -= 1/2 M_f c_loc (c_out . e_out);
+//   - diagonal -= 1/4 (sum of eta over the 4 cells around the edge); rhs += s.
+// The 6x6 complex-symmetric system is solved by an unrolled LDL^T in registers.
+//
+// Orderings: `lex` reproduces the reference's lexicographic
+// sweep exactly by running hyperplanes t = ix + 2 iy + 3 iz one after the
+// other (nodes on one hyperplane never share or neighbour an edge, and every
+// dependency of the sequential sweep points to a smaller t); `color` runs the
+// 8 parity classes (ix&1, iy&1, iz&1), which are conflict-free as well.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace emg {
+
+template <typename T>
+__device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T>& E,
+                                            const FieldView<const T>& S, int ix, int iy, int iz) {
+    const int nd[3] = {ix, iy, iz};
+    const int64_t cs[3] = {1, m.d.n[0], (int64_t)m.d.n[0] * m.d.n[1]};
+    const int64_t c0 = (ix - 1) + cs[1] * (iy - 1) + cs[2] * (iz - 1);  // low corner cell
+
+    // reciprocal widths of the two cells along each axis: rh[a][0] = 1/h_a[nd-1]
+    double rh[3][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rh[a][0] = ldg(m.rh[a] + nd[a] - 1);
+        rh[a][1] = ldg(m.rh[a] + nd[a]);
+    }
+    // zeta of the 8 cells around the node, z[i][j][k] <-> cell (ix-1+i, iy-1+j, iz-1+k)
+    double z[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) z[i][j][k] = ldg(m.zeta + c0 + i + cs[1] * j + cs[2] * k);
+
+    // packed lower triangle, a[r][c], r >= c
+    T a[6][6];
+    T b[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = zero_<T>();
+    }
+
+    // diagonal: -1/4 sum of eta over the four cells around each local edge; rhs: source
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int u = (c + 1) % 3, v = (c + 2) % 3;
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            const int64_t base = c0 + cs[c] * sg;
+            T st = ldg(m.eta[c] + base) + ldg(m.eta[c] + base + cs[u]) +
+                   ldg(m.eta[c] + base + cs[v]) + ldg(m.eta[c] + base + cs[u] + cs[v]);
+            a[2 * c + sg][2 * c + sg] = -0.25 * st;
+            int q[3] = {ix, iy, iz};
+            q[c] += sg - 1;
+            b[2 * c + sg] = ldg(S.p[c] + S.idx(c, q));
+        }
+    }
+
+    // the three coordinate planes (p, q), four quadrants each
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const int p = pl == 2 ? 1 : 0, q = pl == 0 ? 1 : 2, w = 3 - p - q;
+#pragma unroll
+        for (int sp = 0; sp < 2; ++sp) {
+#pragma unroll
+            for (int sq = 0; sq < 2; ++sq) {
+                // cells of this face: p-index 1-sp, q-index 1-sq, both w-indices
+                int i0[3], i1[3];
+                i0[p] = i1[p] = 1 - sp;
+                i0[q] = i1[q] = 1 - sq;
+                i0[w] = 0;
+                i1[w] = 1;
+                const double g = 0.5 * (z[i0[0]][i0[1]][i0[2]] + z[i1[0]][i1[1]][i1[2]]);
+                const double rp = rh[p][1 - sp], rq = rh[q][1 - sq];
+                const double al_p = sq ? -rq : rq;   // entry of the local p-edge
+                const double al_q = sp ? rp : -rp;   // entry of the local q-edge
+                // outer p-edge: same p-cell, q-node moved away from the node
+                int qo[3] = {ix, iy, iz};
+                qo[p] -= sp;
+                qo[q] += sq ? -1 : 1;
+                const T ep = E.p[p][E.idx(p, qo)];
+                int ro[3] = {ix, iy, iz};
+                ro[q] -= sq;
+                ro[p] += sp ? -1 : 1;
+                const T eq = E.p[q][E.idx(q, ro)];
+                const T out = al_p * ep + al_q * eq;   // = -(c_out . e_out)
+                const int lp = 2 * p + (1 - sp), lq = 2 * q + (1 - sq);
+                add_real(a[lp][lp], g * al_p * al_p);
+                add_real(a[lq][lq], g * al_q * al_q);
+                add_real(a[lq][lp], g * al_p * al_q);   // lq > lp always
+                b[lp] += (g * al_p) * out;
+                b[lq] += (g * al_q) * out;
+            }
+        }
+    }
+
+    // LDL^T without pivoting, unknown order 0..5 (emg3d/core.py:1481-1616), then
+    // forward substitution, diagonal scaling, backward substitution.
+    T dinv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        T v[6];
+        T dj = a[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            v[k] = a[j][k] * a[k][k];          // L(j,k) D(k); a[k][k] holds D(k)
+            dj -= a[j][k] * v[k];
+        }
+        a[j][j] = dj;
+        const T r = rcp(dj);
+        dinv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            T t = a[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t -= a[i][k] * v[k];
+            a[i][j] = t * r;
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < 6; ++j) {
+#pragma unroll
+        for (int k = 0; k < j; ++k) b[j] -= a[j][k] * b[k];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) b[j] = b[j] * dinv[j];
+#pragma unroll
+    for (int j = 4; j >= 0; --j) {
+#pragma unroll
+        for (int k = j + 1; k < 6; ++k) b[j] -= a[k][j] * b[k];
+    }
+
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            int q[3] = {ix, iy, iz};
+            q[c] += sg - 1;
+            E.p[c][E.idx(c, q)] = b[2 * c + sg];
+        }
+    }
+}
+
+
+// ---- schedules ---------------------------------------------------------------
+
+// one parity class: ix = fx + 2 i, iy = fy + 2 j, iz = fz + 2 k
+template <typename T>
+__global__ void __launch_bounds__(128)
+gs_point_color_kernel(Model<T> m, T* e, const T* s, int fx, int fy, int fz, int cx, int cy, int cz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i >= cx || j >= cy || k >= cz) return;
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    node_update<T>(m, E, S, fx + 2 * i, fy + 2 * j, fz + 2 * k);
+}
+
+// one hyperplane ix + 2 iy + 3 iz = t of the lexicographic sweep
+template <typename T>
+__global__ void __launch_bounds__(128)
+gs_point_front_kernel(Model<T> m, T* e, const T* s, int t) {
+    const int iy = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int iz = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (iy >= m.d.n[1] || iz >= m.d.n[2]) return;
+    const int ix = t - 2 * iy - 3 * iz;
+    if (ix < 1 || ix >= m.d.n[0]) return;
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    node_update<T>(m, E, S, ix, iy, iz);
+}
+
+// whole smoothing call (all sweeps, all parity classes or all hyperplanes) in
+// one block, for grids small enough that launch latency would dominate.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gs_point_small_kernel(Model<T> m, T* e, const T* s, int nu, int order) {
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    const int nx = m.d.n[0], ny = m.d.n[1], nz = m.d.n[2];
+    const int nint = (nx - 1) * (ny - 1) * (nz - 1);
+    bool back = false;
+    for (int sw = 0; sw < nu; ++sw) {
+        back = !back;                       // first sweep runs descending (core.py:301,311)
+        if (order == ORDER_LEX) {
+            const int tmin = 6, tmax = (nx - 1) + 2 * (ny - 1) + 3 * (nz - 1);
+            const int nyz = (ny - 1) * (nz - 1);
+            for (int tt = tmin; tt <= tmax; ++tt) {
+                const int t = back ? tmax + tmin - tt : tt;
+                for (int q = threadIdx.x; q < nyz; q += blockDim.x) {
+                    const int iy = 1 + q % (ny - 1), iz = 1 + q / (ny - 1);
+                    const int ix = t - 2 * iy - 3 * iz;
+                    if (ix >= 1 && ix < nx) node_update<T>(m, E, S, ix, iy, iz);
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = back ? 7 - cc : cc;
+                const int px = c & 1, py = (c >> 1) & 1, pz = (c >> 2) & 1;
+                for (int q = threadIdx.x; q < nint; q += blockDim.x) {
+                    const int ix = 1 + q % (nx - 1);
+                    const int iy = 1 + (q / (nx - 1)) % (ny - 1);
+                    const int iz = 1 + q / ((nx - 1) * (ny - 1));
+                    if (((ix - 1) & 1) == px && ((iy - 1) & 1) == py && ((iz - 1) & 1) == pz)
+                        node_update<T>(m, E, S, ix, iy, iz);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+template <typename T>
+void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cudaStream_t st) {
+    const int nx = m.d.n[0], ny = m.d.n[1], nz = m.d.n[2];
+    if (nx < 2 || ny < 2 || nz < 2) return;
+    const int64_t nint = (int64_t)(nx - 1) * (ny - 1) * (nz - 1);
+    if (nint <= SMALL_GRID_NODES) {
+        int threads = 32;
+        while (threads < 256 && threads < nint) threads <<= 1;
+        ++g_launch_count; gs_point_small_kernel<T><<<1, threads, 0, st>>>(m, e, s, nu, order);
+        return;
+    }
+    bool back = false;
+    for (int sw = 0; sw < nu; ++sw) {
+        back = !back;
+        if (order == ORDER_LEX) {
+            const int tmin = 6, tmax = (nx - 1) + 2 * (ny - 1) + 3 * (nz - 1);
+            dim3 b(32, 4);
+            dim3 g((ny - 1 + b.x - 1) / b.x, (nz - 1 + b.y - 1) / b.y);
+            for (int tt = tmin; tt <= tmax; ++tt) {
+                const int t = back ? tmax + tmin - tt : tt;
+                ++g_launch_count; gs_point_front_kernel<T><<<g, b, 0, st>>>(m, e, s, t);
+            }
+        } else {
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = back ? 7 - cc : cc;
+                const int fx = 1 + (c & 1), fy = 1 + ((c >> 1) & 1), fz = 1 + ((c >> 2) & 1);
+                const int cx = (nx - fx + 1) / 2, cy = (ny - fy + 1) / 2, cz = (nz - fz + 1) / 2;
+                if (cx <= 0 || cy <= 0 || cz <= 0) continue;
+                dim3 b(32, 4, 1);
+                dim3 g((cx + b.x - 1) / b.x, (cy + b.y - 1) / b.y, cz);
+                ++g_launch_count; gs_point_color_kernel<T><<<g, b, 0, st>>>(m, e, s, fx, fy, fz, cx, cy, cz);
+            }
+        }
+    }
+}
+
+template void launch_gs_point<double>(const Model<double>&, double*, const double*, int, int, cudaStream_t);
+template void launch_gs_point<cplx>(const Model<cplx>&, cplx*, const cplx*, int, int, cudaStream_t);
+
+}  // namespace emg

@@ -1,0 +1,57 @@
+// Internal launch interface between the C-ABI (api.cu) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace emg {
+
+enum { ORDER_LEX = 0, ORDER_COLOR = 1 };
+
+extern long long g_launch_count;   // kernel launches issued (host-side counter)
+
+// grids with at most this many interior nodes (or lines) are smoothed by one
+// thread block in a single launch
+constexpr int64_t SMALL_GRID_NODES = 4096;
+
+// r = s - A e (r may be null, r may alias s), or r = A e when apply_only (s unused);
+// optional ||r||^2 into norm2_out[0]
+template <typename T>
+void launch_residual(const Model<T>& m, const T* s, const T* e, T* r, double* norm2_out,
+                     double* scratch, int apply_only, cudaStream_t st);
+int64_t residual_scratch_doubles(const Dims& d);
+
+template <typename T>
+void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cudaStream_t st);
+
+// line smoothers: factor once per (level, direction), then sweep
+int64_t line_factor_elems(const Dims& d, int dir);     // number of T elements
+template <typename T>
+void launch_line_factor(const Model<T>& m, int dir, T* fac, cudaStream_t st);
+template <typename T>
+void launch_gs_line(const Model<T>& m, int dir, const T* fac, T* e, const T* s, int nu, int order,
+                    cudaStream_t st);
+
+// transfer operators; cflag[a] = 1 if axis a is coarsened
+template <typename T>
+void launch_restrict(const Dims& fine, const int* cflag, const T* r, T* cr, const double* const* wl,
+                     const double* const* w0, const double* const* wr, cudaStream_t st);
+template <typename T>
+void launch_prolong(const Dims& fine, const int* cflag, T* e, const T* ce, const int* const* lo,
+                    const double* const* frac, cudaStream_t st);
+template <typename T>
+void launch_restrict_cells(const Dims& fine, const int* cflag, const T* p, T* cp, cudaStream_t st);
+
+// banded LDL^T solve of one system (interface of core.solve)
+template <typename T>
+void launch_band_solve(int n, T* a, T* b, cudaStream_t st);
+
+// vector helpers
+template <typename T>
+void launch_pec_zero(const Dims& d, T* e, cudaStream_t st);
+template <typename T>
+void launch_dot(int64_t n, const T* x, const T* y, int conj_x, double* out2, double* scratch,
+                cudaStream_t st);
+int64_t dot_scratch_doubles(int64_t n);
+template <typename T>
+void launch_axpby(int64_t n, T a, const T* x, T b, T* y, cudaStream_t st);   // y = a x + b y
+
+}  // namespace emg

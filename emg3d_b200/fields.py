@@ -1,0 +1,206 @@
+"""Field container and source-field assembly as consumed by the multigrid path.
+
+Layout contract of the reference (emg3d/fields.py:40-301): one contiguous 1-D
+array ``field = [fx | fy | fz]``; ``fx`` has shape ``(nx, ny+1, nz+1)``, ``fy``
+``(nx+1, ny, nz+1)``, ``fz`` ``(nx+1, ny+1, nz)``, all Fortran-ordered (x
+fastest); ``complex128`` for ``frequency > 0``, ``float64`` for
+``frequency < 0`` (Laplace domain, ``s = -frequency``).  The same bytes are what
+the CUDA library works on, so host<->device transfers are plain copies.
+"""
+import numpy as np
+from scipy.constants import mu_0
+
+__all__ = ['Field', 'get_source_field']
+
+
+class Field:
+    """x-, y-, z-directed edge fields in one array (emg3d/fields.py:40-136)."""
+
+    def __init__(self, grid, data=None, frequency=None, dtype=None, electric=True):
+        if frequency is not None:
+            if frequency > 0:
+                dtype = np.complex128
+            elif frequency < 0:
+                dtype = np.float64
+            else:
+                raise ValueError(
+                    "`frequency` must be f>0 (frequency domain) or f<0 "
+                    f"(Laplace domain). Provided: {frequency} Hz.")
+        elif data is not None:
+            dtype = np.asarray(data).dtype
+        elif dtype is None:
+            dtype = np.complex128
+        if not electric:
+            raise NotImplementedError("only electric (edge) fields are in scope")
+        self.grid = grid
+        self._frequency = frequency
+        self.electric = True
+        n = grid.n_edges
+        if data is None:
+            self._field = np.zeros(n, dtype=dtype)
+        else:
+            self._field = np.ascontiguousarray(np.asarray(data, dtype=dtype).ravel('F'))
+            if self._field.size != n:
+                raise ValueError(f"data must have {n} entries, got {self._field.size}")
+
+    def __repr__(self):
+        g = self.grid
+        return (f"Field: electric; {g.shape_cells[0]} x {g.shape_cells[1]} x "
+                f"{g.shape_cells[2]}; {self.field.size:,}")
+
+    def __eq__(self, other):
+        return (type(self).__name__ == type(other).__name__ and
+                self.grid == other.grid and
+                self._frequency == other._frequency and
+                np.allclose(self._field, other._field, atol=0, rtol=1e-10))
+
+    def copy(self):
+        return Field(self.grid, self._field.copy(), self._frequency)
+
+    @property
+    def field(self):
+        return self._field
+
+    @field.setter
+    def field(self, value):
+        self._field[:] = value
+
+    def _view(self, comp):
+        g = self.grid
+        n = (g.n_edges_x, g.n_edges_y, g.n_edges_z)
+        shp = (g.shape_edges_x, g.shape_edges_y, g.shape_edges_z)[comp]
+        i0 = sum(n[:comp])
+        return self._field[i0:i0 + n[comp]].reshape(shp, order='F')
+
+    @property
+    def fx(self):
+        return self._view(0)
+
+    @fx.setter
+    def fx(self, v):
+        self._view(0)[...] = v
+
+    @property
+    def fy(self):
+        return self._view(1)
+
+    @fy.setter
+    def fy(self, v):
+        self._view(1)[...] = v
+
+    @property
+    def fz(self):
+        return self._view(2)
+
+    @fz.setter
+    def fz(self, v):
+        self._view(2)[...] = v
+
+    @property
+    def frequency(self):
+        return None if self._frequency is None else abs(self._frequency)
+
+    @property
+    def sval(self):
+        """Laplace parameter: 2 i pi f (f > 0) or -f (f < 0)."""
+        if self._frequency is None:
+            return None
+        if self._frequency < 0:
+            return np.array(-self._frequency)
+        return np.array(2j * np.pi * self._frequency)
+
+    @property
+    def smu0(self):
+        s = self.sval
+        return None if s is None else s * mu_0
+
+
+def _rotation(azimuth, elevation):
+    a, e = np.deg2rad(azimuth), np.deg2rad(elevation)
+    return np.array([np.cos(a) * np.cos(e), np.sin(a) * np.cos(e), np.sin(e)])
+
+
+def _segment_vector(grid, p0, p1):
+    """Distribute a straight current segment p0 -> p1 onto the edges.
+
+    Per cell crossed: clip the segment to the cell, take the midpoint of the
+    clipped piece and spread (piece length / total length) bilinearly onto the
+    four parallel edges of each direction; finally scale each component by the
+    segment's extent in that direction (emg3d/fields.py:792-938).
+    """
+    nodes = [np.round(grid.nodes_x, 9), np.round(grid.nodes_y, 9),
+             np.round(grid.nodes_z, 9)]
+    p0, p1 = np.round(np.asarray(p0, float), 9), np.round(np.asarray(p1, float), 9)
+    for a in range(3):
+        if min(p0[a], p1[a]) < nodes[a][0] or max(p0[a], p1[a]) > nodes[a][-1]:
+            raise ValueError(f"Provided source outside grid: {np.r_[[p0, p1]]}.")
+    d = p1 - p0
+    length = np.linalg.norm(d)
+    if length < 1e-15:
+        raise ValueError(f"Provided finite dipole has no length: {np.r_[[p0, p1]]}.")
+    out = Field(grid, dtype=float)
+    comps = (out.fx, out.fy, out.fz)
+    # cell index ranges touched by the segment
+    rng = []
+    for a in range(3):
+        lo, hi = min(p0[a], p1[a]), max(p0[a], p1[a])
+        i0 = max(0, int(np.searchsorted(nodes[a], lo, side='right')) - 1)
+        i1 = max(0, int(np.searchsorted(nodes[a], hi, side='right')) - 1)
+        rng.append(range(i0, min(i1 + 1, nodes[a].size - 1)))
+    for iz in rng[2]:
+        for iy in rng[1]:
+            for ix in rng[0]:
+                idx = (ix, iy, iz)
+                t0, t1 = 0.0, 1.0          # parameter interval inside the cell
+                for a in range(3):
+                    if d[a] != 0:
+                        ta = (nodes[a][idx[a]] - p0[a]) / d[a]
+                        tb = (nodes[a][idx[a] + 1] - p0[a]) / d[a]
+                        t0, t1 = max(t0, min(ta, tb)), min(t1, max(ta, tb))
+                if t1 - t0 <= 0:
+                    continue
+                mid = p0 + 0.5 * (t0 + t1) * d
+                frac = np.linalg.norm((t1 - t0) * d) / length
+                r = [(mid[a] - nodes[a][idx[a]]) / grid.h[a][idx[a]] for a in range(3)]
+                if min(min(r), min(1 - q for q in r)) < 0:
+                    continue
+                for c in range(3):
+                    u, v = (c + 1) % 3, (c + 2) % 3
+                    for du in (0, 1):
+                        for dv in (0, 1):
+                            j = list(idx)
+                            j[u] += du
+                            j[v] += dv
+                            wu = r[u] if du else 1 - r[u]
+                            wv = r[v] if dv else 1 - r[v]
+                            comps[c][tuple(j)] += wu * wv * frac
+    for c in range(3):
+        comps[c][...] *= d[c]
+    return out
+
+
+def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
+    """Source term ``-s mu_0 J_s`` of an electric dipole on the edges.
+
+    Mirrors the electric-dipole branch of emg3d.fields.get_source_field
+    (emg3d/fields.py:386-519).  ``source`` is ``(x, y, z, azimuth, elevation)``
+    (a dipole of ``length`` metres centred there; emg3d/electrodes.py:752-755),
+    ``(x0, x1, y0, y1, z0, z1)``, or an array of shape ``(n, 3)`` of wire
+    points.  Magnetic sources and point sources are outside the hot path.
+    """
+    src = np.asarray(source, dtype=float)
+    if src.size == 5:
+        half = _rotation(src[3], src[4]) * length / 2
+        pts = np.array([src[:3] - half, src[:3] + half])
+    elif src.size == 6 and src.ndim == 1:
+        pts = np.array([[src[0], src[2], src[4]], [src[1], src[3], src[5]]])
+    else:
+        pts = src.reshape(-1, 3)
+    vec = np.zeros(grid.n_edges)
+    for a, b in zip(pts[:-1], pts[1:]):
+        vec += _segment_vector(grid, a, b).field
+    sfield = Field(grid, data=vec, frequency=frequency)
+    sfield.field *= strength
+    if frequency is not None:
+        sfield.field *= -sfield.smu0
+    return sfield

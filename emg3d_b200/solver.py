@@ -1,0 +1,1118 @@
+"""Multigrid solver driver: the public API of ``emg3d.solver`` on a B200.
+
+Same functions, arguments, return values, messages and exit codes as the
+reference (``emg3d/solver.py``): :func:`solve`, :func:`solve_source`,
+:func:`multigrid`, :func:`krylov`, :func:`smoothing`, :func:`restriction`,
+:func:`prolongation`, :func:`residual`, :class:`MGParameters`,
+:class:`RegularGridProlongator`.  What differs is where the work happens:
+
+* every field, coefficient array and scratch vector lives in HBM for the whole
+  solve; only scalars (norms, dot products) and the final field cross PCIe;
+* the grid hierarchy (coarse grids, summed coefficients, restriction weights,
+  interpolation tables, line factorisations) is built once per solve and cached,
+  where the reference rebuilds it at every visit (solver.py:888-931, 975-1007);
+* BiCGSTAB runs on the device with the recurrence of SciPy's implementation;
+* ``order='color'`` (default) smooths in multicolour order, ``order='lex'``
+  reproduces the reference's lexicographic Gauss-Seidel sweeps.
+
+The public functions also accept the reference's host containers (anything with
+the attributes of ``emg3d.Field`` / ``emg3d.models.VolumeModel``): data are then
+uploaded, processed and written back in place.
+"""
+import itertools
+from dataclasses import dataclass
+from datetime import datetime, timedelta
+from time import perf_counter
+from typing import Union
+
+import numpy as np
+import scipy.sparse.linalg as _ssl
+
+from emg3d_b200 import _lib, core, fields, meshes, models
+
+__all__ = ['solve', 'solve_source', 'multigrid', 'krylov', 'smoothing',
+           'restriction', 'prolongation', 'residual', 'MGParameters',
+           'RegularGridProlongator']
+
+__version__ = '0.1.0'
+
+# lr_dir -> line directions applied one after the other (solver.py:836-846)
+_LR_DIRS = {0: (), 1: (1,), 2: (2,), 3: (3,), 4: (2, 3), 5: (1, 3), 6: (1, 2),
+            7: (1, 2, 3)}
+_LR_CODE = {v: k for k, v in _LR_DIRS.items()}
+
+
+class Timer:
+    """Wall-clock helper with the reference's string formats (utils.py:169-198)."""
+
+    def __init__(self):
+        self._t0 = perf_counter()
+
+    @property
+    def t0(self):
+        return self._t0
+
+    @property
+    def now(self):
+        return datetime.now().strftime("%H:%M:%S")
+
+    @property
+    def elapsed(self):
+        return perf_counter() - self._t0
+
+    @property
+    def runtime(self):
+        return str(timedelta(seconds=np.round(self.elapsed)))
+
+    def __repr__(self):
+        return f"Runtime : {self.runtime}"
+
+
+# =========================================================================== #
+# Device-side hierarchy
+# =========================================================================== #
+
+def _set_dtype(handle, dtype):
+    """Tell a bare level (no coefficients) which dtype its fields have."""
+    _lib.check(_lib.load().emg3d_b200_level_set_model(
+        handle.ptr, int(np.dtype(dtype).kind == 'c'), None, None, None, None))
+
+
+class _Level:
+    """One grid of the hierarchy with its coefficients resident on the device."""
+
+    def __init__(self, grid, dtype, case, eta, zeta):
+        self.grid = grid
+        self.dtype = np.dtype(dtype)
+        self.cplx = self.dtype.kind == 'c'
+        self.case = case
+        self.eta = eta            # three DeviceArrays, aliased as in the reference
+        self.zeta = zeta
+        self.handle = _lib.LevelHandle(grid.h)
+        self.handle.set_model(self.cplx, eta[0], eta[1], eta[2], zeta)
+        self.children = {}        # c_sc_dir -> coarse _Level
+        self.sc_to_parent = None
+        self._res = None          # residual scratch
+        self.s = None             # coarse source / field (owned by coarse levels)
+        self.e = None
+
+    @property
+    def shape(self):
+        return tuple(self.grid.shape_cells)
+
+    @property
+    def n_edges(self):
+        return int(self.grid.n_edges)
+
+    def new_field(self, zero=True):
+        f = _lib.DeviceArray(self.n_edges, self.dtype)
+        if zero:
+            f.zero()
+        return f
+
+    def res_buffer(self):
+        if self._res is None:
+            self._res = _lib.DeviceArray(self.n_edges, self.dtype)
+        return self._res
+
+    @classmethod
+    def from_volume_model(cls, vmodel, dtype):
+        """Upload a (host) VolumeModel; keeps eta aliases (models.py:698-712)."""
+        grid = vmodel.grid
+        dtype = np.dtype(dtype)
+        arrs, devs = [], []
+        for a in (vmodel.eta_x, vmodel.eta_y, vmodel.eta_z):
+            for k, b in enumerate(arrs):
+                if a is b:
+                    devs.append(devs[k])
+                    break
+            else:
+                if np.dtype(a.dtype).kind == 'c' and dtype.kind != 'c':
+                    raise ValueError("complex coefficients with a real-valued field")
+                devs.append(_lib.DeviceArray.from_host(np.asarray(a, dtype=dtype)))
+            arrs.append(a)
+        zeta = _lib.DeviceArray.from_host(np.asarray(vmodel.zeta, dtype=np.float64))
+        if not isinstance(grid, meshes.BaseMesh):
+            grid = meshes.BaseMesh(grid.h, grid.origin)
+        return cls(grid, dtype, getattr(vmodel, 'case', 'triaxial'), devs, zeta)
+
+    def coarse(self, sc_dir):
+        """Coarse level for the (current) semicoarsening pattern; cached."""
+        sc_dir = int(sc_dir)
+        if sc_dir in self.children:
+            return self.children[sc_dir]
+        g = self.grid
+        cflag = core.SC_FLAGS[sc_dir]
+        nodes = (g.nodes_x, g.nodes_y, g.nodes_z)
+        centers = (g.cell_centers_x, g.cell_centers_y, g.cell_centers_z)
+        ch = [np.diff(nodes[a][::2 if cflag[a] else 1]) for a in range(3)]
+        cg = meshes.BaseMesh(ch, g.origin)
+        cnodes = (cg.nodes_x, cg.nodes_y, cg.nodes_z)
+        ccenters = (cg.cell_centers_x, cg.cell_centers_y, cg.cell_centers_z)
+        weights, lo, frac = [None] * 9, [], []
+        for a in range(3):
+            if cflag[a]:
+                weights[3 * a:3 * a + 3] = core.restrict_weights(
+                    nodes[a], centers[a], g.h[a], cnodes[a], ccenters[a], cg.h[a])
+            li, fr = core.interpolation_table(nodes[a], cnodes[a])
+            lo.append(li)
+            frac.append(fr)
+        handle = _lib.LevelHandle(cg.h)
+        handle.link(self.handle, cflag, weights, lo, frac)
+        lib = _lib.load()
+
+        def sum_cells(arr, cplx):
+            out = _lib.DeviceArray(cg.n_cells, arr.dtype)
+            _lib.check(lib.emg3d_b200_restrict_cells(handle.ptr, int(cplx), arr.ptr, out.ptr))
+            return out
+
+        ceta = []
+        for k, a in enumerate(self.eta):
+            for j in range(k):
+                if a is self.eta[j]:
+                    ceta.append(ceta[j])
+                    break
+            else:
+                ceta.append(sum_cells(a, self.cplx))
+        czeta = sum_cells(self.zeta, False)
+        child = _Level.__new__(_Level)
+        child.grid, child.dtype, child.cplx, child.case = cg, self.dtype, self.cplx, self.case
+        child.eta, child.zeta, child.handle = ceta, czeta, handle
+        handle.set_model(self.cplx, ceta[0], ceta[1], ceta[2], czeta)
+        child.children, child._res = {}, None
+        child.sc_to_parent = sc_dir
+        child.s = child.new_field()
+        child.e = child.new_field()
+        self.children[sc_dir] = child
+        return child
+
+
+def _order(var):
+    return core.order_id(getattr(var, 'order', None))
+
+
+def _dev_residual(lv, s, e, norm=False, out=None):
+    """r = s - A e on the device; returns the norm or the residual buffer."""
+    lib = _lib.load()
+    if norm:
+        val = _lib.c_double(0.0)
+        _lib.check(lib.emg3d_b200_residual_norm(lv.handle.ptr, s.ptr, e.ptr, None,
+                                                _lib.byref(val)))
+        return val.value
+    r = lv.res_buffer() if out is None else out
+    _lib.check(lib.emg3d_b200_residual(lv.handle.ptr, s.ptr, e.ptr, r.ptr, None))
+    return r
+
+
+def _dev_smoothing(lv, s, e, nu, lr_dir, order):
+    lib = _lib.load()
+    c_lr_dir = int(_current_lr_dir(lr_dir, lv.grid))
+    dirs = _LR_DIRS[c_lr_dir] or (0,)
+    for ldir in dirs:
+        _lib.check(lib.emg3d_b200_gauss_seidel(lv.handle.ptr, e.ptr, s.ptr, int(nu),
+                                               ldir, order))
+
+
+def _dev_restriction(lv, res, sc_dir):
+    """Coarse level with its source = R res and a zero field."""
+    child = lv.coarse(sc_dir)
+    _lib.check(_lib.load().emg3d_b200_restrict(child.handle.ptr, res.ptr, child.s.ptr))
+    child.e.zero()
+    return child
+
+
+def _dev_prolongation(child, e_fine):
+    _lib.check(_lib.load().emg3d_b200_prolong(child.handle.ptr, e_fine.ptr, child.e.ptr))
+
+
+# =========================================================================== #
+# Public API
+# =========================================================================== #
+
+def solve(model, sfield, sslsolver=True, semicoarsening=True,
+          linerelaxation=True, verb=0, **kwargs):
+    r"""Solve the 3-D EM diffusion problem with multigrid on the GPU.
+
+    Drop-in for ``emg3d.solver.solve`` (emg3d/solver.py:52-449): same
+    parameters (``cycle, efield, tol, maxit, nu_init, nu_pre, nu_coarse,
+    nu_post, clevel, return_info, log, plain, always_return``), same return
+    convention, same ``info_dict`` keys, messages and exit codes.
+
+    Additional keyword
+    ------------------
+    order : {'color', 'lex'}
+        Gauss-Seidel ordering inside the smoothers; default from
+        ``emg3d_b200.core.ORDER`` (environment ``EMG3D_B200_ORDER``, 'color').
+    """
+    always_return = kwargs.pop('always_return', False)
+    if kwargs.pop('plain', False):
+        sslsolver = False if sslsolver is True else sslsolver
+        semicoarsening = False if semicoarsening is True else semicoarsening
+        linerelaxation = False if linerelaxation is True else linerelaxation
+    efield = kwargs.pop('efield', None)
+    order = kwargs.pop('order', None)
+    core.order_id(order)  # validate early
+
+    var = MGParameters(
+        sslsolver=sslsolver, semicoarsening=semicoarsening,
+        linerelaxation=linerelaxation, shape_cells=model.shape, verb=verb,
+        **kwargs)
+    var.order = order
+
+    var.cprint(f"\n:: emg3d START :: {var.time.now} :: "
+               f"v{__version__}\n", 2)
+    var.cprint(var, 2)
+
+    var.l2_refe = float(np.linalg.norm(sfield.field))
+    var.error_at_cycle[0] = var.l2_refe
+
+    if sfield.frequency is None:
+        raise ValueError(
+            "Source field is missing frequency information; Create "
+            "it with `emg3d.fields.get_source_field`, or initiate it "
+            "with `emg3d.fields.Field`, providing frequency information."
+        )
+
+    vmodel = models.VolumeModel(model, sfield)
+    dtype = sfield.field.dtype
+    level = _Level.from_volume_model(vmodel, dtype)
+    d_s = _lib.DeviceArray.from_host(np.asarray(sfield.field))
+    info = ""
+
+    if efield is None:
+        efield = fields.Field(model.grid, dtype=dtype, frequency=sfield._frequency)
+        d_e = level.new_field()
+        var.do_return = True
+    else:
+        if sfield.field.dtype != efield.field.dtype:
+            raise ValueError(
+                "Source field and electric field must have the same "
+                "dtype; complex (f-domain) or real (s-domain). Provided:"
+                f"sfield: {sfield.field.dtype}; efield: {efield.field.dtype}."
+            )
+        if efield.frequency is None:
+            efield._frequency = sfield._frequency
+        d_e = _lib.DeviceArray.from_host(np.asarray(efield.field))
+        _lib.check(_lib.load().emg3d_b200_pec_zero(level.handle.ptr, d_e.ptr))
+        var.do_return = always_return
+        var.l2 = _dev_residual(level, d_s, d_e, norm=True)
+        if var.l2 < var.tol * var.l2_refe:
+            var.sslsolver = None
+            var.cycle = None
+            var.exit_message = "CONVERGED"
+            info = "   > NOTHING DONE (provided efield already good enough)\n"
+
+    if var.l2_refe < 100 * np.finfo(float).tiny:
+        var.l2_refe = np.nan
+        var.sslsolver = None
+        var.cycle = None
+        var.exit_message = "CONVERGED"
+        info = "   > RETURN ZERO E-FIELD (provided sfield is zero)\n"
+        efield = fields.Field(model.grid, dtype=dtype, frequency=sfield._frequency)
+        d_e = level.new_field()
+
+    header = f"   [hh:mm:ss]  {'rel. error':<22}"
+    if var.sslsolver:
+        header += f"{'solver':<20}"
+        if var.cycle:
+            header += f"{'MG':<11} l s"
+        var.cprint(header + "\n", 3)
+    elif var.cycle:
+        var.cprint(header + f"{'[abs. error, last/prev]':>29}   l s\n", 3)
+
+    if var.sslsolver:
+        _krylov(level, d_s, d_e, var)
+    elif var.cycle:
+        _multigrid(level, d_s, d_e, var)
+
+    # Bring the result back into the (possibly user-provided) host field.
+    d_e.download(out=efield.field.view(np.ndarray))
+
+    exit_status = int(var.exit_message != 'CONVERGED')
+
+    if var.verb in [1, 2]:
+        _print_one_liner(var, var.l2, True)
+    elif var.verb > 2:
+        if var.sslsolver:
+            info = f"   > Solver steps     : {var.ssl_it}\n"
+            if var.cycle:
+                info += f"   > MG prec. steps   : {var.it}\n"
+        elif var.cycle:
+            info = f"   > MG cycles        : {var.it}\n"
+        info += f"   > Final rel. error : {var.l2/var.l2_refe:.3e}\n\n"
+        info += f":: emg3d END   :: {var.time.now} :: "
+        info += f"runtime = {var.time.runtime}\n"
+        var.cprint(info, 2)
+    elif var.verb == 0 and exit_status == 1:
+        var.cprint(f"* WARNING :: {var.exit_message}", -1)
+
+    if var.return_info:
+        info_dict = {
+            'exit': exit_status,
+            'exit_message': var.exit_message,
+            'abs_error': var.l2,
+            'rel_error': var.l2 / var.l2_refe,
+            'ref_error': var.l2_refe,
+            'tol': var.tol,
+            'it_mg': var.it,
+            'it_ssl': var.ssl_it,
+            'time': var.runtime_at_cycle[-1],
+            'runtime_at_cycle': var.runtime_at_cycle,
+            'error_at_cycle': var.error_at_cycle,
+            'log': var.log_message,
+        }
+
+    if var.do_return and var.return_info:
+        return efield, info_dict
+    elif var.do_return:
+        return efield
+    elif var.return_info:
+        return info_dict
+
+
+def solve_source(model, source, frequency, **kwargs):
+    """``get_source_field`` followed by :func:`solve` (solver.py:452-467)."""
+    sfield = fields.get_source_field(model.grid, source, frequency)
+    return solve(model, sfield, **kwargs)
+
+
+# --------------------------------------------------------------------------- #
+# host <-> device adapters for the public sub-routines
+# --------------------------------------------------------------------------- #
+
+def _as_level(model, dtype):
+    """Device level of a (Volume)model-like object; cached on the object."""
+    if isinstance(model, _Level):
+        return model
+    cached = getattr(model, '_b200_level', None)
+    if cached is not None and cached.dtype == np.dtype(dtype):
+        return cached
+    lv = _Level.from_volume_model(model, dtype)
+    try:
+        model._b200_level = lv
+    except AttributeError:
+        pass
+    return lv
+
+
+def _up(field):
+    if isinstance(field, _lib.DeviceArray):
+        return field
+    return _lib.DeviceArray.from_host(np.asarray(field.field))
+
+
+def _down(dev, field):
+    if not isinstance(field, _lib.DeviceArray):
+        dev.download(out=np.asarray(field.field).view(np.ndarray))
+
+
+def multigrid(model, sfield, efield, var, **kwargs):
+    """Multigrid V/W/F cycling (solver.py:471-649); ``efield`` updated in place."""
+    lv = _as_level(model, np.asarray(sfield.field).dtype
+                   if not isinstance(sfield, _lib.DeviceArray) else sfield.dtype)
+    d_s, d_e = _up(sfield), _up(efield)
+    _multigrid(lv, d_s, d_e, var, **kwargs)
+    _down(d_e, efield)
+
+
+def krylov(model, sfield, efield, var):
+    """Krylov solver with optional MG preconditioner (solver.py:652-784)."""
+    lv = _as_level(model, np.asarray(sfield.field).dtype
+                   if not isinstance(sfield, _lib.DeviceArray) else sfield.dtype)
+    d_s, d_e = _up(sfield), _up(efield)
+    _krylov(lv, d_s, d_e, var)
+    _down(d_e, efield)
+
+
+def smoothing(model, sfield, efield, nu, lr_dir, order=None):
+    """``nu`` Gauss-Seidel sweeps with line relaxation ``lr_dir`` (solver.py:788-846)."""
+    lv = _as_level(model, np.asarray(sfield.field).dtype)
+    d_s, d_e = _up(sfield), _up(efield)
+    _dev_smoothing(lv, d_s, d_e, nu, lr_dir, core.order_id(order))
+    _down(d_e, efield)
+
+
+class _CoarseModel:
+    """Coarse-grid model returned by :func:`restriction` (solver.py:909-926)."""
+
+    def __init__(self, level):
+        self._b200_level = level
+        self.case = level.case
+        self.grid = level.grid
+        self._host = {}
+
+    def _get(self, k):
+        if k not in self._host:
+            lv = self._b200_level
+            src = lv.zeta if k == 3 else lv.eta[k]
+            for j in range(k if k < 3 else 0):
+                if lv.eta[j] is src:
+                    self._host[k] = self._get(j)
+                    break
+            else:
+                self._host[k] = src.download().reshape(lv.shape, order='F')
+        return self._host[k]
+
+    eta_x = property(lambda self: self._get(0))
+    eta_y = property(lambda self: self._get(1))
+    eta_z = property(lambda self: self._get(2))
+    zeta = property(lambda self: self._get(3))
+
+
+def restriction(model, sfield, residual, sc_dir):
+    """Coarse grid, coarse model and restricted residual (solver.py:849-944)."""
+    dtype = np.asarray(sfield.field).dtype
+    lv = _as_level(model, dtype)
+    child = _dev_restriction(lv, _up(residual), sc_dir)
+    freq = getattr(sfield, '_frequency', None)
+    csfield = fields.Field(child.grid, data=child.s.download(), frequency=freq)
+    cefield = fields.Field(child.grid, dtype=dtype, frequency=freq)
+    return _CoarseModel(child), csfield, cefield
+
+
+def prolongation(efield, cefield, sc_dir):
+    """``efield += P cefield`` on interior edges (solver.py:947-1019)."""
+    g, cg = efield.grid, cefield.grid
+    dtype = np.asarray(efield.field).dtype
+    cflag = core.SC_FLAGS[int(sc_dir)]
+    fine = _lib.LevelHandle(g.h)
+    coarse = _lib.LevelHandle(cg.h)
+    lo, frac = [], []
+    for a, n in enumerate('xyz'):
+        li, fr = core.interpolation_table(getattr(g, 'nodes_' + n), getattr(cg, 'nodes_' + n))
+        lo.append(li)
+        frac.append(fr)
+    weights = [None] * 9
+    for a in range(3):
+        if cflag[a]:
+            weights[3 * a:3 * a + 3] = [np.zeros(cg.shape_nodes[a])] * 3
+    coarse.link(fine, cflag, weights, lo, frac)
+    _set_dtype(coarse, dtype)
+    d_e, d_c = _up(efield), _up(cefield)
+    _lib.check(_lib.load().emg3d_b200_prolong(coarse.ptr, d_e.ptr, d_c.ptr))
+    _down(d_e, efield)
+
+
+def residual(model, sfield, efield, norm=False):
+    """Residual field ``s - A e`` or its l2-norm (solver.py:1022-1070)."""
+    dtype = np.asarray(sfield.field).dtype
+    lv = _as_level(model, dtype)
+    d_s, d_e = _up(sfield), _up(efield)
+    if norm:
+        return _dev_residual(lv, d_s, d_e, norm=True)
+    r = _dev_residual(lv, d_s, d_e)
+    return fields.Field(sfield.grid, data=r.download(),
+                        frequency=getattr(sfield, '_frequency', None))
+
+
+# =========================================================================== #
+# Cycling on the device
+# =========================================================================== #
+
+def _multigrid(lv, s, e, var, level=0, new_cycmax=0):
+    """Recursive multigrid cycle on device-resident data (solver.py:471-649)."""
+    order = _order(var)
+    it = 0
+    coarsest = level == var.clevel[var.sc_dir]
+    if coarsest:
+        cycmax = 1
+    elif new_cycmax == 0 or var.cycle != 'F':
+        cycmax = var.cycmax
+    else:
+        cycmax = new_cycmax
+    cyc = 0
+
+    # The reference evaluates the residual norm on entry at every level but uses
+    # it on level 0 only (and for verb > 4 printing); skip the unused ones.
+    want_norm = level == 0 or var.verb > 4
+    l2_last = _dev_residual(lv, s, e, norm=True) if want_norm else 0.0
+    l2_stag = np.ones(var.maxcycle) * l2_last
+
+    if var.first_cycle and var.verb > 3:
+        var.level_all.append(level)
+
+    if level == 0:
+        var.cprint("     it cycmax               error", 4)
+        var.cprint("      level [  dimension  ]            info\n", 4)
+        if var.verb > 4:
+            _print_gs_info(var, it, level, cycmax, lv.grid, l2_last, "initial error")
+
+    if level == 0 and var.nu_init > 0:
+        _dev_smoothing(lv, s, e, var.nu_init, var.lr_dir, order)
+        if var.verb > 4:
+            _print_gs_info(var, it, level, cycmax, lv.grid,
+                           _dev_residual(lv, s, e, norm=True), "initial smoothing")
+
+    while level == 0 or (level > 0 and it < cycmax):
+        l2_prev = l2_last
+        l2_stag[(it - 1) % var.maxcycle] = l2_last
+
+        if level == var.clevel[var.sc_dir]:
+            _dev_smoothing(lv, s, e, var.nu_coarse, var.lr_dir, order)
+            if var.verb > 4:
+                _print_gs_info(var, it, level, cycmax, lv.grid,
+                               _dev_residual(lv, s, e, norm=True), "coarsest level")
+        else:
+            if var.nu_pre > 0:
+                _dev_smoothing(lv, s, e, var.nu_pre, var.lr_dir, order)
+                if var.verb > 4:
+                    _print_gs_info(var, it, level, cycmax, lv.grid,
+                                   _dev_residual(lv, s, e, norm=True), "pre-smoothing")
+
+            sc_dir = _current_sc_dir(var.sc_dir, lv.grid)
+            res = _dev_residual(lv, s, e)
+            child = _dev_restriction(lv, res, sc_dir)
+            _multigrid(child, child.s, child.e, var, level=level + 1,
+                       new_cycmax=cycmax - cyc)
+            _dev_prolongation(child, e)
+
+            if var.first_cycle and var.verb > 3:
+                var.level_all.append(level)
+
+            if var.nu_post > 0:
+                _dev_smoothing(lv, s, e, var.nu_post, var.lr_dir, order)
+                if var.verb > 4:
+                    _print_gs_info(var, it, level, cycmax, lv.grid,
+                                   _dev_residual(lv, s, e, norm=True), "post-smoothing")
+
+        it += 1
+        if level == 0:
+            var.it += 1
+
+        if level > 0:
+            cyc += 1
+        else:
+            l2_last = _dev_residual(lv, s, e, norm=True)
+            _print_cycle_info(var, l2_last, l2_prev)
+            if var.sc_cycle:
+                var.sc_dir = next(var.sc_cycle)
+            if var.lr_cycle:
+                var.lr_dir = next(var.lr_cycle)
+            if _terminate(var, l2_last, l2_stag[(it - 1) % var.maxcycle], it):
+                break
+
+    var.l2 = l2_last
+
+
+class _Vec:
+    """Device vector algebra for the Krylov iteration."""
+
+    def __init__(self, cplx, n):
+        self.cplx, self.n = int(cplx), int(n)
+        self.lib = _lib.load()
+
+    def dot(self, x, y, conj=True):
+        out = (_lib.c_double * 2)()
+        _lib.check(self.lib.emg3d_b200_dot_host(self.cplx, self.n, x.ptr, y.ptr,
+                                                int(conj), out))
+        return complex(out[0], out[1]) if self.cplx else out[0]
+
+    def norm(self, x):
+        out = (_lib.c_double * 2)()
+        _lib.check(self.lib.emg3d_b200_dot_host(self.cplx, self.n, x.ptr, x.ptr, 1, out))
+        return float(np.sqrt(out[0]))
+
+    def axpby(self, a, x, b, y):
+        """y = a x + b y"""
+        a, b = complex(a), complex(b)
+        _lib.check(self.lib.emg3d_b200_axpby(self.cplx, self.n, a.real, a.imag, x.ptr,
+                                             b.real, b.imag, y.ptr))
+
+
+def _krylov(lv, s, e, var):
+    """Krylov solvers with multigrid as preconditioner (solver.py:652-784)."""
+
+    def record(x):
+        var.ssl_it += 1
+        var.runtime_at_cycle = np.r_[var.runtime_at_cycle, var.time.elapsed]
+        var.l2 = _dev_residual(lv, s, x, norm=True)
+        var.error_at_cycle = np.r_[var.error_at_cycle, var.l2]
+        if var.verb > 3:
+            log = f"   [{var.time.now}]   {var.l2/var.l2_refe:.3e} "
+            log += f" after {var.ssl_it:3} {var.sslsolver}-cycles"
+            if var.ssl_it == 1 and var.it == 0 and var.cycle is not None:
+                log += "\n"
+            var.cprint(log, 3)
+        elif var.verb in [2, 3]:
+            _print_one_liner(var, var.l2)
+
+    try:
+        if var.sslsolver == 'bicgstab':
+            i = _bicgstab(lv, s, e, var, record)
+        else:
+            i = _scipy_krylov(lv, s, e, var, record)
+    except _ConvergenceError:
+        i = -1
+        e.zero()
+        var.exit_message += " (returned field is zero)"
+
+    if var.verb == 3:
+        pre = 50 * " " + "\r"
+    else:
+        pre = "\n"
+    pre += "   > "
+    if i < 0:
+        if var.exit_message == '':
+            var.exit_message = f"Error in {var.sslsolver} ({i})"
+        pre = "\n* ERROR   :: "
+    elif i > 0:
+        var.exit_message = "MAX. ITERATION REACHED, NOT CONVERGED"
+    else:
+        var.exit_message = "CONVERGED"
+    var.cprint(pre + var.exit_message, 2)
+
+
+def _bicgstab(lv, b, x, var, callback):
+    """Preconditioned BiCGSTAB on the device.
+
+    Same recurrence, breakdown tests and stopping rule as
+    ``scipy.sparse.linalg.bicgstab`` (SciPy 1.18, ``_isolve/iterative.py``),
+    which the reference calls at solver.py:763-765 with ``rtol=tol``,
+    ``atol=1e-30``, ``maxiter=ssl_maxit`` and a callback per iteration.
+    Returns SciPy's ``info`` code.
+    """
+    lib = _lib.load()
+    vec = _Vec(lv.cplx, lv.n_edges)
+    matvec = lambda src, dst: _lib.check(lib.emg3d_b200_apply(lv.handle.ptr, src.ptr, dst.ptr))
+
+    def psolve(src, dst):
+        if var.cycle:
+            dst.zero()
+            _multigrid(lv, src, dst, var)
+        else:
+            dst.copy_from(src)
+
+    bnrm2 = vec.norm(b)
+    atol = max(1e-30, float(var.tol) * bnrm2)
+    if bnrm2 == 0:
+        x.copy_from(b)
+        return 0
+    rhotol = np.finfo(np.float64).eps ** 2
+    omegatol = rhotol
+
+    new = lambda: _lib.DeviceArray(lv.n_edges, lv.dtype)
+    r, rtilde, p, v, s_, t, phat, shat = (new() for _ in range(8))
+    # r = b - A x (x may be a user-provided start field)
+    if vec.norm(x) > 0:
+        matvec(x, r)
+        vec.axpby(1.0, b, -1.0, r)
+    else:
+        r.copy_from(b)
+    rtilde.copy_from(r)
+    rho_prev = omega = alpha = None
+
+    for iteration in range(var.ssl_maxit):
+        if vec.norm(r) < atol:
+            return 0
+        rho = vec.dot(rtilde, r)
+        if abs(rho) < rhotol:
+            return -10
+        if iteration > 0:
+            if abs(omega) < omegatol:
+                return -11
+            beta = (rho / rho_prev) * (alpha / omega)
+            vec.axpby(-omega, v, 1.0, p)      # p -= omega v
+            vec.axpby(1.0, r, beta, p)        # p = beta p + r
+        else:
+            p.copy_from(r)
+        psolve(p, phat)
+        matvec(phat, v)
+        rv = vec.dot(rtilde, v)
+        if rv == 0:
+            return -11
+        alpha = rho / rv
+        vec.axpby(-alpha, v, 1.0, r)          # r -= alpha v
+        s_.copy_from(r)
+        if vec.norm(s_) < atol:
+            vec.axpby(alpha, phat, 1.0, x)
+            return 0
+        psolve(s_, shat)
+        matvec(shat, t)
+        omega = vec.dot(t, s_) / vec.dot(t, t)
+        vec.axpby(alpha, phat, 1.0, x)
+        vec.axpby(omega, shat, 1.0, x)
+        vec.axpby(-omega, t, 1.0, r)
+        rho_prev = rho
+        callback(x)
+    return var.ssl_maxit
+
+
+def _scipy_krylov(lv, s, e, var, callback):
+    """CGS / GCROT(m,k): SciPy drives, the GPU applies A and the preconditioner."""
+    lib = _lib.load()
+    n = lv.n_edges
+    d_in, d_out = lv.new_field(False), lv.new_field(False)
+
+    def amatvec(x):
+        d_in.upload(np.ascontiguousarray(x, dtype=lv.dtype))
+        _lib.check(lib.emg3d_b200_apply(lv.handle.ptr, d_in.ptr, d_out.ptr))
+        return d_out.download()
+
+    def mg_matvec(b):
+        d_in.upload(np.ascontiguousarray(b, dtype=lv.dtype))
+        d_out.zero()
+        _multigrid(lv, d_in, d_out, var)
+        return d_out.download()
+
+    A = _ssl.LinearOperator((n, n), dtype=lv.dtype, matvec=amatvec)
+    M = _ssl.LinearOperator((n, n), dtype=lv.dtype, matvec=mg_matvec) if var.cycle else None
+    d_x = lv.new_field(False)
+
+    def cb(x):
+        d_x.upload(np.ascontiguousarray(x, dtype=lv.dtype))
+        callback(d_x)
+
+    x, i = getattr(_ssl, var.sslsolver)(
+        A=A, b=s.download(), x0=e.download(), rtol=var.tol, maxiter=var.ssl_maxit,
+        atol=1e-30, M=M, callback=cb)
+    e.upload(np.ascontiguousarray(x, dtype=lv.dtype))
+    return i
+
+
+# =========================================================================== #
+# Parameters
+# =========================================================================== #
+
+@dataclass
+class MGParameters:
+    """Settings and running state of one solve (solver.py:1074-1381)."""
+
+    verb: int
+    sslsolver: Union[str, bool]
+    semicoarsening: Union[int, bool]
+    linerelaxation: Union[int, bool]
+    shape_cells: tuple
+    cycle: Union[str, None] = 'F'
+    tol: float = 1e-6
+    maxit: int = 50
+    nu_init: int = 0
+    nu_pre: int = 2
+    nu_coarse: int = 1
+    nu_post: int = 2
+    clevel: int = -1
+    return_info: bool = False
+    log: int = 0
+
+    def __post_init__(self):
+        self.level_all = list()
+        self.first_cycle = True
+        self.it = 0
+        self.ssl_it = 0
+        self.l2 = 1.0
+        self.l2_refe = 1.0
+        self.order = None
+        self._max_level()
+        self.exit_message = ''
+        self.log_message = ''
+        self.time = Timer()
+        self.runtime_at_cycle = np.array([0.])
+        self.error_at_cycle = np.array([0.])
+        self.do_return = True
+        self._semicoarsening()
+        self._linerelaxation()
+        self._solver_and_cycle()
+
+    def __repr__(self):
+        nx, ny, nz = self.shape_cells
+        cl = self._repr_clevel
+        return (
+            f"   MG-cycle       : {self.cycle!r:17}"
+            f"   sslsolver : {self.sslsolver!r}\n"
+            f"   semicoarsening : {self._repr_sc_dir:17}"
+            f"   tol       : {self.tol}\n"
+            f"   linerelaxation : {self._repr_lr_dir:17}"
+            f"   maxit     : {self._repr_maxit}\n"
+            f"   nu_{{i,1,c,2}}   : {self.nu_init}, {self.nu_pre},"
+            f" {self.nu_coarse}, {self.nu_post}       "
+            f"   verb      : {self.verb}\n"
+            f"   Original grid  : {nx:3} x {ny:3} x {nz:3}     =>"
+            f" {nx*ny*nz:,} cells\n"
+            f"   Coarsest grid  : {cl['shape_cells'][0]:3} x"
+            f" {cl['shape_cells'][1]:3} x {cl['shape_cells'][2]:3}  "
+            f"   => {cl['n_cells']:,} cells\n"
+            f"   Coarsest level : {cl['clevel'][0]:3} ; {cl['clevel'][1]:3}"
+            f" ;{cl['clevel'][2]:4}   {cl['message']}\n"
+        )
+
+    def cprint(self, info, verbosity, **kwargs):
+        """Print and/or log ``info`` if ``verb > verbosity`` (solver.py:1181-1200)."""
+        if self.verb > verbosity:
+            if self.log != 0:
+                self.log_message += str(info) + '\n'
+            if self.log >= 0:
+                print(info, **kwargs)
+
+    def _max_level(self):
+        """How often each axis can be halved (solver.py:1202-1270)."""
+        user = np.inf if self.clevel < 0 else self.clevel
+        halvings = np.zeros(3, dtype=np.int64)
+        for a, n in enumerate(self.shape_cells):
+            while n % 2 == 0 and n > 2:
+                halvings[a] += 1
+                n //= 2
+            if -1 < self.clevel < halvings[a]:
+                halvings[a] = self.clevel
+        cx, cy, cz = (int(v) for v in halvings)
+        # coarsest level for sc_dir = 0, 1, 2, 3
+        self.clevel = np.array([max(cx, cy, cz), max(cy, cz), max(cx, cz), max(cx, cy)])
+        coarsest = tuple(int(n / 2**c) for n, c in zip(self.shape_cells, halvings))
+        self._repr_clevel = {'n_cells': int(np.prod(coarsest)), 'shape_cells': coarsest,
+                             'clevel': halvings}
+        too_big = any(c < user and m > 7 for c, m in zip(halvings, coarsest))
+        too_few = any(halvings < min(user, 3))
+        self._repr_clevel['message'] = (
+            "  :: Grid not optimal for MG solver ::" if too_big or too_few else "")
+        if np.any(np.array(self.shape_cells) < 2):
+            raise ValueError(
+                "Nr. of cells must be at least two in each direction "
+                "Provided shape: ({self.shape_cells[0]}, "
+                f"{self.shape_cells[1]}, {self.shape_cells[2]})."
+            )
+
+    @staticmethod
+    def _direction_cycle(flag, default, upper):
+        """(sequence, iterator-or-False) from a True/False/int/digits flag."""
+        if flag is True:
+            seq = np.array(default)
+            return seq, itertools.cycle(seq)
+        if flag in np.arange(upper + 1):
+            return np.array([int(flag)]), False
+        seq = np.array([int(c) for c in str(abs(flag))])
+        return seq, itertools.cycle(seq)
+
+    def _semicoarsening(self):
+        seq, cyc = self._direction_cycle(self.semicoarsening, [1, 2, 3], 3)
+        if np.any(seq < 0) or np.any(seq > 3):
+            raise ValueError(
+                "`semicoarsening` must be one of {False;True;0;1;2;3}. "
+                "Or a combination of {0;1;2;3} to cycle, e.g. 1213. "
+                f"Provided: {self.semicoarsening}."
+            )
+        self.sc_cycle = cyc
+        self.sc_dir = next(cyc) if cyc else seq[0]
+        self.semicoarsening = self.sc_dir != 0
+        self._repr_sc_dir = f"{self.semicoarsening} {seq}"
+        self.raw_sc_cycle = seq
+
+    def _linerelaxation(self):
+        seq, cyc = self._direction_cycle(self.linerelaxation, [4, 5, 6], 7)
+        if np.any(seq < 0) or np.any(seq > 7):
+            raise ValueError(
+                "`linerelaxation` must be one of "
+                "{False;True;0;1;2;3;4;5;6;7}. Or a combination of "
+                "{1;2;3;4;5;6;7} to cycle, e.g. 1213. "
+                f"Provided: {self.linerelaxation}."
+            )
+        self.lr_cycle = cyc
+        self.lr_dir = next(cyc) if cyc else seq[0]
+        self.linerelaxation = self.lr_dir != 0
+        self._repr_lr_dir = f"{self.linerelaxation} {seq}"
+        self.raw_lr_cycle = seq
+
+    def _solver_and_cycle(self):
+        solvers = ['bicgstab', 'cgs', 'gcrotmk']
+        if self.sslsolver is True:
+            self.sslsolver = 'bicgstab'
+        elif self.sslsolver is not False and self.sslsolver not in solvers:
+            raise ValueError(
+                f"`sslsolver` must be True, False, or one of {solvers}. "
+                f"Provided: {self.sslsolver!r}."
+            )
+        if self.cycle not in ['F', 'V', 'W', None]:
+            raise ValueError(
+                "`cycle` must be one of {'F';'V';'W';None}. "
+                f"Provided: {self.cycle}."
+            )
+        self.cycmax = 2 if self.cycle in ['F', 'W'] else 1
+        if not self.sslsolver and not self.cycle:
+            raise ValueError(
+                "At least `cycle` or `sslsolver` is required. Provided"
+                f"input: cycle={self.cycle}; sslsolver={self.sslsolver}."
+            )
+        self.ssl_maxit = 0
+        self._repr_maxit = f"{self.maxit}"
+        self.maxcycle = max(len(self.raw_sc_cycle), len(self.raw_lr_cycle))
+        if self.sslsolver:
+            self.ssl_maxit = self.maxit
+            if self.cycle is not None:
+                self.maxit = self.maxcycle
+                self._repr_maxit += f" ({self.maxit})"
+
+
+class RegularGridProlongator:
+    """Bilinear prolongation of 2-D slices from a coarse to a fine tensor grid.
+
+    Interface of the reference's class (solver.py:1385-1478): initialise with
+    coarse ``(cx, cy)`` and fine ``(x, y)`` coordinates; calling it with coarse
+    values of shape ``(cx.size, cy.size)`` returns the fine values flattened in
+    Fortran order.  (Inside the solver the same tables are applied by the CUDA
+    prolongation kernel; this host class serves callers of the public name.)
+    """
+
+    def __init__(self, cx, cy, x, y):
+        self._ix, self._tx = core.interpolation_table(x, cx)
+        self._iy, self._ty = core.interpolation_table(y, cy)
+        self.size = self._ix.size * self._iy.size
+
+    def __call__(self, values):
+        v = np.asarray(values)
+        ix, iy = self._ix[:, None], self._iy[None, :]
+        tx, ty = self._tx[:, None], self._ty[None, :]
+        out = (v[ix, iy] * ((1 - tx) * (1 - ty)) + v[ix, iy + 1] * ((1 - tx) * ty) +
+               v[ix + 1, iy] * (tx * (1 - ty)) + v[ix + 1, iy + 1] * (tx * ty))
+        return out.ravel('F')
+
+
+# =========================================================================== #
+# Helpers
+# =========================================================================== #
+
+def _current_sc_dir(sc_dir, grid):
+    """Semicoarsening pattern usable on this grid (solver.py:1482-1531)."""
+    n = grid.shape_cells
+    keep = [n[a] % 2 != 0 or n[a] < 3 or sc_dir == a + 1 for a in range(3)]
+    table = {(False, False, False): 0, (True, False, False): 1,
+             (False, True, False): 2, (False, False, True): 3,
+             (False, True, True): 4, (True, False, True): 5,
+             (True, True, False): 6, (True, True, True): 6}
+    return table[tuple(bool(k) for k in keep)]
+
+
+def _current_lr_dir(lr_dir, grid):
+    """Drop line directions with only two cells (solver.py:1534-1588)."""
+    n = grid.shape_cells
+    dirs = tuple(d for d in _LR_DIRS[int(lr_dir)] if n[d - 1] != 2)
+    return np.array(_LR_CODE[dirs])
+
+
+class _ConvergenceError(Exception):
+    """Raised inside a Krylov run when the preconditioner diverges/stagnates."""
+
+
+def _terminate(var, l2_last, l2_stag, it):
+    """Termination criteria of the multigrid iteration (solver.py:1591-1664)."""
+    finished = sslabort = False
+    if l2_last < var.tol * var.l2_refe:
+        var.exit_message = "CONVERGED"
+        finished = True
+    elif l2_last > 10 * var.l2_refe or not np.isfinite(l2_last):
+        var.exit_message = "DIVERGED"
+        finished = sslabort = True
+    elif it > 2 and l2_last >= l2_stag:
+        var.exit_message = "STAGNATED"
+        finished = sslabort = True
+    elif it == var.maxit:
+        if not var.sslsolver:
+            var.exit_message = "MAX. ITERATION REACHED, NOT CONVERGED"
+        finished = True
+
+    if finished:
+        if var.sslsolver and sslabort:
+            raise _ConvergenceError
+        elif not var.sslsolver:
+            if var.verb == 3:
+                add = 50 * " " + "\r"
+            elif var.verb < 5:
+                add = "\n"
+            else:
+                add = ""
+            var.cprint(add + "   > " + var.exit_message, 2)
+    return finished
+
+
+def _restrict_model_parameters(param, sc_dir):
+    """Coarse cell = sum of its fine cells, on the device (solver.py:1667-1718)."""
+    param = np.asfortranarray(param)
+    cflag = core.SC_FLAGS[int(sc_dir)]
+    cshape = tuple(n // 2 if f else n for n, f in zip(param.shape, cflag))
+    fine = _lib.LevelHandle([np.ones(n) for n in param.shape])
+    coarse = _lib.LevelHandle([np.ones(n) for n in cshape])
+    dummy = [(np.zeros(n + 1, np.int32), np.zeros(n + 1)) for n in param.shape]
+    weights = [None] * 9
+    for a in range(3):
+        if cflag[a]:
+            weights[3 * a:3 * a + 3] = [np.zeros(cshape[a] + 1)] * 3
+    coarse.link(fine, cflag, weights, [d[0] for d in dummy], [d[1] for d in dummy])
+    d_p = _lib.DeviceArray.from_host(param)
+    d_c = _lib.DeviceArray(int(np.prod(cshape)), param.dtype)
+    _lib.check(_lib.load().emg3d_b200_restrict_cells(
+        coarse.ptr, int(param.dtype.kind == 'c'), d_p.ptr, d_c.ptr))
+    return d_c.download().reshape(cshape, order='F')
+
+
+def _get_restriction_weights(grid, cgrid, sc_dir):
+    """Restriction weights per axis; dummies where not coarsened (solver.py:1721-1780)."""
+    cflag = core.SC_FLAGS[int(sc_dir)]
+    out = []
+    for a, n in enumerate('xyz'):
+        if cflag[a]:
+            out.append(core.restrict_weights(
+                getattr(grid, 'nodes_' + n), getattr(grid, 'cell_centers_' + n), grid.h[a],
+                getattr(cgrid, 'nodes_' + n), getattr(cgrid, 'cell_centers_' + n), cgrid.h[a]))
+        else:
+            zeros = np.zeros(grid.shape_nodes[a], dtype=np.float64)
+            out.append((zeros, np.ones(grid.shape_nodes[a], dtype=np.float64), zeros))
+    return tuple(out)
+
+
+# ---- log output (formats pinned by the reference's tests) -------------------
+
+def _print_cycle_info(var, l2_last, l2_prev):
+    """End-of-cycle log line and, once, the cycle diagram (solver.py:1788-1862)."""
+    var.runtime_at_cycle = np.r_[var.runtime_at_cycle, var.time.elapsed]
+    var.error_at_cycle = np.r_[var.error_at_cycle, l2_last]
+
+    if var.verb in [2, 3]:
+        _print_one_liner(var, l2_last)
+    if var.verb < 4:
+        return
+    info = "\n" if var.verb > 4 else ""
+
+    if var.first_cycle:
+        lv = np.array(var.level_all, dtype=np.int64)
+        depth = np.max(lv)
+        step = ((lv[1:] + lv[:-1]) // 2 + 1) * (lv[1:] - lv[:-1])   # +down, -up
+        shown = min(len(step), 70)
+        rows = ["       h_\n"]
+        for cl in range(depth):
+            row = f"   {2**(cl+1):4}h_ "
+            for v in range(shown):
+                row += " " if abs(step[v]) != cl + 1 else "\\" if step[v] > 0 else "/"
+            rows.append(row + ("\n" if cl < depth - 1 else ""))
+        info += "".join(rows) + "\n\n"
+        if len(step) > 70:
+            info += "  (Cycle-QC restricted to first 70 steps of "
+            info += f"{len(step)} steps.)\n"
+        var.first_cycle = False
+
+    info += f"   [{var.time.now}]   {l2_last/var.l2_refe:.3e}  "
+    if var.sslsolver:
+        info += f"after {19*' '} {var.it:3} {var.cycle}-cycles "
+    else:
+        info += f"after {var.it:3} {var.cycle}-cycles   "
+        info += f"[{l2_last:.3e}, {l2_last/l2_prev:.3f}]"
+    info += f"   {var.lr_dir} {var.sc_dir}"
+    if var.verb > 4:
+        info += "\n"
+    var.cprint(info, 3)
+
+
+def _print_gs_info(var, it, level, cycmax, grid, norm, add):
+    """Log line after a smoothing step, verb > 4 (solver.py:1865-1892)."""
+    n = grid.shape_cells
+    info = f"     {it:2} {level} {cycmax} [{n[0]:3}, {n[1]:3}, {n[2]:3}]: {norm:.3e} "
+    var.cprint(info + add, 4)
+
+
+def _print_one_liner(var, l2_last, last=False):
+    """Continuously updated one-line status (solver.py:1895-1919)."""
+    info = f":: emg3d :: {l2_last/var.l2_refe:.1e}; "
+    if var.sslsolver:
+        info += f"{var.ssl_it}({var.it}); "
+    else:
+        info += f"{var.it}; "
+    info += f"{var.time.runtime}"
+    if last:
+        var.cprint(info + f"; {var.exit_message}", -100)
+    else:
+        var.cprint(info, -100, end='\r')

@@ -1,0 +1,152 @@
+/* emg3d_b200 -- C ABI of the B200-native multigrid hot path.
+ *
+ * Drop-in boundary for the module-level calls that emg3d/solver.py makes into
+ * emg3d/core.py (the reference has no plugin registry).
+ * Plain C types only: ints, sizes, raw pointers.  Unless stated otherwise all
+ * data pointers are DEVICE pointers obtained from emg3d_b200_malloc.
+ *
+ * Layout contract (emg3d/fields.py:116, 201-259; emg3d/models.py:662-691):
+ *   field  = [fx | fy | fz], fx (nx, ny+1, nz+1), fy (nx+1, ny, nz+1),
+ *            fz (nx+1, ny+1, nz), x fastest; complex128 (cplx = 1, interleaved
+ *            re/im) or float64 (cplx = 0, Laplace domain);
+ *   eta_x, eta_y, eta_z : (nx, ny, nz), x fastest, same dtype as the fields,
+ *            may alias each other (isotropic / VTI / HTI);
+ *   zeta, hx, hy, hz    : float64.
+ *
+ * Every function returns 0 on success and a non-zero code on failure; the
+ * message is available from emg3d_b200_last_error().  One device per process
+ * (one process per GPU); all work is issued on one library-owned CUDA stream.
+ */
+#ifndef EMG3D_B200_H
+#define EMG3D_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct emg3d_b200_level emg3d_b200_level;
+
+enum { EMG3D_B200_ORDER_LEX = 0, EMG3D_B200_ORDER_COLOR = 1 };
+
+/* ---- runtime ------------------------------------------------------------- */
+int emg3d_b200_abi_version(void);
+const char* emg3d_b200_last_error(void);
+int emg3d_b200_device_count(int* count);
+int emg3d_b200_init(int device);
+int emg3d_b200_device_name(char* buf, int buflen);
+int emg3d_b200_mem_info(size_t* free_bytes, size_t* total_bytes);
+int emg3d_b200_sync(void);
+/* number of kernel launches issued by the library so far */
+int emg3d_b200_launch_count(long long* count);
+
+/* ---- memory -------------------------------------------------------------- */
+int emg3d_b200_malloc(void** dptr, size_t nbytes);
+int emg3d_b200_free(void* dptr);
+int emg3d_b200_memset(void* dptr, int byte, size_t nbytes);
+int emg3d_b200_h2d(void* dst_dev, const void* src_host, size_t nbytes);
+int emg3d_b200_d2h(void* dst_host, const void* src_dev, size_t nbytes);
+int emg3d_b200_d2d(void* dst_dev, const void* src_dev, size_t nbytes);
+int emg3d_b200_host_alloc(void** hptr, size_t nbytes);   /* pinned host memory */
+int emg3d_b200_host_free(void* hptr);
+
+/* ---- timing and CUDA graphs (all on the library stream) ------------------- */
+int emg3d_b200_event_create(void** ev);
+int emg3d_b200_event_record(void* ev);
+int emg3d_b200_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms); /* syncs on stop */
+int emg3d_b200_event_destroy(void* ev);
+int emg3d_b200_graph_begin(void);
+int emg3d_b200_graph_end(void** graph_exec);
+int emg3d_b200_graph_launch(void* graph_exec);
+int emg3d_b200_graph_destroy(void* graph_exec);
+
+/* ---- grid levels ----------------------------------------------------------
+ * A level = one grid of the multigrid hierarchy: cell counts, widths (HOST
+ * arrays, copied), the coefficient arrays (device, NOT owned) and cached line
+ * factorisations (owned).  Replaces the (grid, VolumeModel) pair that
+ * emg3d/solver.py passes around (solver.py:827-830, 1060-1062).               */
+int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz,
+                            const double* hx_host, const double* hy_host,
+                            const double* hz_host);
+int emg3d_b200_level_destroy(emg3d_b200_level* lv);
+int emg3d_b200_level_set_model(emg3d_b200_level* lv, int cplx, const void* eta_x,
+                               const void* eta_y, const void* eta_z, const double* zeta);
+/* bytes of the cached factorisation of line direction ldir (1, 2, 3) */
+int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes);
+int emg3d_b200_level_drop_factors(emg3d_b200_level* lv);
+/* Link a coarse level to its parent.  cflag[a] = 1 if axis a is coarsened
+ * (emg3d/solver.py:891-897).  weights[3*a + {0,1,2}] = wl, w0, wr of axis a as
+ * returned by core.restrict_weights (core.py:2004-2076), HOST arrays of
+ * length n_coarse_nodes(a), ignored (may be NULL) when axis a is not
+ * coarsened.  lo[a], frac[a]: per FINE node of axis a the lower coarse node
+ * and the fraction inside that coarse cell (the bilinear weights of
+ * solver.py:1447-1473), HOST arrays of length n_fine_nodes(a).                */
+int emg3d_b200_level_link(emg3d_b200_level* coarse, const emg3d_b200_level* fine,
+                          const int* cflag, const double* const* weights,
+                          const int* const* lo, const double* const* frac);
+
+/* ---- kernels -------------------------------------------------------------- */
+/* r -= A e.  Replaces core.amat_x (core.py:57-58; call sites solver.py:695-699,
+ * 1060-1062).                                                                  */
+int emg3d_b200_amat_x(emg3d_b200_level* lv, void* r, const void* e);
+/* out = A e: the matvec of the Krylov wrapper (solver.py:686-702, where the
+ * reference calls amat_x on a zero field and negates).                        */
+int emg3d_b200_apply(emg3d_b200_level* lv, const void* e, void* out);
+/* r = s - A e (r may be NULL) and, if norm2_dev != NULL, norm2_dev[0] =
+ * ||r||_2^2 over ALL edges.  Replaces solver.residual (solver.py:1022-1070).  */
+int emg3d_b200_residual(emg3d_b200_level* lv, const void* s, const void* e, void* r,
+                        double* norm2_dev);
+/* same, synchronous, returning ||r||_2 to the host */
+int emg3d_b200_residual_norm(emg3d_b200_level* lv, const void* s, const void* e, void* r,
+                             double* norm_host);
+/* nu Gauss-Seidel sweeps, in place on e.  ldir 0 = point smoother
+ * (core.gauss_seidel, core.py:210-212), 1/2/3 = x/y/z line relaxation
+ * (core.gauss_seidel_x/_y/_z, core.py:506-508, 786-788, 1071-1073).
+ * order: LEX = sequentially equivalent to the reference's lexicographic
+ * sweeps; COLOR = multicolour ordering (8 colours point, 4 colours lines).     */
+int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu, int ldir,
+                            int order);
+/* coarse_s = R r_fine.  Replaces core.restrict (core.py:1620-1621).            */
+int emg3d_b200_restrict(emg3d_b200_level* coarse, const void* r_fine, void* s_coarse);
+/* e_fine += P e_coarse on interior edges.  Replaces solver.prolongation
+ * (solver.py:947-1019).                                                        */
+int emg3d_b200_prolong(emg3d_b200_level* coarse, void* e_fine, const void* e_coarse);
+/* coarse cell array = sum of the fine cells.  Replaces
+ * solver._restrict_model_parameters (solver.py:1667-1718).                     */
+int emg3d_b200_restrict_cells(emg3d_b200_level* coarse, int cplx, const void* p_fine,
+                              void* p_coarse);
+/* zero the tangential boundary edges (solver.py:350-355) */
+int emg3d_b200_pec_zero(emg3d_b200_level* lv, void* e);
+
+/* ---- vector helpers for the Krylov wrapper and the termination tests -------
+ * n counts elements of the given dtype.  dot2_dev[0..1] = (re, im) of
+ * sum conj?(x) y.  Scalars are (re, im) pairs; im ignored when cplx = 0.       */
+int emg3d_b200_dot(int cplx, long long n, const void* x, const void* y, int conj_x,
+                   double* dot2_dev);
+int emg3d_b200_dot_host(int cplx, long long n, const void* x, const void* y, int conj_x,
+                        double* dot2_host);
+int emg3d_b200_axpby(int cplx, long long n, double a_re, double a_im, const void* x,
+                     double b_re, double b_im, void* y);
+
+/* ---- host-array convenience entry points ----------------------------------
+ * Exact signatures of the reference kernels on HOST arrays (upload, run,
+ * download); these are what a ctypes/cffi shim inside emg3d/core.py would
+ * bind, see INTEGRATION.md.                                                    */
+int emg3d_b200_host_amat_x(int cplx, int nx, int ny, int nz, void* rx, void* ry, void* rz,
+                           const void* ex, const void* ey, const void* ez, const void* eta_x,
+                           const void* eta_y, const void* eta_z, const double* zeta,
+                           const double* hx, const double* hy, const double* hz);
+int emg3d_b200_host_gauss_seidel(int cplx, int ldir, int order, int nx, int ny, int nz, void* ex,
+                                 void* ey, void* ez, const void* sx, const void* sy,
+                                 const void* sz, const void* eta_x, const void* eta_y,
+                                 const void* eta_z, const double* zeta, const double* hx,
+                                 const double* hy, const double* hz, int nu);
+
+/* core.solve (core.py:1481-1482): amat has 6 n entries, bvec n; both in place. */
+int emg3d_b200_host_solve(int cplx, int n, void* amat, void* bvec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMG3D_B200_H */

@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the emg3d multigrid hot path.
+
+A plain-C restatement (``emg3d_oracle.c`` + ``kernels.inc``) of the reference's
+numba kernels (emg3d/core.py) with the same call signatures, loaded via ctypes,
+plus :mod:`oracle.mg`, a NumPy restatement of the driver (emg3d/solver.py).
+
+Parity status: **pinned** -- checked against outputs of the reference itself
+(imported in the build container by ``tests/golden/make_golden.py``) and against
+the reference's own regression data (``tests/data/regression.npz``), see
+``tests/test_oracle_golden.py``.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import this package.  The product
+(``emg3d_b200``) never does and has no CPU fallback.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, 'libemg3d_oracle.so')
+
+
+def build(force=False):
+    """Compile the oracle with gcc (a few seconds)."""
+    if force or not os.path.exists(_LIBPATH) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIBPATH)
+            for f in ('emg3d_oracle.c', 'kernels.inc')):
+        subprocess.run(['make', '-C', _HERE, '-s', '-B'], check=True)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIBPATH)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f(a, dtype):
+    """Check that `a` is an F-contiguous (or 1-D contiguous) array of dtype."""
+    if a.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {a.dtype}")
+    if not (a.flags.f_contiguous or a.flags.c_contiguous and a.ndim == 1):
+        raise ValueError("array must be Fortran-contiguous")
+    return a
+
+
+def _suffix(dtype):
+    return '_c' if np.dtype(dtype) == np.complex128 else '_r'
+
+
+def _h(h):
+    return np.ascontiguousarray(h, dtype=np.float64)
+
+
+def amat_x(rx, ry, rz, ex, ey, ez, eta_x, eta_y, eta_z, zeta, hx, hy, hz):
+    """r -= A e; signature of emg3d.core.amat_x (core.py:57-58)."""
+    dt = ex.dtype
+    hx, hy, hz = _h(hx), _h(hy), _h(hz)
+    fn = getattr(lib(), 'orc_amat_x' + _suffix(dt))
+    eta = [np.asfortranarray(a, dtype=dt) for a in (eta_x, eta_y, eta_z)]
+    fn(_p(_f(rx, dt)), _p(_f(ry, dt)), _p(_f(rz, dt)),
+       _p(_f(ex, dt)), _p(_f(ey, dt)), _p(_f(ez, dt)),
+       _p(eta[0]), _p(eta[1]), _p(eta[2]),
+       _p(_f(np.asfortranarray(zeta), np.float64)), _p(hx), _p(hy), _p(hz),
+       ctypes.c_int(hx.size), ctypes.c_int(hy.size), ctypes.c_int(hz.size))
+
+
+def _gs(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy, hz, nu):
+    dt = ex.dtype
+    hx, hy, hz = _h(hx), _h(hy), _h(hz)
+    fn = getattr(lib(), 'orc_gauss_seidel' + _suffix(dt))
+    eta = [np.asfortranarray(a, dtype=dt) for a in (eta_x, eta_y, eta_z)]
+    fn(ctypes.c_int(ldir),
+       _p(_f(ex, dt)), _p(_f(ey, dt)), _p(_f(ez, dt)),
+       _p(_f(sx, dt)), _p(_f(sy, dt)), _p(_f(sz, dt)),
+       _p(eta[0]), _p(eta[1]), _p(eta[2]),
+       _p(_f(np.asfortranarray(zeta), np.float64)), _p(hx), _p(hy), _p(hz),
+       ctypes.c_int(hx.size), ctypes.c_int(hy.size), ctypes.c_int(hz.size),
+       ctypes.c_int(int(nu)))
+
+
+def gauss_seidel(*args):
+    """Point smoother; signature of emg3d.core.gauss_seidel (core.py:210-212)."""
+    _gs(0, *args)
+
+
+def gauss_seidel_x(*args):
+    """x-line smoother; emg3d.core.gauss_seidel_x (core.py:506-508)."""
+    _gs(1, *args)
+
+
+def gauss_seidel_y(*args):
+    """y-line smoother; emg3d.core.gauss_seidel_y (core.py:786-788)."""
+    _gs(2, *args)
+
+
+def gauss_seidel_z(*args):
+    """z-line smoother; emg3d.core.gauss_seidel_z (core.py:1071-1073)."""
+    _gs(3, *args)
+
+
+def solve(amat, bvec):
+    """Banded LDL^T solve in place; emg3d.core.solve (core.py:1481-1482)."""
+    dt = bvec.dtype
+    if amat.dtype != dt:
+        raise TypeError("amat and bvec must have the same dtype")
+    fn = getattr(lib(), 'orc_solve' + _suffix(dt))
+    fn(_p(_f(amat, dt)), _p(_f(bvec, dt)), ctypes.c_int(bvec.size))
+
+
+# sc_dir -> which axes are coarsened (solver.py:891-897)
+SC_FLAGS = {0: (1, 1, 1), 1: (0, 1, 1), 2: (1, 0, 1), 3: (1, 1, 0),
+            4: (1, 0, 0), 5: (0, 1, 0), 6: (0, 0, 1)}
+
+
+def restrict(crx, cry, crz, rx, ry, rz, wx, wy, wz, sc_dir):
+    """Full-weighting restriction; emg3d.core.restrict (core.py:1620-1621)."""
+    dt = rx.dtype
+    fn = getattr(lib(), 'orc_restrict' + _suffix(dt))
+    nx, ny, nz = ry.shape[0] - 1, rx.shape[1] - 1, rx.shape[2] - 1
+    flags = (ctypes.c_int * 3)(*SC_FLAGS[int(sc_dir)])
+    w = [np.ascontiguousarray(a, dtype=np.float64) for t in (wx, wy, wz) for a in t]
+    fn(_p(_f(crx, dt)), _p(_f(cry, dt)), _p(_f(crz, dt)),
+       _p(_f(rx, dt)), _p(_f(ry, dt)), _p(_f(rz, dt)),
+       *[_p(a) for a in w],
+       ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(nz), flags)
+
+
+def restrict_weights(nodes, cell_centers, h, cnodes, ccell_centers, ch):
+    """1-D restriction weights; emg3d.core.restrict_weights (core.py:2004-2005)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64)
+            for a in (nodes, cell_centers, h, cnodes, ccell_centers, ch)]
+    n = arrs[3].size
+    wl, w0, wr = np.empty(n), np.empty(n), np.empty(n)
+    lib().orc_restrict_weights(*[_p(a) for a in arrs], ctypes.c_int(n),
+                               _p(wl), _p(w0), _p(wr))
+    return wl, w0, wr
+
+
+def prolong(ex, ey, ez, cex, cey, cez, nodes, cnodes, sc_dir):
+    """e += P ce on interior edges; emg3d.solver.prolongation (solver.py:947-1019).
+
+    ``nodes``/``cnodes`` are (x, y, z) tuples of fine/coarse node coordinates.
+    """
+    dt = ex.dtype
+    fn = getattr(lib(), 'orc_prolong' + _suffix(dt))
+    nx, ny, nz = ey.shape[0] - 1, ex.shape[1] - 1, ex.shape[2] - 1
+    flags = (ctypes.c_int * 3)(*SC_FLAGS[int(sc_dir)])
+    xs = [np.ascontiguousarray(a, dtype=np.float64) for a in (*nodes, *cnodes)]
+    fn(_p(_f(ex, dt)), _p(_f(ey, dt)), _p(_f(ez, dt)),
+       _p(_f(cex, dt)), _p(_f(cey, dt)), _p(_f(cez, dt)),
+       *[_p(a) for a in xs],
+       ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(nz), flags)
