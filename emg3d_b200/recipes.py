@@ -1,0 +1,112 @@
+"""Seeded synthetic inputs for the configurations named in BASELINE.json.
+
+Plain arrays only (widths, origin, resistivities, source, frequency), so the same
+numbers can be fed to this package, to the CPU oracle and -- in the build
+container, when generating golden vectors -- to the reference itself.
+Recipes follow SURVEY.md section 8(d) / Appendix C.
+"""
+import numpy as np
+
+SEED = 20261017
+
+
+def widths(n, alpha, core=50.):
+    """n cells: n/2 uniform core cells, n/4 stretched padding cells per side."""
+    npad = n // 4
+    pad = core * alpha ** (np.arange(npad) + 1)
+    return np.r_[pad[::-1], np.ones(n - 2 * npad) * core, pad]
+
+
+def grid_arrays(nx, ny, nz, ax, ay, az, zc=-1000.):
+    """Widths and origin of a stretched grid centred on (0, 0, zc)."""
+    h = [widths(nx, ax), widths(ny, ay), widths(nz, az)]
+    origin = (-h[0].sum() / 2, -h[1].sum() / 2, zc - h[2].sum() / 2)
+    return h, origin
+
+
+def _centers(h, origin):
+    out = []
+    for a in range(3):
+        nodes = np.r_[0., h[a].cumsum()] + origin[a]
+        out.append((nodes[1:] + nodes[:-1]) / 2)
+    return out
+
+
+def model_halfspace(h, origin):
+    """Isotropic half-space: 1 Ohm.m below z = 0, 100 Ohm.m above (config 1)."""
+    cx, cy, cz = _centers(h, origin)
+    shape = (cx.size, cy.size, cz.size)
+    Z = cz[None, None, :] * np.ones(shape)
+    return {'property_x': np.where(Z > 0, 100., 1.)}
+
+
+def model_triaxial(h, origin, rng):
+    """Layered background with log-normal perturbation, triaxial (configs 2, 5)."""
+    cx, cy, cz = _centers(h, origin)
+    shape = (cx.size, cy.size, cz.size)
+    Z = cz[None, None, :] * np.ones(shape)
+    rho_h = np.where(Z > 0, 0.3, np.where(Z > -1500, 1., np.where(Z > -2500, 2., 5.)))
+    rx = rho_h * np.exp(0.2 * rng.standard_normal(shape))
+    return {'property_x': rx, 'property_y': 1.5 * rx, 'property_z': 3 * rx}
+
+
+def model_marine(h, origin, rho_air=1e8):
+    """Air / sea / VTI sediment with a thin resistor (configs 3, 4)."""
+    cx, cy, cz = _centers(h, origin)
+    shape = (cx.size, cy.size, cz.size)
+    X = cx[:, None, None] * np.ones(shape)
+    Y = cy[None, :, None] * np.ones(shape)
+    Z = cz[None, None, :] * np.ones(shape)
+    rh = np.where(Z > 0, rho_air, np.where(Z > -1000, 0.3, 1.0))
+    rv = np.where(Z > 0, rho_air, np.where(Z > -1000, 0.3, 2.0))
+    tgt = (abs(X) < 2500) & (abs(Y) < 2500) & (Z < -1900) & (Z > -2000)
+    rh[tgt] = rv[tgt] = 100.
+    return {'property_x': rh, 'property_z': rv}
+
+
+def config(name, n=None):
+    """Inputs of one named configuration, optionally at a reduced size ``n``.
+
+    Returns a dict with ``h`` (3 width arrays), ``origin``, ``model`` (kwargs of
+    ``Model``), ``source`` (x, y, z, azimuth, elevation), ``frequency`` and
+    ``solver`` (kwargs of ``solve``).
+    """
+    rng = np.random.default_rng(SEED)
+    if name == 'config1':          # 32^3 uniform half-space, one V(2,2)-cycle
+        n = n or 32
+        h = [np.ones(n) * 50.] * 3
+        origin = (-25. * n, -25. * n, -25. * n)
+        return dict(h=h, origin=origin, model=model_halfspace(h, origin),
+                    source=(0., 0., -100., 0., 0.), frequency=1.0,
+                    solver=dict(plain=True, cycle='V', maxit=1))
+    if name == 'config2':          # 128^3 stretched, triaxial, F-cycle
+        n = n or 128
+        alpha = {128: 1.04, 64: 1.06, 32: 1.10}.get(n, 1.10)
+        h, origin = grid_arrays(n, n, n, alpha, alpha, alpha)
+        return dict(h=h, origin=origin, model=model_triaxial(h, origin, rng),
+                    source=(0., 0., -950., 0., 0.), frequency=1.0,
+                    solver=dict(sslsolver=False, cycle='F'))
+    if name == 'config3':          # 256^3 marine CSEM, V-cycle + BiCGSTAB
+        n = n or 256
+        alpha = {256: 1.03, 128: 1.04, 64: 1.06, 32: 1.10}.get(n, 1.10)
+        h, origin = grid_arrays(n, n, n, alpha, alpha, alpha)
+        return dict(h=h, origin=origin, model=model_marine(h, origin),
+                    source=(0., 0., -950., 0., 0.), frequency=1.0,
+                    solver=dict(cycle='V', sslsolver='bicgstab'))
+    if name == 'config4':          # 512 x 512 x 256, F-cycle, sc + lr
+        n = n or 512
+        axy = {512: 1.02, 256: 1.03, 128: 1.04, 64: 1.06, 32: 1.10}.get(n, 1.10)
+        az = {512: 1.03, 256: 1.04, 128: 1.06, 64: 1.10, 32: 1.15}.get(n, 1.15)
+        h, origin = grid_arrays(n, n, n // 2, axy, axy, az)
+        return dict(h=h, origin=origin, model=model_marine(h, origin),
+                    source=(0., 0., -950., 0., 0.), frequency=1.0,
+                    solver=dict(sslsolver=False, cycle='F', semicoarsening=True,
+                                linerelaxation=True))
+    if name == 'config5':          # 512^3 stretched, triaxial, W-cycle
+        n = n or 512
+        alpha = {512: 1.02, 256: 1.03, 128: 1.04, 64: 1.06, 32: 1.10}.get(n, 1.10)
+        h, origin = grid_arrays(n, n, n, alpha, alpha, alpha)
+        return dict(h=h, origin=origin, model=model_triaxial(h, origin, rng),
+                    source=(0., 0., -950., 0., 0.), frequency=1.0,
+                    solver=dict(cycle='W', sslsolver=False))
+    raise ValueError(f"unknown configuration {name!r}")

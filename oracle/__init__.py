@@ -162,3 +162,57 @@ def prolong(ex, ey, ez, cex, cey, cez, nodes, cnodes, sc_dir):
        _p(_f(cex, dt)), _p(_f(cey, dt)), _p(_f(cez, dt)),
        *[_p(a) for a in xs],
        ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(nz), flags)
+
+
+def gs_sequence(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy, hz, seq):
+    """Relax the blocks listed in ``seq`` one after the other (test helper).
+
+    ``seq``: int array of (ix, iy, iz) rows for ``ldir = 0`` or (t1, t2) rows
+    (transverse node indices in the reference's slot order) for line smoothers.
+    """
+    dt = ex.dtype
+    hx, hy, hz = _h(hx), _h(hy), _h(hz)
+    fn = getattr(lib(), 'orc_gs_sequence' + _suffix(dt))
+    eta = [np.asfortranarray(a, dtype=dt) for a in (eta_x, eta_y, eta_z)]
+    seq = np.ascontiguousarray(seq, dtype=np.int32)
+    fn(ctypes.c_int(ldir),
+       _p(_f(ex, dt)), _p(_f(ey, dt)), _p(_f(ez, dt)),
+       _p(_f(sx, dt)), _p(_f(sy, dt)), _p(_f(sz, dt)),
+       _p(eta[0]), _p(eta[1]), _p(eta[2]),
+       _p(_f(np.asfortranarray(zeta), np.float64)), _p(hx), _p(hy), _p(hz),
+       ctypes.c_int(hx.size), ctypes.c_int(hy.size), ctypes.c_int(hz.size),
+       _p(seq), ctypes.c_int(seq.shape[0]))
+
+
+def color_sequence(ldir, shape, nu):
+    """Block sequence of ``nu`` multicolour sweeps as the CUDA kernels run them.
+
+    Point smoother: 8 parity classes of (ix-1, iy-1, iz-1), class index
+    ``px + 2 py + 4 pz``; line smoothers: 4 classes ``pp + 2 pq`` of the
+    transverse node indices.  Odd sweeps run the classes in descending order,
+    even sweeps ascending (the first sweep of the reference is the descending
+    one, core.py:301, 311).
+    """
+    rows = []
+    back = False
+    for _ in range(nu):
+        back = not back
+        if ldir == 0:
+            nx, ny, nz = shape
+            classes = range(7, -1, -1) if back else range(8)
+            for c in classes:
+                px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+                for iz in range(1 + pz, nz, 2):
+                    for iy in range(1 + py, ny, 2):
+                        for ix in range(1 + px, nx, 2):
+                            rows.append((ix, iy, iz))
+        else:
+            d = ldir - 1
+            t1, t2 = (1 if d == 0 else 0), (1 if d == 2 else 2)
+            classes = range(3, -1, -1) if back else range(4)
+            for c in classes:
+                pp, pq = c & 1, c >> 1
+                for b in range(1 + pq, shape[t2], 2):
+                    for a in range(1 + pp, shape[t1], 2):
+                        rows.append((a, b))
+    return np.array(rows, dtype=np.int32).reshape(-1, 3 if ldir == 0 else 2)

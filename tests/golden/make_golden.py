@@ -1,0 +1,277 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE itself.
+
+Run in the build container only (needs /root/reference and numba):
+
+    NUMBA_CACHE_DIR=/tmp/nbcache python tests/golden/make_golden.py
+
+The reference package hard-imports ``empymod`` and ``scooby`` (not installed,
+not on the hot path); ``_refstubs/`` provides two-line stand-ins.  Outputs:
+
+    kernels.npz   amat_x, gauss_seidel{,_x,_y,_z} on small odd-shaped stretched
+                  grids, complex and real, triaxial, mu_r != 1, eps_r != 0
+    transfer.npz  restrict / restrict_weights / prolongation / model restriction
+                  for all seven semicoarsening patterns
+    solves.npz    full solves: the reference's own regression data
+                  (tests/data/regression.npz: res, reg_2, lap) re-exported as bare
+                  arrays, plus small siblings of the five BASELINE.json configs
+    host.npz      VolumeModel and source-field vectors (host-side inputs)
+
+The fixtures travel to the GPU box; the reference does not.
+"""
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, '_refstubs'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, REPO)
+
+import emg3d  # noqa: E402
+from emg3d import core, solver  # noqa: E402
+
+from emg3d_b200 import recipes  # noqa: E402
+
+
+def pec(f):
+    f.fx[:, 0, :] = f.fx[:, -1, :] = 0.
+    f.fx[:, :, 0] = f.fx[:, :, -1] = 0.
+    f.fy[0, :, :] = f.fy[-1, :, :] = 0.
+    f.fy[:, :, 0] = f.fy[:, :, -1] = 0.
+    f.fz[0, :, :] = f.fz[-1, :, :] = 0.
+    f.fz[:, 0, :] = f.fz[:, -1, :] = 0.
+
+
+def random_case(rng, shape, cplx):
+    nx, ny, nz = shape
+    hx = 50 * 1.1 ** rng.uniform(-3, 3, nx)
+    hy = 60 * 1.2 ** rng.uniform(-3, 3, ny)
+    hz = 40 * 1.15 ** rng.uniform(-3, 3, nz)
+    g = emg3d.TensorMesh([hx, hy, hz], (-hx.sum() / 2, -hy.sum() / 2, -hz.sum() / 2))
+    rx = 10 ** rng.uniform(-0.5, 1.5, g.shape_cells)
+    m = emg3d.Model(g, rx, 1.5 * rx * rng.uniform(.5, 2, g.shape_cells), 3 * rx,
+                    mu_r=rng.uniform(1, 2, g.shape_cells),
+                    epsilon_r=rng.uniform(1, 10, g.shape_cells))
+    freq = 1.3 if cplx else -1.3
+    sf = emg3d.Field(g, frequency=freq)
+    ef = emg3d.Field(g, frequency=freq)
+    n = sf.field.size
+    sf.field[:] = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    ef.field[:] = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    pec(ef)
+    return g, emg3d.models.VolumeModel(m, sf), sf, ef
+
+
+def make_kernels():
+    rng = np.random.default_rng(1)
+    out = {}
+    cases = [((6, 4, 8), True), ((2, 4, 6), True), ((5, 3, 2), False), ((7, 2, 3), True),
+             ((8, 8, 8), False), ((8, 8, 8), True), ((4, 10, 6), True)]
+    for k, (shape, cplx) in enumerate(cases):
+        g, vm, sf, ef = random_case(rng, shape, cplx)
+        p = f"k{k}_"
+        out[p + 'hx'], out[p + 'hy'], out[p + 'hz'] = g.h
+        out[p + 'eta_x'], out[p + 'eta_y'], out[p + 'eta_z'] = vm.eta_x, vm.eta_y, vm.eta_z
+        out[p + 'zeta'] = vm.zeta
+        out[p + 's'] = np.asarray(sf.field)
+        out[p + 'e'] = np.asarray(ef.field)
+        args = (vm.eta_x, vm.eta_y, vm.eta_z, vm.zeta, g.h[0], g.h[1], g.h[2])
+        r = sf.copy()
+        core.amat_x(r.fx, r.fy, r.fz, ef.fx, ef.fy, ef.fz, *args)
+        out[p + 'r'] = np.asarray(r.field)
+        for ldir, name in enumerate(['gauss_seidel', 'gauss_seidel_x', 'gauss_seidel_y',
+                                     'gauss_seidel_z']):
+            for nu in (1, 2):
+                e1 = ef.copy()
+                getattr(core, name)(e1.fx, e1.fy, e1.fz, sf.fx, sf.fy, sf.fz, *args, nu)
+                out[p + f'gs{ldir}_nu{nu}'] = np.asarray(e1.field)
+    out['n_cases'] = len(cases)
+    np.savez_compressed(os.path.join(HERE, 'kernels.npz'), **out)
+
+
+def make_transfer():
+    rng = np.random.default_rng(2)
+    out = {}
+    cases = [((8, 4, 12), True), ((4, 6, 2), True), ((6, 2, 4), False), ((16, 8, 8), True)]
+    sc_flags = {0: (1, 1, 1), 1: (0, 1, 1), 2: (1, 0, 1), 3: (1, 1, 0),
+                4: (1, 0, 0), 5: (0, 1, 0), 6: (0, 0, 1)}
+    for k, (shape, cplx) in enumerate(cases):
+        g, vm, sf, ef = random_case(rng, shape, cplx)
+        p = f"t{k}_"
+        out[p + 'hx'], out[p + 'hy'], out[p + 'hz'] = g.h
+        out[p + 'origin'] = g.origin
+        out[p + 'eta_x'], out[p + 'eta_y'], out[p + 'eta_z'] = vm.eta_x, vm.eta_y, vm.eta_z
+        out[p + 'zeta'] = vm.zeta
+        out[p + 'r'] = np.asarray(ef.field)      # used as the fine "residual"
+        out[p + 'e'] = np.asarray(sf.field)      # fine field to prolongate onto
+        scs = []
+        for sc, fl in sc_flags.items():
+            if any(f and (n % 2 or n < 2) for f, n in zip(fl, shape)):
+                continue
+            scs.append(sc)
+            cm, cs, ce = solver.restriction(vm, sf, ef, sc)
+            q = p + f"sc{sc}_"
+            out[q + 'cs'] = np.asarray(cs.field)
+            out[q + 'ceta_x'], out[q + 'ceta_y'], out[q + 'ceta_z'] = cm.eta_x, cm.eta_y, cm.eta_z
+            out[q + 'czeta'] = cm.zeta
+            wx, wy, wz = solver._get_restriction_weights(g, cm.grid, sc)
+            for a, w in zip('xyz', (wx, wy, wz)):
+                out[q + f'w{a}'] = np.array(w)
+            ce.field[:] = rng.standard_normal(ce.field.size)
+            out[q + 'ce'] = np.asarray(ce.field)
+            e1 = sf.copy()
+            solver.prolongation(e1, ce, sc)
+            out[q + 'e_out'] = np.asarray(e1.field)
+        out[p + 'sc_dirs'] = np.array(scs)
+    out['n_cases'] = len(cases)
+    np.savez_compressed(os.path.join(HERE, 'transfer.npz'), **out)
+
+
+def _store_solve(out, p, grid, model, sfield, kwargs, freq, source=None):
+    """Run the reference and store inputs + result under prefix p."""
+    out[p + 'hx'], out[p + 'hy'], out[p + 'hz'] = grid.h
+    out[p + 'origin'] = np.asarray(grid.origin, dtype=float)
+    for name in ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r'):
+        v = getattr(model, name)
+        if v is not None:
+            out[p + name] = np.asarray(v)
+    out[p + 'frequency'] = float(freq)
+    out[p + 'sfield'] = np.asarray(sfield.field)
+    if source is not None:
+        out[p + 'source'] = np.asarray(source, dtype=float)
+    buf = io.StringIO()
+    kw = dict(kwargs)
+    with redirect_stdout(buf):
+        efield, info = solver.solve(model, sfield, return_info=True, **kw)
+    out[p + 'efield'] = np.asarray(efield.field)
+    out[p + 'kwargs'] = json.dumps(kwargs)
+    out[p + 'it_mg'] = info['it_mg']
+    out[p + 'it_ssl'] = info['it_ssl']
+    out[p + 'exit_message'] = info['exit_message']
+    out[p + 'abs_error'] = info['abs_error']
+    out[p + 'ref_error'] = info['ref_error']
+    out[p + 'error_at_cycle'] = info['error_at_cycle']
+    out[p + 'stdout'] = buf.getvalue()
+    print(p, kwargs, '->', info['exit_message'], info['it_mg'], info['it_ssl'],
+          f"{info['rel_error']:.3e}")
+
+
+def make_solves():
+    out = {}
+    reg = emg3d.load('/root/reference/tests/data/regression.npz', verb=0)
+
+    # --- reference regression data: 'res' (tests/test_solver.py:18-70)
+    dat = reg['res']
+    model = emg3d.Model(**dat['input_model'])
+    src = dat['input_source']
+    sfield = emg3d.get_source_field(**src)
+    for key, kw in (('F', dict(plain=True, verb=4)), ('W', dict(plain=True, cycle='W')),
+                    ('V', dict(plain=True, cycle='V')),
+                    ('bic', dict(verb=4, sslsolver='bicgstab', plain=True))):
+        p = f"res_{key}_"
+        _store_solve(out, p, model.grid, model, sfield, kw, src['frequency'], src['source'])
+        # the stored regression result must agree with what we just computed
+        want = dat[{'F': 'Fresult', 'W': 'Wresult', 'V': 'Vresult', 'bic': 'bicresult'}[key]]
+        np.testing.assert_allclose(want.field, out[p + 'efield'])
+        out[p + 'regression'] = np.asarray(want.field)
+
+    # --- 'reg_2' (tests/test_solver.py:152-176)
+    dat = reg['reg_2']
+    model, sfield, inp = dat['model'], dat['sfield'], dict(dat['inp'])
+    for n in ['nu_init', 'nu_pre', 'nu_coarse', 'nu_post', 'clevel', 'maxit',
+              'semicoarsening', 'linerelaxation', 'verb']:
+        inp[n] = int(inp[n])
+    inp['tol'] = float(inp['tol'])
+    inp['sslsolver'] = False
+    _store_solve(out, 'reg2_', model.grid, model, sfield, inp, sfield._frequency)
+    np.testing.assert_allclose(dat['result'].field, out['reg2_efield'])
+    out['reg2_regression'] = np.asarray(dat['result'].field)
+
+    # --- 'lap' (tests/test_solver.py:227-247), Laplace domain = real arithmetic
+    dat = reg['lap']
+    model = emg3d.Model(**dat['input_model'])
+    src = dat['input_source']
+    sfield = emg3d.get_source_field(**src)
+    _store_solve(out, 'lap_F_', model.grid, model, sfield, dict(plain=True),
+                 src['frequency'], src['source'])
+    np.testing.assert_allclose(dat['Fresult'].field, out['lap_F_efield'], atol=1e-14)
+    out['lap_F_regression'] = np.asarray(dat['Fresult'].field)
+    _store_solve(out, 'lap_bic_', model.grid, model, sfield,
+                 dict(semicoarsening=False, linerelaxation=False),
+                 src['frequency'], src['source'])
+    np.testing.assert_allclose(dat['bicresult'].field, out['lap_bic_efield'], atol=1e-14)
+    out['lap_bic_regression'] = np.asarray(dat['bicresult'].field)
+
+    # --- small siblings of the BASELINE.json configurations
+    for name, n in (('config1', 32), ('config2', 32), ('config3', 32), ('config4', 32),
+                    ('config5', 32)):
+        cfg = recipes.config(name, n)
+        grid = emg3d.TensorMesh(cfg['h'], cfg['origin'])
+        model = emg3d.Model(grid, **cfg['model'])
+        sfield = emg3d.get_source_field(grid, cfg['source'], cfg['frequency'])
+        _store_solve(out, f"{name}_", grid, model, sfield, cfg['solver'], cfg['frequency'],
+                     cfg['source'])
+    # tight-tolerance versions (for the multicolour ordering: agreement at convergence)
+    for name in ('config2', 'config3'):
+        cfg = recipes.config(name, 32)
+        if name == 'config3':
+            cfg['model'] = recipes.model_marine(cfg['h'], cfg['origin'], rho_air=1e4)
+        grid = emg3d.TensorMesh(cfg['h'], cfg['origin'])
+        model = emg3d.Model(grid, **cfg['model'])
+        sfield = emg3d.get_source_field(grid, cfg['source'], cfg['frequency'])
+        kw = dict(cfg['solver'], tol=1e-11, maxit=60)
+        _store_solve(out, f"{name}_tight_", grid, model, sfield, kw, cfg['frequency'],
+                     cfg['source'])
+    np.savez_compressed(os.path.join(HERE, 'solves.npz'), **out)
+
+
+def make_host():
+    """VolumeModel and source vectors, to pin the host-side input builders."""
+    out = {}
+    rng = np.random.default_rng(3)
+    hx = recipes.widths(8, 1.2, 30.)
+    hy = recipes.widths(6, 1.1, 40.)
+    hz = recipes.widths(10, 1.3, 20.)
+    origin = (-hx.sum() / 2, -hy.sum() / 2 + 3., -hz.sum() / 2 - 7.)
+    grid = emg3d.TensorMesh([hx, hy, hz], origin)
+    out['hx'], out['hy'], out['hz'], out['origin'] = hx, hy, hz, np.array(origin)
+    sources = [(0., 0., 0., 0., 0.), (12.3, -20.1, 5.5, 30., 20.), (-31., 14., -60., -50., 75.),
+               (-40., 40., -10., 10., -20., 30.)]
+    for k, src in enumerate(sources):
+        for freq in (1.0, -2.5):
+            sf = emg3d.get_source_field(grid, src, freq)
+            out[f'src{k}_f{freq}'] = np.asarray(sf.field)
+        out[f'src{k}'] = np.array(src)
+    out['n_sources'] = len(sources)
+    shape = grid.shape_cells
+    props = dict(property_x=10 ** rng.uniform(-1, 2, shape), property_y=10 ** rng.uniform(-1, 2, shape),
+                 property_z=10 ** rng.uniform(-1, 2, shape), mu_r=rng.uniform(1, 3, shape),
+                 epsilon_r=rng.uniform(1, 20, shape))
+    for k, v in props.items():
+        out['vm_' + k] = v
+    for case, keys in (('iso', ['property_x']), ('vti', ['property_x', 'property_z']),
+                       ('hti', ['property_x', 'property_y']),
+                       ('tri', ['property_x', 'property_y', 'property_z']),
+                       ('full', list(props))):
+        model = emg3d.Model(grid, **{k: props[k] for k in keys})
+        for freq in (0.7, -3.0):
+            sf = emg3d.Field(grid, frequency=freq)
+            vm = emg3d.models.VolumeModel(model, sf)
+            for n in ('eta_x', 'eta_y', 'eta_z', 'zeta'):
+                out[f'vm_{case}_f{freq}_{n}'] = np.asarray(getattr(vm, n))
+    np.savez_compressed(os.path.join(HERE, 'host.npz'), **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host']
+    for w in which:
+        globals()['make_' + w]()
+    for f in ('kernels', 'transfer', 'solves', 'host'):
+        fn = os.path.join(HERE, f + '.npz')
+        if os.path.exists(fn):
+            print(f, os.path.getsize(fn) // 1024, 'KiB')

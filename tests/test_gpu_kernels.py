@@ -1,0 +1,274 @@
+"""Parity of the CUDA kernels (through the C ABI) with the reference / oracle.
+
+All comparisons are norm-wise relative errors ``||x_gpu - x_ref|| / ||x_ref||``.
+Bars (fp64 throughout):
+
+* ``amat_x`` / residual, restriction, prolongation, cell sums: <= 1e-13
+  (pure stencils, no solves);
+* smoothers in ``order='lex'`` against the reference's own outputs (golden) and
+  against the oracle on larger grids: <= 1e-11 after a call (every update is a
+  6x6 or banded solve; the reference itself is only defined to ~1e-13 because
+  numba runs with fastmath);
+* smoothers in ``order='color'`` against the oracle run in the same colour
+  sequence: <= 1e-11.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import mg
+from conftest import rel_err
+from helpers import kernel_case, split_field
+
+pytestmark = pytest.mark.gpu
+
+GS = ['gauss_seidel', 'gauss_seidel_x', 'gauss_seidel_y', 'gauss_seidel_z']
+
+
+@pytest.fixture(scope='module')
+def core():
+    from emg3d_b200 import core, _lib
+    _lib.init()
+    return core
+
+
+def _margs(c):
+    return (c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'], c['hx'], c['hy'], c['hz'])
+
+
+def random_case(rng, shape, cplx, aliased=False):
+    """Random stretched grid, triaxial eta with real part (eps_r), mu_r != 1."""
+    nx, ny, nz = shape
+    h = [50 * 1.1 ** rng.uniform(-3, 3, nx), 60 * 1.2 ** rng.uniform(-3, 3, ny),
+         40 * 1.15 ** rng.uniform(-3, 3, nz)]
+    g = mg.Grid(h)
+    res = 10 ** rng.uniform(-0.5, 1.5, shape)
+    vm = mg.VolumeModel(g, res, None if aliased else 1.5 * res * rng.uniform(.5, 2, shape),
+                        None if aliased else 3 * res, rng.uniform(1, 2, shape),
+                        rng.uniform(1, 10, shape), 1.3 if cplx else -1.3)
+    n = g.n_edges
+    s = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    e = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    ex, ey, ez = g.split(e)
+    ex[:, 0, :] = ex[:, -1, :] = 0
+    ex[:, :, 0] = ex[:, :, -1] = 0
+    ey[0, :, :] = ey[-1, :, :] = 0
+    ey[:, :, 0] = ey[:, :, -1] = 0
+    ez[0, :, :] = ez[-1, :, :] = 0
+    ez[:, 0, :] = ez[:, -1, :] = 0
+    d = dict(shape=shape, hx=h[0], hy=h[1], hz=h[2], eta_x=vm.eta_x, eta_y=vm.eta_y,
+             eta_z=vm.eta_z, zeta=vm.zeta, s=s, e=e, grid=g, vm=vm)
+    return d
+
+
+def test_amat_x_golden(core, golden):
+    gk = golden('kernels')
+    for k in range(int(gk['n_cases'])):
+        c = kernel_case(gk, k)
+        r = c['s'].copy()
+        core.amat_x(*split_field(c['shape'], r), *split_field(c['shape'], c['e']), *_margs(c))
+        assert rel_err(r, c['r']) < 1e-13, k
+
+
+def test_amat_x_random_boundaries(core):
+    """Non-zero boundary values of e and s exercise the reference's boundary rules."""
+    rng = np.random.default_rng(11)
+    for shape, cplx in (((9, 7, 5), True), ((33, 6, 10), False), ((40, 37, 35), True)):
+        c = random_case(rng, shape, cplx)
+        e = rng.standard_normal(c['e'].size) + (1j * rng.standard_normal(c['e'].size) if cplx else 0)
+        r1, r2 = c['s'].copy(), c['s'].copy()
+        oracle.amat_x(*split_field(shape, r1), *split_field(shape, e), *_margs(c))
+        core.amat_x(*split_field(shape, r2), *split_field(shape, e), *_margs(c))
+        assert rel_err(r2, r1) < 1e-13
+
+
+@pytest.mark.parametrize('ldir', [0, 1, 2, 3])
+def test_gauss_seidel_lex_golden(core, golden, ldir):
+    gk = golden('kernels')
+    fn = getattr(core, GS[ldir])
+    for k in range(int(gk['n_cases'])):
+        c = kernel_case(gk, k)
+        for nu in (1, 2):
+            e = c['e'].copy()
+            fn(*split_field(c['shape'], e), *split_field(c['shape'], c['s']), *_margs(c), nu,
+               order='lex')
+            assert rel_err(e, gk[c['prefix'] + f'gs{ldir}_nu{nu}']) < 1e-11, (k, nu)
+
+
+# shapes chosen so that both the single-block path (small grids) and the
+# multi-launch path (> 4096 interior nodes / > 1024 lines) are exercised
+BIG = [((24, 20, 18), True), ((6, 40, 36), True), ((38, 5, 37), False), ((36, 35, 4), True),
+       ((12, 11, 9), False)]
+
+
+@pytest.mark.parametrize('ldir', [0, 1, 2, 3])
+@pytest.mark.parametrize('order', ['lex', 'color'])
+def test_gauss_seidel_vs_oracle(core, ldir, order):
+    rng = np.random.default_rng(100 + ldir)
+    fn, ofn = getattr(core, GS[ldir]), getattr(oracle, GS[ldir])
+    for shape, cplx in BIG:
+        c = random_case(rng, shape, cplx, aliased=(shape[0] == 12))
+        for nu in (1, 3):
+            e_gpu, e_cpu = c['e'].copy(), c['e'].copy()
+            fn(*split_field(shape, e_gpu), *split_field(shape, c['s']), *_margs(c), nu, order=order)
+            if order == 'lex':
+                ofn(*split_field(shape, e_cpu), *split_field(shape, c['s']), *_margs(c), nu)
+            else:
+                seq = oracle.color_sequence(ldir, shape, nu)
+                oracle.gs_sequence(ldir, *split_field(shape, e_cpu), *split_field(shape, c['s']),
+                                   *_margs(c), seq)
+            assert rel_err(e_gpu, e_cpu) < 1e-11, (shape, nu)
+
+
+@pytest.mark.parametrize('order', ['lex', 'color'])
+def test_single_block_exactness(core, order):
+    """On a grid with one block a sweep solves the system exactly (residual ~ 0)."""
+    rng = np.random.default_rng(7)
+    for ldir, shape in ((0, (2, 2, 2)), (1, (7, 2, 2)), (2, (2, 6, 2)), (3, (2, 2, 5))):
+        c = random_case(rng, shape, True)
+        e = np.zeros_like(c['e'])
+        getattr(core, GS[ldir])(*split_field(shape, e), *split_field(shape, c['s']), *_margs(c), 1,
+                                order=order)
+        r = c['s'].copy()
+        core.amat_x(*split_field(shape, r), *split_field(shape, e), *_margs(c))
+        # interior residual only: boundary edges keep r = s
+        rx, ry, rz = split_field(shape, r)
+        inner = np.r_[rx[:, 1:-1, 1:-1].ravel(), ry[1:-1, :, 1:-1].ravel(), rz[1:-1, 1:-1, :].ravel()]
+        assert np.linalg.norm(inner) < 1e-12 * np.linalg.norm(c['s'])
+
+
+def test_line_equals_point_on_degenerate_grids(core):
+    """With a single interior node along the line a line sweep is a point sweep
+    (the reference's own test of the line smoothers, tests/test_core.py:88-139)."""
+    rng = np.random.default_rng(8)
+    for ldir, shape in ((1, (2, 8, 8)), (2, (8, 2, 8)), (3, (8, 8, 2))):
+        c = random_case(rng, shape, True)
+        e0, e1 = c['e'].copy(), c['e'].copy()
+        core.gauss_seidel(*split_field(shape, e0), *split_field(shape, c['s']), *_margs(c), 2,
+                          order='lex')
+        getattr(core, GS[ldir])(*split_field(shape, e1), *split_field(shape, c['s']), *_margs(c), 2,
+                                order='lex')
+        assert rel_err(e1, e0) < 1e-10
+
+
+def test_determinism(core):
+    rng = np.random.default_rng(9)
+    c = random_case(rng, (24, 20, 18), True)
+    outs = []
+    for _ in range(2):
+        e = c['e'].copy()
+        core.gauss_seidel(*split_field(c['shape'], e), *split_field(c['shape'], c['s']), *_margs(c),
+                          2, order='color')
+        core.gauss_seidel_y(*split_field(c['shape'], e), *split_field(c['shape'], c['s']), *_margs(c),
+                            2, order='color')
+        outs.append(e)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_band_solve(core):
+    rng = np.random.default_rng(5)
+    for n, cplx in ((6, False), (6, True), (41, True), (1, True), (3, False), (636, True)):
+        A = np.zeros((n, n), dtype=complex if cplx else float)
+        for i in range(n):
+            for j in range(max(0, i - 5), i + 1):
+                A[i, j] = A[j, i] = rng.standard_normal() + (1j * rng.standard_normal() if cplx else 0)
+            A[i, i] += 10
+        b = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+        amat = np.zeros(6 * n, dtype=A.dtype)
+        for j in range(n):
+            for i in range(j, min(n, j + 6)):
+                amat[i + 5 * j] = A[i, j]
+        a_o, x_o = amat.copy(), b.copy()
+        oracle.solve(a_o, x_o)
+        x = b.copy()
+        core.solve(amat, x)
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-10)
+        np.testing.assert_allclose(x, x_o, rtol=1e-10)
+        np.testing.assert_allclose(amat, a_o, rtol=1e-10, atol=1e-14)
+
+
+def test_restrict_golden(core, golden):
+    gt = golden('transfer')
+    for k in range(int(gt['n_cases'])):
+        p = f"t{k}_"
+        shape = tuple(gt[p + n].size for n in ('hx', 'hy', 'hz'))
+        for sc in gt[p + 'sc_dirs']:
+            q = p + f"sc{sc}_"
+            fl = core.SC_FLAGS[int(sc)]
+            cshape = tuple(n // 2 if f else n for n, f in zip(shape, fl))
+            cs = np.zeros_like(gt[q + 'cs'])
+            w = [tuple(gt[q + f'w{a}']) for a in 'xyz']
+            core.restrict(*split_field(cshape, cs), *split_field(shape, gt[p + 'r'].copy()), *w, sc)
+            assert rel_err(cs, gt[q + 'cs']) < 1e-13, (k, sc)
+
+
+def test_solver_wrappers_golden(golden):
+    """restriction / prolongation / residual / smoothing wrappers on host containers."""
+    import emg3d_b200 as eb
+    from emg3d_b200 import solver
+    gt = golden('transfer')
+    for k in range(int(gt['n_cases'])):
+        p = f"t{k}_"
+        grid = eb.TensorMesh([gt[p + 'hx'], gt[p + 'hy'], gt[p + 'hz']], gt[p + 'origin'])
+        dt = gt[p + 'r'].dtype
+        freq = 1.3 if dt.kind == 'c' else -1.3
+
+        class VM:
+            pass
+        vm = VM()
+        vm.grid, vm.case = grid, 'triaxial'
+        vm.eta_x, vm.eta_y, vm.eta_z, vm.zeta = (np.asfortranarray(gt[p + n]) for n in
+                                                 ('eta_x', 'eta_y', 'eta_z', 'zeta'))
+        sfield = eb.Field(grid, gt[p + 'e'].copy(), frequency=freq)
+        rfield = eb.Field(grid, gt[p + 'r'].copy(), frequency=freq)
+        for sc in gt[p + 'sc_dirs']:
+            q = p + f"sc{sc}_"
+            cm, cs, ce = solver.restriction(vm, sfield, rfield, int(sc))
+            assert rel_err(cs.field, gt[q + 'cs']) < 1e-13
+            assert np.all(ce.field == 0)
+            for n in ('eta_x', 'eta_y', 'eta_z', 'zeta'):
+                assert rel_err(getattr(cm, n), gt[q + 'c' + n]) < 1e-15, (k, sc, n)
+            assert cm.grid.shape_cells == tuple(
+                m // 2 if f else m for m, f in zip(grid.shape_cells, core_flags(sc)))
+            ce.field[:] = gt[q + 'ce']
+            e1 = sfield.copy()
+            solver.prolongation(e1, ce, int(sc))
+            assert rel_err(e1.field, gt[q + 'e_out']) < 1e-14, (k, sc)
+            np.testing.assert_allclose(
+                solver._restrict_model_parameters(vm.zeta, int(sc)), gt[q + 'czeta'], rtol=1e-15)
+
+
+def core_flags(sc):
+    from emg3d_b200 import core
+    return core.SC_FLAGS[int(sc)]
+
+
+def test_residual_and_smoothing_wrappers(golden):
+    import emg3d_b200 as eb
+    from emg3d_b200 import solver
+    gk = golden('kernels')
+    for k in range(int(gk['n_cases'])):
+        c = kernel_case(gk, k)
+        grid = eb.TensorMesh([c['hx'], c['hy'], c['hz']], (0, 0, 0))
+        freq = 1.3 if c['s'].dtype.kind == 'c' else -1.3
+
+        class VM:
+            pass
+        vm = VM()
+        vm.grid, vm.case = grid, 'triaxial'
+        vm.eta_x, vm.eta_y, vm.eta_z, vm.zeta = c['eta_x'], c['eta_y'], c['eta_z'], c['zeta']
+        s = eb.Field(grid, c['s'].copy(), frequency=freq)
+        e = eb.Field(grid, c['e'].copy(), frequency=freq)
+        r = solver.residual(vm, s, e)
+        assert rel_err(r.field, c['r']) < 1e-13
+        nrm = solver.residual(vm, s, e, norm=True)
+        assert abs(nrm - np.linalg.norm(c['r'])) < 1e-13 * np.linalg.norm(c['r'])
+        # lr_dir dispatch incl. dropping 2-cell directions (solver.py:1534-1588)
+        for lr_dir in range(8):
+            e1 = e.copy()
+            solver.smoothing(vm, s, e1, 2, lr_dir, order='lex')
+            e2 = c['e'].copy()
+            g = mg.Grid([c['hx'], c['hy'], c['hz']])
+            ovm = mg.VolumeModel.from_arrays(g, c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'])
+            mg.smoothing(ovm, c['s'], e2, 2, lr_dir)
+            assert rel_err(e1.field, e2) < 1e-11, (k, lr_dir)

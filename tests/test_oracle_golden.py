@@ -1,0 +1,127 @@
+"""Pin the CPU oracle (oracle/) against golden vectors produced by the reference.
+
+Tolerances are norm-wise relative errors.  The reference's numba kernels run
+with fastmath (reassociation, contraction), the oracle is plain C with a
+different but algebraically identical summation order, so agreement is to
+rounding: <= 1e-12 for single kernel calls on these well-conditioned models.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import mg
+from conftest import rel_err
+from helpers import kernel_case, solve_case, split_field
+
+KTOL = 1e-12
+
+
+def test_amat_x(golden):
+    gk = golden('kernels')
+    for k in range(int(gk['n_cases'])):
+        c = kernel_case(gk, k)
+        r = c['s'].copy()
+        oracle.amat_x(*split_field(c['shape'], r), *split_field(c['shape'], c['e']),
+                      c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'], c['hx'], c['hy'], c['hz'])
+        assert rel_err(r, c['r']) < 1e-14
+
+
+@pytest.mark.parametrize('ldir', [0, 1, 2, 3])
+def test_gauss_seidel(golden, ldir):
+    gk = golden('kernels')
+    fn = [oracle.gauss_seidel, oracle.gauss_seidel_x, oracle.gauss_seidel_y,
+          oracle.gauss_seidel_z][ldir]
+    for k in range(int(gk['n_cases'])):
+        c = kernel_case(gk, k)
+        for nu in (1, 2):
+            e = c['e'].copy()
+            fn(*split_field(c['shape'], e), *split_field(c['shape'], c['s']),
+               c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'], c['hx'], c['hy'], c['hz'], nu)
+            assert rel_err(e, gk[c['prefix'] + f'gs{ldir}_nu{nu}']) < KTOL
+
+
+def test_solve_known_answer():
+    # band LDL^T against a dense solve (the reference tests do the same,
+    # tests/test_core.py:203-262), real and complex, n = 6 and a long band
+    rng = np.random.default_rng(5)
+    for n, cplx in ((6, False), (6, True), (41, True), (1, True), (3, False)):
+        A = np.zeros((n, n), dtype=complex if cplx else float)
+        for i in range(n):
+            for j in range(max(0, i - 5), i + 1):
+                v = rng.standard_normal() + (1j * rng.standard_normal() if cplx else 0)
+                A[i, j] = A[j, i] = v
+            A[i, i] += 10
+        b = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+        amat = np.zeros(6 * n, dtype=A.dtype)
+        for j in range(n):
+            for i in range(j, min(n, j + 6)):
+                amat[i + 5 * j] = A[i, j]
+        x = b.copy()
+        oracle.solve(amat, x)
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-11)
+
+
+def test_transfer(golden):
+    gt = golden('transfer')
+    for k in range(int(gt['n_cases'])):
+        p = f"t{k}_"
+        h = [gt[p + 'hx'], gt[p + 'hy'], gt[p + 'hz']]
+        shape = tuple(a.size for a in h)
+        g = mg.Grid(h, gt[p + 'origin'])
+        for sc in gt[p + 'sc_dirs']:
+            q = p + f"sc{sc}_"
+            vm = mg.VolumeModel.from_arrays(
+                g, *(np.asfortranarray(gt[p + n]) for n in ('eta_x', 'eta_y', 'eta_z', 'zeta')))
+            cvm, cs, _ = mg.restriction(vm, gt[p + 'r'].copy(), sc)
+            assert rel_err(cs, gt[q + 'cs']) < 1e-14
+            for n, arr in (('ceta_x', cvm.eta_x), ('ceta_y', cvm.eta_y),
+                           ('ceta_z', cvm.eta_z), ('czeta', cvm.zeta)):
+                assert rel_err(arr, gt[q + n]) < 1e-15
+            # weights (dummy ones where the axis is not coarsened)
+            fl = oracle.SC_FLAGS[int(sc)]
+            for a, ax in enumerate('xyz'):
+                if fl[a]:
+                    w = oracle.restrict_weights(g.nodes[a], g.centers[a], g.h[a],
+                                                cvm.grid.nodes[a], cvm.grid.centers[a],
+                                                cvm.grid.h[a])
+                    np.testing.assert_allclose(np.array(w), gt[q + f'w{ax}'], rtol=1e-12, atol=1e-14)
+            e = gt[p + 'e'].copy()
+            mg.prolongation(g, e, cvm.grid, gt[q + 'ce'].copy(), sc)
+            assert rel_err(e, gt[q + 'e_out']) < 1e-15
+        assert shape == g.shape_cells
+
+
+def _oracle_solve(c, **extra):
+    g = mg.Grid([c['hx'], c['hy'], c['hz']], c['origin'])
+    m = c['model']
+    vm = mg.VolumeModel(g, m['property_x'], m.get('property_y'), m.get('property_z'),
+                        m.get('mu_r'), m.get('epsilon_r'), c['frequency'])
+    kw = {k: v for k, v in c['kwargs'].items() if k not in ('verb', 'plain')}
+    if c['kwargs'].get('plain'):
+        kw.setdefault('sslsolver', False)
+        kw.setdefault('semicoarsening', False)
+        kw.setdefault('linerelaxation', False)
+    else:
+        kw.setdefault('sslsolver', True)
+        kw.setdefault('semicoarsening', True)
+        kw.setdefault('linerelaxation', True)
+    kw.update(extra)
+    return mg.solve(vm, c['sfield'].copy(), **kw)
+
+
+@pytest.mark.parametrize('prefix', ['res_F_', 'res_W_', 'res_V_', 'res_bic_', 'reg2_',
+                                    'lap_F_', 'lap_bic_', 'config1_', 'config5_'])
+def test_solves(golden, prefix):
+    """Full solves: same iteration counts, per-cycle errors and fields."""
+    c = solve_case(golden('solves'), prefix)
+    e, info = _oracle_solve(c)
+    assert info['it_mg'] == c['it_mg']
+    assert info['it_ssl'] == c['it_ssl']
+    assert info['exit_message'] == c['exit_message']
+    np.testing.assert_allclose(info['error_at_cycle'] / c['ref_error'],
+                               c['error_at_cycle'] / c['ref_error'], rtol=1e-6, atol=1e-12)
+    assert rel_err(e, c['efield']) < 1e-9
+    if prefix + 'regression' in golden('solves').files:
+        # the reference's own regression data (tests/data/regression.npz)
+        np.testing.assert_allclose(e, golden('solves')[prefix + 'regression'],
+                                   rtol=1e-6, atol=1e-14 * np.abs(c['efield']).max() + 1e-30)
