@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the emg3d multigrid hot path on B200 (contract: see DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): cells x smoother-sweeps per second on a 256^3 V-cycle,
+next to the achieved HBM GB/s of the dominant kernel against the measured peak.
+
+A "step" is one plain V(2,2) multigrid cycle (nu_coarse = 1) on the 256^3
+marine CSEM model of BASELINE.json configs[2] (air / sea / VTI sediment /
+resistor, stretched grid, 1 Hz x-dipole), inputs resident in HBM.  The work of a
+step is  W = sum over levels of cells(level) x sweeps(level) = 76 695 816
+cell-sweeps.  ``e2e`` times the public call
+``emg3d_b200.solve(model, sfield, plain=True, cycle='V', maxit=1)`` with host
+buffers (pinned source/field buffers), host<->device copies included.
+
+``--impl reference`` times the CPU implementation of the same cycle (the oracle
+port, one independent cycle per host core like the reference's process pool) on
+a bounded sample (64^3 sibling of the same model).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
+
+METRIC = "cell_smoother_sweeps_per_s_256cube_Vcycle"
+UNIT = "cell-sweeps/s"
+
+
+def vcycle_work(shape, nu_pre=2, nu_post=2, nu_coarse=1):
+    """W of one plain V-cycle: cells x sweeps summed over the levels."""
+    n = list(shape)
+    work = 0
+    while True:
+        cells = n[0] * n[1] * n[2]
+        if any(m % 2 or m <= 2 for m in n):
+            # coarsest reachable grid (standard coarsening halves all axes together)
+            work += cells * nu_coarse
+            break
+        work += cells * (nu_pre + nu_post)
+        n = [m // 2 for m in n]
+    return work
+
+
+def peaks():
+    fn = os.path.join(HERE, 'MEASURED_PEAKS.json')
+    if os.path.exists(fn):
+        with open(fn) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (rank 0)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.device}', f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_inputs(n):
+    import emg3d_b200 as eb
+    from emg3d_b200 import recipes
+    cfg = recipes.config('config3', n)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    sfield = eb.get_source_field(grid, cfg['source'], cfg['frequency'])
+    return cfg, grid, model, sfield
+
+
+# --------------------------------------------------------------------------- #
+# CPU legs (oracle port)
+# --------------------------------------------------------------------------- #
+
+def _cpu_cycle(n):
+    """One plain V(2,2)-cycle of the oracle on the n^3 sibling; returns (W, seconds)."""
+    from oracle import mg
+    from emg3d_b200 import recipes
+    import emg3d_b200 as eb
+    cfg = recipes.config('config3', n)
+    g = mg.Grid(cfg['h'], cfg['origin'])
+    m = cfg['model']
+    vm = mg.VolumeModel(g, m['property_x'], None, m['property_z'], None, None, cfg['frequency'])
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    s = np.asarray(eb.get_source_field(grid, cfg['source'], cfg['frequency']).field)
+    t0 = time.perf_counter()
+    _, info = mg.solve(vm, s.copy(), cycle='V', maxit=1)
+    return info['cell_sweeps'], time.perf_counter() - t0
+
+
+def cpu_baseline(n=128):
+    import oracle
+    oracle.build()
+    _cpu_cycle(16)                                   # warm-up (library load)
+    work, sec = _cpu_cycle(n)
+    return {"value": work / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"one plain V(2,2)-cycle of the C oracle on the {n}^3 sibling of the "
+                      f"workload ({work} cell-sweeps, {sec:.1f} s, 1 thread)"}
+
+
+def run_reference(args):
+    """--impl reference: CPU implementation on all host cores, bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n = 64
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_cycle, [32] * cores)
+        t0 = time.perf_counter()
+        work = 0
+        for _ in range(args.steps):
+            res = pool.map(_cpu_cycle, [n] * cores)
+            work += sum(r[0] for r in res)
+        sec = time.perf_counter() - t0
+    value = work / sec
+    sample = (f"{cores} concurrent independent plain V(2,2)-cycles (one per host core, the "
+              f"reference's process-pool mode) of the C oracle port on the {n}^3 sibling of "
+              f"the workload, {args.steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "plain V(2,2) multigrid cycle, marine CSEM model "
+                               "(BASELINE.json configs[2]); CPU arm sampled at 64^3"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# GPU arm
+# --------------------------------------------------------------------------- #
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--size', type=int, default=256, help='cells per axis (256 = the metric)')
+    ap.add_argument('--order', default='color', choices=['color', 'lex'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    import emg3d_b200 as eb
+    from emg3d_b200 import _lib, solver
+    _lib.init(local_rank)
+
+    def barrier():
+        _lib.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.size
+    cfg, grid, model, sfield = build_inputs(n)
+    work = vcycle_work(grid.shape_cells)
+    vmodel = eb.VolumeModel(model, sfield)
+    level = solver._Level.from_volume_model(vmodel, sfield.field.dtype)
+    d_s = _lib.DeviceArray.from_host(sfield.field)
+    d_e = level.new_field()
+    kw = dict(verb=0, sslsolver=False, semicoarsening=False, linerelaxation=False,
+              shape_cells=grid.shape_cells, cycle='V', maxit=1)
+
+    def step():
+        var = solver.MGParameters(**kw)
+        var.order = args.order
+        var.l2_refe = 1.0
+        d_e.zero()
+        solver._multigrid(level, d_s, d_e, var)
+        return var
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    n0 = _lib.launch_count()
+    ev0, ev1 = _lib.Event(), _lib.Event()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_ms(ev1))
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    value = world * work * args.steps / (ms * 1e-3)
+
+    # --- dominant kernel: the point smoother on the finest grid -------------------
+    # nu = 2 sweeps = 16 colour launches; algorithmic bytes per cell-sweep: E read +
+    # write 96, S 48, eta 16 per distinct array, zeta 8.
+    n_eta = len({id(a) for a in level.eta})
+    bytes_per_cell_sweep = 96 + 48 + 16 * n_eta + 8
+    reps = 5
+    lib = _lib.load()
+    order = solver.core.order_id(args.order)
+    for _ in range(2):
+        _lib.check(lib.emg3d_b200_gauss_seidel(level.handle.ptr, d_e.ptr, d_s.ptr, 2, 0, order))
+    k0, k1 = _lib.Event(), _lib.Event()
+    l0 = _lib.launch_count()
+    k0.record()
+    for _ in range(reps):
+        _lib.check(lib.emg3d_b200_gauss_seidel(level.handle.ptr, d_e.ptr, d_s.ptr, 2, 0, order))
+    k1.record()
+    kms = k0.elapsed_ms(k1)
+    klaunch = _lib.launch_count() - l0
+    cells = grid.n_cells
+    peak, peak_src = peaks()
+    bytes_per_launch = bytes_per_cell_sweep * cells * 2 * reps / klaunch
+    achieved = bytes_per_launch / (kms * 1e-3 / klaunch) / 1e9
+    roofline = {"bound": "hbm", "kernel": "gs_point_color_kernel (finest grid)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": None,
+                "bytes_per_cell_sweep": bytes_per_cell_sweep,
+                "launch_ms": kms / klaunch,
+                "cell_sweeps_per_s": cells * 2 * reps / (kms * 1e-3)}
+
+    # --- other hot kernels on the finest grid (same accounting) -------------------
+    kernels = {}
+
+    def time_call(fn, nrep=3):
+        fn()
+        a, b = _lib.Event(), _lib.Event()
+        a.record()
+        for _ in range(nrep):
+            fn()
+        b.record()
+        return a.elapsed_ms(b) / nrep
+
+    if rank == 0:
+        for ldir, name in ((1, 'gauss_seidel_x'), (2, 'gauss_seidel_y'), (3, 'gauss_seidel_z')):
+            try:
+                t = time_call(lambda: _lib.check(lib.emg3d_b200_gauss_seidel(
+                    level.handle.ptr, d_e.ptr, d_s.ptr, 2, ldir, order)))
+                gbs = bytes_per_cell_sweep * cells * 2 / (t * 1e-3) / 1e9
+                kernels[name] = {"ms_nu2": t, "cell_sweeps_per_s": cells * 2 / (t * 1e-3),
+                                 "algorithmic_GBs": gbs, "frac": gbs / peak}
+            finally:
+                level.handle.drop_factors()
+        r = level.res_buffer()
+        t = time_call(lambda: _lib.check(lib.emg3d_b200_residual(
+            level.handle.ptr, d_s.ptr, d_e.ptr, r.ptr, None)))
+        gbs = (bytes_per_cell_sweep + 0) * cells / (t * 1e-3) / 1e9
+        kernels['residual'] = {"ms": t, "cells_per_s": cells / (t * 1e-3),
+                               "algorithmic_GBs": gbs, "frac": gbs / peak}
+
+    # --- end to end through the public API with host buffers ----------------------
+    e2e = None
+    if not args.no_e2e:
+        pin_s = _lib.PinnedArray(sfield.field.size, sfield.field.dtype)
+        pin_s.array[:] = sfield.field
+        pin_e = _lib.PinnedArray(sfield.field.size, sfield.field.dtype)
+        h_s = eb.Field(grid, pin_s.array, frequency=cfg['frequency'])
+        nst = max(1, min(args.steps, 3))
+        h2d = (sum(level.eta[i].nbytes for i in range(3)
+                   if all(level.eta[i] is not level.eta[j] for j in range(i))) +
+               level.zeta.nbytes + d_s.nbytes + d_s.nbytes)
+        d2h = d_s.nbytes
+        del d_e, d_s, level       # the public call allocates its own device buffers
+        eb.solve(model, h_s, plain=True, cycle='V', maxit=1, order=args.order, verb=-1,
+                 efield=eb.Field(grid, pin_e.array, frequency=cfg['frequency']))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            pin_e.array[:] = 0
+            eb.solve(model, h_s, plain=True, cycle='V', maxit=1, order=args.order, verb=-1,
+                     efield=eb.Field(grid, pin_e.array, frequency=cfg['frequency']))
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * work * nst / sec, "unit": UNIT, "steps": nst,
+               "ms_per_step": 1e3 * sec / nst, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h),
+               "call": "emg3d_b200.solve(model, sfield, plain=True, cycle='V', maxit=1, efield=...)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(128 if n >= 128 else n)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"plain V(2,2) multigrid cycle (nu_coarse=1) on the {n}^3 marine "
+                                   "CSEM model of BASELINE.json configs[2], complex128, VTI; "
+                                   f"{work} cell-sweeps per step",
+                       "order": args.order, "cells": int(cells), "cell_sweeps_per_step": int(work),
+                       "l2": "working set 3.2 GB per step, far larger than the 126 MB L2",
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"{world} independent replicas (one solve per GPU, the "
+                                       "reference's own parallel mode)")},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "device": _lib.device_name(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

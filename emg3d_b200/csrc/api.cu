@@ -225,7 +225,7 @@ int emg3d_b200_graph_destroy(void* graph_exec) {
 int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz, const double* hx,
                             const double* hy, const double* hz) {
     NEED_INIT();
-    if (nx < 2 || ny < 2 || nz < 2) return fail_msg("level_create: need at least 2 cells per axis");
+    if (nx < 1 || ny < 1 || nz < 1) return fail_msg("level_create: need at least 1 cell per axis");
     emg3d_b200_level* lv = new emg3d_b200_level();
     memset(lv, 0, sizeof *lv);
     lv->d.n[0] = nx; lv->d.n[1] = ny; lv->d.n[2] = nz;

@@ -23,6 +23,55 @@
 
 namespace emg {
 
+#define A(r, c) a[((r) * ((r) + 1)) / 2 + (c)]
+
+// Contribution of the face in plane (P, Q), quadrant (SP, SQ) of the node, to the
+// packed node matrix a and right-hand side b.  All indices are template
+// parameters so that a and b stay in registers.
+template <typename T>
+struct Faces {
+    template <int P, int Q, int SP, int SQ>
+    static __device__ __forceinline__ void quad(const FieldView<T>& E, int ix, int iy, int iz,
+                                                const double (&z)[2][2][2], const double (&rh)[3][2],
+                                                T (&a)[21], T (&b)[6]) {
+        constexpr int W = 3 - P - Q;
+        // cells of this face: P-index 1-SP, Q-index 1-SQ, both W-indices
+        constexpr int i0x = P == 0 ? 1 - SP : Q == 0 ? 1 - SQ : 0;
+        constexpr int i0y = P == 1 ? 1 - SP : Q == 1 ? 1 - SQ : 0;
+        constexpr int i0z = P == 2 ? 1 - SP : Q == 2 ? 1 - SQ : 0;
+        constexpr int i1x = W == 0 ? 1 : i0x, i1y = W == 1 ? 1 : i0y, i1z = W == 2 ? 1 : i0z;
+        const double g = 0.5 * (z[i0x][i0y][i0z] + z[i1x][i1y][i1z]);
+        const double rp = rh[P][1 - SP], rq = rh[Q][1 - SQ];
+        const double al_p = SQ ? -rq : rq;   // stencil entry of the local P-edge
+        const double al_q = SP ? rp : -rp;   // stencil entry of the local Q-edge
+        // outer P-edge: same P-cell, Q-node moved away from the node
+        int qo[3] = {ix, iy, iz};
+        qo[P] -= SP;
+        qo[Q] += SQ ? -1 : 1;
+        const T ep = E.p[P][E.idx(P, qo)];
+        int ro[3] = {ix, iy, iz};
+        ro[Q] -= SQ;
+        ro[P] += SP ? -1 : 1;
+        const T eq = E.p[Q][E.idx(Q, ro)];
+        const T out = al_p * ep + al_q * eq;   // = -(c_out . e_out)
+        constexpr int lp = 2 * P + (1 - SP), lq = 2 * Q + (1 - SQ);   // lq > lp
+        add_real(A(lp, lp), g * al_p * al_p);
+        add_real(A(lq, lq), g * al_q * al_q);
+        add_real(A(lq, lp), g * al_p * al_q);
+        b[lp] += (g * al_p) * out;
+        b[lq] += (g * al_q) * out;
+    }
+    template <int P, int Q>
+    static __device__ __forceinline__ void plane(const FieldView<T>& E, int ix, int iy, int iz,
+                                                 const double (&z)[2][2][2], const double (&rh)[3][2],
+                                                 T (&a)[21], T (&b)[6]) {
+        quad<P, Q, 0, 0>(E, ix, iy, iz, z, rh, a, b);
+        quad<P, Q, 0, 1>(E, ix, iy, iz, z, rh, a, b);
+        quad<P, Q, 1, 0>(E, ix, iy, iz, z, rh, a, b);
+        quad<P, Q, 1, 1>(E, ix, iy, iz, z, rh, a, b);
+    }
+};
+
 template <typename T>
 __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T>& E,
                                             const FieldView<const T>& S, int ix, int iy, int iz) {
@@ -46,14 +95,11 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
 #pragma unroll
             for (int k = 0; k < 2; ++k) z[i][j][k] = ldg(m.zeta + c0 + i + cs[1] * j + cs[2] * k);
 
-    // packed lower triangle, a[r][c], r >= c
-    T a[6][6];
+    // packed lower triangle: A(r, c), r >= c
+    T a[21];
     T b[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-#pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = zero_<T>();
-    }
+    for (int r = 0; r < 21; ++r) a[r] = zero_<T>();
 
     // diagonal: -1/4 sum of eta over the four cells around each local edge; rhs: source
 #pragma unroll
@@ -64,85 +110,61 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
             const int64_t base = c0 + cs[c] * sg;
             T st = ldg(m.eta[c] + base) + ldg(m.eta[c] + base + cs[u]) +
                    ldg(m.eta[c] + base + cs[v]) + ldg(m.eta[c] + base + cs[u] + cs[v]);
-            a[2 * c + sg][2 * c + sg] = -0.25 * st;
+            A(2 * c + sg, 2 * c + sg) = -0.25 * st;
             int q[3] = {ix, iy, iz};
             q[c] += sg - 1;
             b[2 * c + sg] = ldg(S.p[c] + S.idx(c, q));
         }
     }
 
-    // the three coordinate planes (p, q), four quadrants each
-#pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
-        const int p = pl == 2 ? 1 : 0, q = pl == 0 ? 1 : 2, w = 3 - p - q;
-#pragma unroll
-        for (int sp = 0; sp < 2; ++sp) {
-#pragma unroll
-            for (int sq = 0; sq < 2; ++sq) {
-                // cells of this face: p-index 1-sp, q-index 1-sq, both w-indices
-                int i0[3], i1[3];
-                i0[p] = i1[p] = 1 - sp;
-                i0[q] = i1[q] = 1 - sq;
-                i0[w] = 0;
-                i1[w] = 1;
-                const double g = 0.5 * (z[i0[0]][i0[1]][i0[2]] + z[i1[0]][i1[1]][i1[2]]);
-                const double rp = rh[p][1 - sp], rq = rh[q][1 - sq];
-                const double al_p = sq ? -rq : rq;   // entry of the local p-edge
-                const double al_q = sp ? rp : -rp;   // entry of the local q-edge
-                // outer p-edge: same p-cell, q-node moved away from the node
-                int qo[3] = {ix, iy, iz};
-                qo[p] -= sp;
-                qo[q] += sq ? -1 : 1;
-                const T ep = E.p[p][E.idx(p, qo)];
-                int ro[3] = {ix, iy, iz};
-                ro[q] -= sq;
-                ro[p] += sp ? -1 : 1;
-                const T eq = E.p[q][E.idx(q, ro)];
-                const T out = al_p * ep + al_q * eq;   // = -(c_out . e_out)
-                const int lp = 2 * p + (1 - sp), lq = 2 * q + (1 - sq);
-                add_real(a[lp][lp], g * al_p * al_p);
-                add_real(a[lq][lq], g * al_q * al_q);
-                add_real(a[lq][lp], g * al_p * al_q);   // lq > lp always
-                b[lp] += (g * al_p) * out;
-                b[lq] += (g * al_q) * out;
-            }
-        }
-    }
+    // the three coordinate planes (p, q), four quadrants each (compile-time indices)
+    Faces<T>::template plane<0, 1>(E, ix, iy, iz, z, rh, a, b);
+    Faces<T>::template plane<0, 2>(E, ix, iy, iz, z, rh, a, b);
+    Faces<T>::template plane<1, 2>(E, ix, iy, iz, z, rh, a, b);
 
     // LDL^T without pivoting, unknown order 0..5 (emg3d/core.py:1481-1616), then
-    // forward substitution, diagonal scaling, backward substitution.
+    // forward substitution, diagonal scaling, backward substitution.  All loops
+    // run over the full range with compile-time guards so that they unroll
+    // completely and the matrix stays in registers.
     T dinv[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         T v[6];
-        T dj = a[j][j];
+        T dj = A(j, j);
 #pragma unroll
-        for (int k = 0; k < j; ++k) {
-            v[k] = a[j][k] * a[k][k];          // L(j,k) D(k); a[k][k] holds D(k)
-            dj -= a[j][k] * v[k];
+        for (int k = 0; k < 6; ++k) {
+            if (k < j) {
+                v[k] = A(j, k) * A(k, k);      // L(j,k) D(k); A(k, k) holds D(k)
+                dj -= A(j, k) * v[k];
+            }
         }
-        a[j][j] = dj;
+        A(j, j) = dj;
         const T r = rcp(dj);
         dinv[j] = r;
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            T t = a[i][j];
+        for (int i = 0; i < 6; ++i) {
+            if (i > j) {
+                T t = A(i, j);
 #pragma unroll
-            for (int k = 0; k < j; ++k) t -= a[i][k] * v[k];
-            a[i][j] = t * r;
+                for (int k = 0; k < 6; ++k)
+                    if (k < j) t -= A(i, k) * v[k];
+                A(i, j) = t * r;
+            }
         }
     }
 #pragma unroll
     for (int j = 1; j < 6; ++j) {
 #pragma unroll
-        for (int k = 0; k < j; ++k) b[j] -= a[j][k] * b[k];
+        for (int k = 0; k < 6; ++k)
+            if (k < j) b[j] -= A(j, k) * b[k];
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j) b[j] = b[j] * dinv[j];
 #pragma unroll
     for (int j = 4; j >= 0; --j) {
 #pragma unroll
-        for (int k = j + 1; k < 6; ++k) b[j] -= a[k][j] * b[k];
+        for (int k = 0; k < 6; ++k)
+            if (k > j) b[j] -= A(k, j) * b[k];
     }
 
 #pragma unroll
@@ -157,6 +179,8 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
 }
 
 
+#undef A
+
 // ---- schedules ---------------------------------------------------------------
 
 // one parity class: ix = fx + 2 i, iy = fy + 2 j, iz = fz + 2 k
@@ -170,6 +194,36 @@ gs_point_color_kernel(Model<T> m, T* e, const T* s, int fx, int fy, int fz, int 
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
     node_update<T>(m, E, S, fx + 2 * i, fy + 2 * j, fz + 2 * k);
+}
+
+// Tile-fused multicolour sweep for grids that do not fit the L2: the nodes are
+// cut into tiles of TX x TY x TZ nodes; tiles are coloured by the parity of
+// their tile index (8 tile colours, one launch each: tiles of one colour are at
+// least a full tile apart and cannot interact), and one thread block relaxes
+// all 8 node colours of its tile back to back, with a block barrier between
+// colours.  The tile's edges, sources and coefficients are then read from HBM
+// once per sweep instead of once per node colour (the re-reads hit L1/L2).
+constexpr int TX = 16, TY = 8, TZ = 8;
+constexpr int TILE_THREADS = (TX / 2) * (TY / 2) * (TZ / 2);
+
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS)
+gs_point_tile_kernel(Model<T> m, T* e, const T* s, int tcx, int tcy, int tcz, int back) {
+    // tile index of this block within its tile colour
+    const int x0 = 1 + (2 * blockIdx.x + tcx) * TX;
+    const int y0 = 1 + (2 * blockIdx.y + tcy) * TY;
+    const int z0 = 1 + (2 * blockIdx.z + tcz) * TZ;
+    const int t = threadIdx.x;
+    const int i = t % (TX / 2), j = (t / (TX / 2)) % (TY / 2), k = t / ((TX / 2) * (TY / 2));
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = back ? 7 - cc : cc;
+        const int ix = x0 + 2 * i + (c & 1), iy = y0 + 2 * j + ((c >> 1) & 1),
+                  iz = z0 + 2 * k + ((c >> 2) & 1);
+        if (ix < m.d.n[0] && iy < m.d.n[1] && iz < m.d.n[2]) node_update<T>(m, E, S, ix, iy, iz);
+        __syncthreads();   // block-wide visibility of the global stores of this colour
+    }
 }
 
 // one hyperplane ix + 2 iy + 3 iz = t of the lexicographic sweep
@@ -248,6 +302,16 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
             for (int tt = tmin; tt <= tmax; ++tt) {
                 const int t = back ? tmax + tmin - tt : tt;
                 ++g_launch_count; gs_point_front_kernel<T><<<g, b, 0, st>>>(m, e, s, t);
+            }
+        } else if (nint > TILE_MIN_NODES) {
+            const int ntx = (nx - 1 + TX - 1) / TX, nty = (ny - 1 + TY - 1) / TY,
+                      ntz = (nz - 1 + TZ - 1) / TZ;
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = back ? 7 - cc : cc;
+                const int tcx = c & 1, tcy = (c >> 1) & 1, tcz = (c >> 2) & 1;
+                dim3 g((ntx - tcx + 1) / 2, (nty - tcy + 1) / 2, (ntz - tcz + 1) / 2);
+                if (g.x == 0 || g.y == 0 || g.z == 0) continue;
+                ++g_launch_count; gs_point_tile_kernel<T><<<g, TILE_THREADS, 0, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
             }
         } else {
             for (int cc = 0; cc < 8; ++cc) {

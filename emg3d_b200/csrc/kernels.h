@@ -11,6 +11,9 @@ extern long long g_launch_count;   // kernel launches issued (host-side counter)
 // grids with at most this many interior nodes (or lines) are smoothed by one
 // thread block in a single launch
 constexpr int64_t SMALL_GRID_NODES = 4096;
+// point smoother, multicolour order: grids with more interior nodes than this
+// (working set beyond the 126 MB L2) use the tile-fused schedule
+constexpr int64_t TILE_MIN_NODES = 300000;
 
 // r = s - A e (r may be null, r may alias s), or r = A e when apply_only (s unused);
 // optional ||r||^2 into norm2_out[0]

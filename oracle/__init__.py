@@ -184,6 +184,11 @@ def gs_sequence(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy,
        _p(seq), ctypes.c_int(seq.shape[0]))
 
 
+# schedule constants of the CUDA point smoother (csrc/kernels.h, csrc/gs_point.cu)
+TILE = (16, 8, 8)
+TILE_MIN_NODES = 300000
+
+
 def color_sequence(ldir, shape, nu):
     """Block sequence of ``nu`` multicolour sweeps as the CUDA kernels run them.
 
@@ -195,9 +200,28 @@ def color_sequence(ldir, shape, nu):
     """
     rows = []
     back = False
+    tiled = ldir == 0 and (shape[0] - 1) * (shape[1] - 1) * (shape[2] - 1) > TILE_MIN_NODES
     for _ in range(nu):
         back = not back
-        if ldir == 0:
+        if tiled:
+            # large grids (csrc/gs_point.cu, tile-fused schedule): tiles of
+            # TILE nodes coloured by tile-index parity; per tile colour every
+            # tile runs its 8 node colours; both orders reverse on odd sweeps
+            nx, ny, nz = shape
+            tx, ty, tz = TILE
+            ntile = [-(-(n - 1) // t) for n, t in zip(shape, TILE)]
+            classes = list(range(7, -1, -1) if back else range(8))
+            for tc in classes:
+                for c in classes:
+                    px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+                    for kz in range((tc >> 2) & 1, ntile[2], 2):
+                        for ky in range((tc >> 1) & 1, ntile[1], 2):
+                            for kx in range(tc & 1, ntile[0], 2):
+                                for iz in range(1 + kz * tz + pz, min(nz, 1 + (kz + 1) * tz), 2):
+                                    for iy in range(1 + ky * ty + py, min(ny, 1 + (ky + 1) * ty), 2):
+                                        for ix in range(1 + kx * tx + px, min(nx, 1 + (kx + 1) * tx), 2):
+                                            rows.append((ix, iy, iz))
+        elif ldir == 0:
             nx, ny, nz = shape
             classes = range(7, -1, -1) if back else range(8)
             for c in classes:
