@@ -30,29 +30,46 @@
 
 namespace emg {
 
+constexpr int LINE_STAGES = 4;   // factor blocks in flight per line (cp.async ring)
+
 template <int D> struct Ax {
     static constexpr int d = D;
     static constexpr int p = (D == 0) ? 1 : 0;
     static constexpr int q = (D == 2) ? 1 : 2;
 };
 
-// colour-major slot of line (tp, tq) in the factor array
+// Factor layout.  Lines are numbered colour-major ("slot"): the four parity
+// classes one after the other, each padded to a multiple of 32 lines, and
+// within a class p fastest.  A warp of the colour kernel therefore owns one
+// aligned group of 32 consecutive slots, and the factors are stored
+//     [group][block i][entry e][lane]          (32 lanes, 15 entries, N blocks)
+// so that a warp reads ONE contiguous 15*32*sizeof(T) chunk per block and walks
+// through HBM sequentially from block to block.
+constexpr int FAC_ES = 32;          // stride between entries of one block
+constexpr int FAC_BS = 15 * 32;     // stride between blocks of one line
+
 struct LineSlots {
-    int na[2], off[4];
-    int64_t nl;
+    int na[2], nb[2], off[4], cnt[4];
+    int64_t nl;                     // padded number of slots
     __host__ __device__ LineSlots() {}
     __host__ __device__ LineSlots(int npi, int nqi) {
         na[0] = (npi + 1) / 2; na[1] = npi / 2;
-        const int nb0 = (nqi + 1) / 2, nb1 = nqi / 2;
-        off[0] = 0;
-        off[1] = na[0] * nb0;
-        off[2] = off[1] + na[1] * nb0;
-        off[3] = off[2] + na[0] * nb1;
-        nl = (int64_t)npi * nqi;
+        nb[0] = (nqi + 1) / 2; nb[1] = nqi / 2;
+        int o = 0;
+        for (int c = 0; c < 4; ++c) {
+            off[c] = o;
+            cnt[c] = na[c & 1] * nb[c >> 1];
+            o += (cnt[c] + 31) / 32 * 32;
+        }
+        nl = o;
     }
     __host__ __device__ __forceinline__ int64_t slot(int tp, int tq) const {
         const int cp = (tp - 1) & 1, cq = (tq - 1) & 1;
         return off[cp + 2 * cq] + ((tp - 1) >> 1) + (int64_t)na[cp] * ((tq - 1) >> 1);
+    }
+    // offset of (block 0, entry 0) of a slot for lines of N blocks
+    __host__ __device__ __forceinline__ int64_t base(int64_t slot, int N) const {
+        return (slot >> 5) * ((int64_t)N * FAC_BS) + (slot & 31);
     }
 };
 
@@ -133,7 +150,7 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
     using A = Ax<D>;
     Line<T, D> ln(m, tp, tq);
     const int N = ln.N;
-    const int64_t slot = ls.slot(tp, tq), nl = ls.nl;
+    T* const fbase = fac + ls.base(ls.slot(tp, tq), N);
 
     double zc[2][2], zn[2][2];
     ln.load_zeta(0, zc);
@@ -235,7 +252,7 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
                 }
             }
         }
-        T* out = fac + ((int64_t)i * 15) * nl + slot;
+        T* out = fbase + (int64_t)i * FAC_BS;
         if (last) {
             out[0] = rcp(S[0][0]);
             break;
@@ -247,9 +264,9 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
 #pragma unroll
             for (int r = 1; r < 5; ++r)
 #pragma unroll
-                for (int c = 0; c < r; ++c) out[(int64_t)(e++) * nl] = S[r][c];
+                for (int c = 0; c < r; ++c) out[(e++) * FAC_ES] = S[r][c];
 #pragma unroll
-            for (int r = 0; r < 5; ++r) out[(int64_t)(10 + r) * nl] = dinv[r];
+            for (int r = 0; r < 5; ++r) out[(10 + r) * FAC_ES] = dinv[r];
         }
         // X = (L4 D4 L4^T)^-1 with L4 = L[1:,1:], D4 = D[1:]
         {
@@ -279,14 +296,246 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
 }
 
 // ---- one line sweep: forward and backward block substitution ----------------
+//
+// What one thread streams per block of its line:
+//   forward  : 15 factor entries, 5 sources, 4 parallel line edges of the next
+//              cell, 8 outer transverse edges of the end faces, 4 zeta
+//   backward : 15 factor entries, the 5 intermediate values it stored, 4 zeta
+// One thread per line leaves one warp per scheduler (16 k lines per colour at
+// 256^3), so nothing hides memory latency unless the loads of later blocks are
+// in flight while the current block is being solved.  `Staged` does that with
+// cp.async (LDGSTS) into a shared-memory ring [stage][word][thread], STAGES
+// blocks ahead, without touching the register file; `Direct` loads on demand
+// (used by the small-grid and hyperplane kernels).
+__device__ __forceinline__ void cp_async(cplx* dst, const cplx* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+constexpr int FWD_WORDS = 32;   // T-words per forward stage: 15 + 5 + 4 + 8
+constexpr int BWD_WORDS = 20;   // 15 + 5
+
+// addresses of everything a line touches
+template <typename T, int D>
+struct LineAddr {
+    using A = Ax<D>;
+    T *ed, *ep, *eq;
+    const T *sdp, *spp, *sqp;
+    const T* fac;             // (block 0, entry 0) of this line
+    int64_t sd, sp, sq;       // element strides along the line
+    int64_t oL, oLn[4], oP[2][3], oQ[2][3];
+
+    __device__ LineAddr(const FieldView<T>& E, const FieldView<const T>& S, const T* fac_,
+                        int tp, int tq) {
+        ed = E.p[A::d]; ep = E.p[A::p]; eq = E.p[A::q];
+        sdp = S.p[A::d]; spp = S.p[A::p]; sqp = S.p[A::q];
+        fac = fac_;
+        sd = D == 0 ? 1 : D == 1 ? E.s1[A::d] : E.s2[A::d];
+        sp = D == 0 ? 1 : D == 1 ? E.s1[A::p] : E.s2[A::p];
+        sq = D == 0 ? 1 : D == 1 ? E.s1[A::q] : E.s2[A::q];
+        int pos[3];
+        pos[A::d] = 0; pos[A::p] = tp; pos[A::q] = tq;
+        oL = E.idx(A::d, pos);
+        pos[A::p] = tp - 1; oLn[0] = E.idx(A::d, pos);
+        pos[A::p] = tp + 1; oLn[1] = E.idx(A::d, pos);
+        pos[A::p] = tp; pos[A::q] = tq - 1; oLn[2] = E.idx(A::d, pos);
+        pos[A::q] = tq + 1; oLn[3] = E.idx(A::d, pos);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                pos[A::d] = 0; pos[A::p] = tp - 1 + j; pos[A::q] = tq - 1 + o;
+                oP[j][o] = E.idx(A::p, pos);     // p-edge in p-cell j at q-node tq-1+o
+                pos[A::p] = tp - 1 + o; pos[A::q] = tq - 1 + j;
+                oQ[j][o] = E.idx(A::q, pos);     // q-edge in q-cell j at p-node tp-1+o
+            }
+    }
+    // source pointers of the forward words 15.. of block j (node m = j+1, cell j+1)
+    __device__ __forceinline__ const T* fwd_src(int w, int j) const {
+        const int m = j + 1;
+        switch (w) {
+            case 15: return sdp + oL + sd * j;
+            case 16: return spp + oP[0][1] + sp * m;
+            case 17: return spp + oP[1][1] + sp * m;
+            case 18: return sqp + oQ[0][1] + sq * m;
+            case 19: return sqp + oQ[1][1] + sq * m;
+            case 20: case 21: case 22: case 23: return ed + oLn[w - 20] + sd * m;
+            case 24: return ep + oP[0][0] + sp * m;   // (jp, jq) = (0, 0)
+            case 25: return ep + oP[0][2] + sp * m;   // (0, 1)
+            case 26: return ep + oP[1][0] + sp * m;   // (1, 0)
+            case 27: return ep + oP[1][2] + sp * m;   // (1, 1)
+            case 28: return eq + oQ[0][0] + sq * m;   // (0, 0)
+            case 29: return eq + oQ[1][0] + sq * m;   // (0, 1): q-cell 1, p-node tp-1
+            case 30: return eq + oQ[0][2] + sq * m;   // (1, 0)
+            default: return eq + oQ[1][2] + sq * m;   // (1, 1)
+        }
+    }
+    __device__ __forceinline__ const T* bwd_src(int w, int i) const {
+        const int m = i + 1;
+        switch (w) {
+            case 15: return ed + oL + sd * i;
+            case 16: return ep + oP[0][1] + sp * m;
+            case 17: return ep + oP[1][1] + sp * m;
+            case 18: return eq + oQ[0][1] + sq * m;
+            default: return eq + oQ[1][1] + sq * m;
+        }
+    }
+};
+
+// Forward words: f15 = w[0..14]; s5 = w[15..19]; en = w[20..23];
+// epo(jp,jq) = w[24 + 2 jp + jq]; eqo(jp,jq) = w[28 + 2 jp + jq].
+template <typename T, int NW>
+struct RegWords {            // words held in registers
+    T v[NW];
+    __device__ __forceinline__ T operator[](int e) const { return v[e]; }
+};
 template <typename T>
-__device__ __forceinline__ void solve5(const T* __restrict__ fp, int64_t nl, T y[5], bool first_zero) {
-    // fp points at entry 0 of this block for this line; entries strided by nl
+struct SmemWords {           // words read from the shared-memory ring on use
+    const T* src;
+    int nt;
+    __device__ __forceinline__ T operator[](int e) const { return src[e * nt]; }
+};
+
+template <typename T, int D>
+struct Direct {
+    using FwdView = RegWords<T, FWD_WORDS>;
+    using BwdView = RegWords<T, BWD_WORDS>;
+    const LineAddr<T, D>& a;
+    const Line<T, D>& ln;
+    int N;
+    __device__ Direct(const LineAddr<T, D>& a_, const Line<T, D>& ln_) : a(a_), ln(ln_), N(ln_.N) {}
+    __device__ __forceinline__ void fwd_start() {}
+    __device__ __forceinline__ void bwd_start() {}
+    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
+        FwdView w;
+        const T* fp = a.fac + (int64_t)j * FAC_BS;
+#pragma unroll
+        for (int e = 0; e < 15; ++e) w.v[e] = ldg(fp + e * FAC_ES);
+        w.v[15] = ldg(a.fwd_src(15, j));
+        if (j < N - 1) {
+#pragma unroll
+            for (int e = 16; e < 20; ++e) w.v[e] = ldg(a.fwd_src(e, j));
+#pragma unroll
+            for (int e = 20; e < FWD_WORDS; ++e) w.v[e] = *a.fwd_src(e, j);
+            ln.load_zeta(j + 1, zn);
+        }
+        return w;
+    }
+    __device__ __forceinline__ BwdView bwd_get(int, int i, double zc[2][2]) {
+        BwdView w;
+        const T* fp = a.fac + (int64_t)i * FAC_BS;
+#pragma unroll
+        for (int e = 0; e < 15; ++e) w.v[e] = ldg(fp + e * FAC_ES);
+#pragma unroll
+        for (int e = 15; e < BWD_WORDS; ++e) w.v[e] = *a.bwd_src(e, i);
+        if (i > 0) ln.load_zeta(i, zc);
+        return w;
+    }
+};
+
+template <typename T, int D, int STAGES>
+struct Staged {
+    using FwdView = SmemWords<T>;
+    using BwdView = SmemWords<T>;
+    const LineAddr<T, D>& a;
+    const Line<T, D>& ln;
+    int N, nt;
+    T* smT;          // this thread's column: word w of stage s at smT[(s * FWD_WORDS + w) * nt]
+    double* smZ;     // zeta ring: smZ[(s * 4 + c) * nt]
+    __device__ Staged(const LineAddr<T, D>& a_, const Line<T, D>& ln_, T* smT_, double* smZ_, int nt_)
+        : a(a_), ln(ln_), N(ln_.N), nt(nt_), smT(smT_), smZ(smZ_) {}
+
+    __device__ __forceinline__ void fwd_issue(int j) {
+        if (j < N) {
+            T* dst = smT + (int64_t)(j % STAGES) * FWD_WORDS * nt;
+            const T* fp = a.fac + (int64_t)j * FAC_BS;
+#pragma unroll
+            for (int e = 0; e < 15; ++e) cp_async(dst + e * nt, fp + e * FAC_ES);
+            cp_async(dst + 15 * nt, a.fwd_src(15, j));
+            if (j < N - 1) {
+#pragma unroll
+                for (int e = 16; e < FWD_WORDS; ++e) cp_async(dst + e * nt, a.fwd_src(e, j));
+                double* dz = smZ + (int64_t)(j % STAGES) * 4 * nt;
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+                    for (int jq = 0; jq < 2; ++jq)
+                        cp_async(dz + (2 * jp + jq) * nt,
+                                 ln.m.zeta + ln.cbase[jp][jq] + ln.cstr * (j + 1));
+            }
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void fwd_start() {
+#pragma unroll
+        for (int k = 0; k < STAGES - 1; ++k) fwd_issue(k);
+    }
+    // The stage overwritten by the new copies is the one consumed in the previous
+    // step; its words were all read (into registers) before this call.
+    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
+        fwd_issue(j + STAGES - 1);
+        cp_async_wait<STAGES - 1>();
+        const double* sz = smZ + (int64_t)(j % STAGES) * 4 * nt;
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) zn[jp][jq] = sz[(2 * jp + jq) * nt];
+        return FwdView{smT + (int64_t)(j % STAGES) * FWD_WORDS * nt, nt};
+    }
+    // backward sequence: k-th step handles block i = N - 2 - k
+    __device__ __forceinline__ void bwd_issue(int k) {
+        const int i = N - 2 - k;
+        if (i >= 0) {
+            T* dst = smT + (int64_t)(k % STAGES) * FWD_WORDS * nt;
+            const T* fp = a.fac + (int64_t)i * FAC_BS;
+#pragma unroll
+            for (int e = 0; e < 15; ++e) cp_async(dst + e * nt, fp + e * FAC_ES);
+#pragma unroll
+            for (int e = 15; e < BWD_WORDS; ++e) cp_async(dst + e * nt, a.bwd_src(e, i));
+            if (i > 0) {
+                double* dz = smZ + (int64_t)(k % STAGES) * 4 * nt;
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+                    for (int jq = 0; jq < 2; ++jq)
+                        cp_async(dz + (2 * jp + jq) * nt, ln.m.zeta + ln.cbase[jp][jq] + ln.cstr * i);
+            }
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void bwd_start() {
+        // our own stores of the forward pass must be visible to the async copies
+        __threadfence_block();
+#pragma unroll
+        for (int k = 0; k < STAGES - 1; ++k) bwd_issue(k);
+    }
+    __device__ __forceinline__ BwdView bwd_get(int k, int, double zc[2][2]) {
+        bwd_issue(k + STAGES - 1);
+        cp_async_wait<STAGES - 1>();
+        const double* sz = smZ + (int64_t)(k % STAGES) * 4 * nt;
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) zc[jp][jq] = sz[(2 * jp + jq) * nt];
+        return BwdView{smT + (int64_t)(k % STAGES) * FWD_WORDS * nt, nt};
+    }
+};
+
+template <typename T, class W>
+__device__ __forceinline__ void solve5(const W& f, T y[5], bool first_zero) {
     T L[10], dinv[5];
 #pragma unroll
-    for (int e = 0; e < 10; ++e) L[e] = ldg(fp + (int64_t)e * nl);
+    for (int e = 0; e < 10; ++e) L[e] = f[e];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) dinv[r] = ldg(fp + (int64_t)(10 + r) * nl);
+    for (int e = 0; e < 5; ++e) dinv[e] = f[10 + e];
     // L index: (1,0)=0 (2,0)=1 (2,1)=2 (3,0)=3 (3,1)=4 (3,2)=5 (4,0)=6 (4,1)=7 (4,2)=8 (4,3)=9
     if (!first_zero) {
         y[1] -= L[0] * y[0];
@@ -308,67 +557,36 @@ __device__ __forceinline__ void solve5(const T* __restrict__ fp, int64_t nl, T y
     y[0] -= L[6] * y[4] + L[3] * y[3] + L[1] * y[2] + L[0] * y[1];
 }
 
-template <typename T, int D>
-__device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restrict__ fac,
-                           const LineSlots& ls, const FieldView<T>& E, const FieldView<const T>& S) {
+template <typename T, int D, class Loader>
+__device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a, Loader& ld) {
     using A = Ax<D>;
-    Line<T, D> ln(m, tp, tq);
+    const Model<T>& m = ln.m;
     const int N = ln.N;
-    const int64_t slot = ls.slot(tp, tq), nl = ls.nl;
-
-    // element strides along the line in the three component arrays
-    const int64_t sd = D == 0 ? 1 : D == 1 ? E.s1[A::d] : E.s2[A::d];
-    const int64_t sp = D == 0 ? 1 : D == 1 ? E.s1[A::p] : E.s2[A::p];
-    const int64_t sq = D == 0 ? 1 : D == 1 ? E.s1[A::q] : E.s2[A::q];
-    int pos[3];
-    // line edge L_0 and its four parallel neighbours
-    pos[A::d] = 0; pos[A::p] = tp; pos[A::q] = tq;
-    const int64_t oL = E.idx(A::d, pos);
-    int64_t oLn[4];
-    pos[A::p] = tp - 1; oLn[0] = E.idx(A::d, pos);
-    pos[A::p] = tp + 1; oLn[1] = E.idx(A::d, pos);
-    pos[A::p] = tp; pos[A::q] = tq - 1; oLn[2] = E.idx(A::d, pos);
-    pos[A::q] = tq + 1; oLn[3] = E.idx(A::d, pos);
-    // transverse edges at line node 0: p-edges (jp) with q-node tq-1, tq, tq+1
-    int64_t oP[2][3], oQ[2][3];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int o = 0; o < 3; ++o) {
-            pos[A::d] = 0; pos[A::p] = tp - 1 + j; pos[A::q] = tq - 1 + o;
-            oP[j][o] = E.idx(A::p, pos);     // p-edge in p-cell j at q-node tq-1+o
-            pos[A::p] = tp - 1 + o; pos[A::q] = tq - 1 + j;
-            oQ[j][o] = E.idx(A::q, pos);     // q-edge in q-cell j at p-node tp-1+o
-        }
-    T* ed = E.p[A::d];
-    T* ep = E.p[A::p];
-    T* eq = E.p[A::q];
-    const T* sdp = S.p[A::d];
-    const T* spp = S.p[A::p];
-    const T* sqp = S.p[A::q];
 
     // ---------------- forward ----------------
+    ld.fwd_start();
     double zc[2][2], zn[2][2], gs[4], gn[4];
     ln.load_zeta(0, zc);
     ln.side_g(zc, gs);
     double rd = ldg(m.rh[A::d]);
     T eo[4];                             // parallel neighbours of L_i
 #pragma unroll
-    for (int k = 0; k < 4; ++k) eo[k] = ed[oLn[k]];
+    for (int k = 0; k < 4; ++k) eo[k] = a.ed[a.oLn[k]];
     T wT[4];                             // transverse part of previous block's solution
 #pragma unroll
     for (int k = 0; k < 4; ++k) wT[k] = zero_<T>();
 
     for (int i = 0; i < N; ++i) {
         const bool last = (i == N - 1);
+        const typename Loader::FwdView w = ld.fwd_get(i, zn);
         T y[5];
         // line edge
         {
-            T acc = ldg(sdp + oL + sd * i);
+            T acc = w[15];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double a = ln.a_side(k);
-                acc += (gs[k] * a * a) * eo[k];
+                const double as = ln.a_side(k);
+                acc += (gs[k] * as * as) * eo[k];
             }
             y[0] = acc;
         }
@@ -382,28 +600,21 @@ __device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restric
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[0] -= f[k] * wT[k];
         }
-        const T* fp = fac + ((int64_t)i * 15) * nl + slot;
         if (last) {
-            ed[oL + sd * i] = y[0] * ldg(fp);
+            a.ed[a.oL + a.sd * i] = y[0] * w[0];
             break;
         }
         // transverse edges at node m = i+1
         const int mnode = i + 1;
-        ln.load_zeta(i + 1, zn);
         ln.side_g(zn, gn);
         const double rdn = ldg(m.rh[A::d] + i + 1);
-        T en[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) en[k] = ed[oLn[k] + sd * (i + 1)];
-        y[1] = ldg(spp + oP[0][1] + sp * mnode);
-        y[2] = ldg(spp + oP[1][1] + sp * mnode);
-        y[3] = ldg(sqp + oQ[0][1] + sq * mnode);
-        y[4] = ldg(sqp + oQ[1][1] + sq * mnode);
+        for (int k = 0; k < 4; ++k) y[1 + k] = w[16 + k];
         // side faces of L_i (+) and L_{i+1} (-)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double a = ln.a_side(k);
-            y[1 + k] += (gs[k] * rd * a) * eo[k] - (gn[k] * rdn * a) * en[k];
+            const double as = ln.a_side(k);
+            y[1 + k] += (gs[k] * rd * as) * eo[k] - (gn[k] * rdn * as) * w[20 + k];
         }
         // end faces at node m
 #pragma unroll
@@ -412,9 +623,7 @@ __device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restric
             for (int jq = 0; jq < 2; ++jq) {
                 const double g = 0.5 * (zc[jp][jq] + zn[jp][jq]);
                 const double ap = ln.al_p(jq), aq = ln.al_q(jp);
-                const T epo = ep[oP[jp][jq == 0 ? 0 : 2] + sp * mnode];
-                const T eqo = eq[oQ[jq][jp == 0 ? 0 : 2] + sq * mnode];
-                const T out = ap * epo + aq * eqo;
+                const T out = ap * w[24 + 2 * jp + jq] + aq * w[28 + 2 * jp + jq];
                 y[1 + jp] += (g * ap) * out;
                 y[3 + jq] += (g * aq) * out;
             }
@@ -422,14 +631,14 @@ __device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restric
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[1 + k] -= dk[k] * wT[k];
         }
-        solve5<T>(fp, nl, y, false);
-        ed[oL + sd * i] = y[0];
-        ep[oP[0][1] + sp * mnode] = y[1];
-        ep[oP[1][1] + sp * mnode] = y[2];
-        eq[oQ[0][1] + sq * mnode] = y[3];
-        eq[oQ[1][1] + sq * mnode] = y[4];
+        solve5<T>(w, y, false);
+        a.ed[a.oL + a.sd * i] = y[0];
+        a.ep[a.oP[0][1] + a.sp * mnode] = y[1];
+        a.ep[a.oP[1][1] + a.sp * mnode] = y[2];
+        a.eq[a.oQ[0][1] + a.sq * mnode] = y[3];
+        a.eq[a.oQ[1][1] + a.sq * mnode] = y[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { wT[k] = y[1 + k]; eo[k] = en[k]; gs[k] = gn[k]; }
+        for (int k = 0; k < 4; ++k) { wT[k] = y[1 + k]; eo[k] = w[20 + k]; gs[k] = gn[k]; }
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp)
 #pragma unroll
@@ -439,7 +648,8 @@ __device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restric
 
     // ---------------- backward ----------------
     // x_i = w_i - S_i^{-1} F_{i+1}^T x_{i+1};  gs / rd now belong to line cell N-1
-    T xL = ed[oL + sd * (N - 1)];
+    T xL = a.ed[a.oL + a.sd * (N - 1)];
+    ld.bwd_start();
     T xT[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xT[k] = zero_<T>();
@@ -452,47 +662,77 @@ __device__ void sweep_line(const Model<T>& m, int tp, int tq, const T* __restric
             const double dkk = -gs[k] * rd * rd;
             v[1 + k] = fk * xL + dkk * xT[k];
         }
-        const T* fp = fac + ((int64_t)i * 15) * nl + slot;
-        solve5<T>(fp, nl, v, true);
+        const typename Loader::BwdView w = ld.bwd_get(N - 2 - i, i, zc);
+        solve5<T>(w, v, true);
         const int mnode = i + 1;
-        xL = ed[oL + sd * i] - v[0];
-        xT[0] = ep[oP[0][1] + sp * mnode] - v[1];
-        xT[1] = ep[oP[1][1] + sp * mnode] - v[2];
-        xT[2] = eq[oQ[0][1] + sq * mnode] - v[3];
-        xT[3] = eq[oQ[1][1] + sq * mnode] - v[4];
-        ed[oL + sd * i] = xL;
-        ep[oP[0][1] + sp * mnode] = xT[0];
-        ep[oP[1][1] + sp * mnode] = xT[1];
-        eq[oQ[0][1] + sq * mnode] = xT[2];
-        eq[oQ[1][1] + sq * mnode] = xT[3];
+        xL = w[15] - v[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xT[k] = w[16 + k] - v[1 + k];
+        a.ed[a.oL + a.sd * i] = xL;
+        a.ep[a.oP[0][1] + a.sp * mnode] = xT[0];
+        a.ep[a.oP[1][1] + a.sp * mnode] = xT[1];
+        a.eq[a.oQ[0][1] + a.sq * mnode] = xT[2];
+        a.eq[a.oQ[1][1] + a.sq * mnode] = xT[3];
         if (i > 0) {
-            ln.load_zeta(i, zc);
             ln.side_g(zc, gs);
             rd = ldg(m.rh[A::d] + i);
         }
     }
 }
 
-// ---- kernels ---------------------------------------------------------------
 template <typename T, int D>
-__global__ void __launch_bounds__(128)
-line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int npi, int nqi) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y * blockDim.y + threadIdx.y;
-    if (a >= npi || b >= nqi) return;
-    factor_line<T, D>(m, 1 + a, 1 + b, fac, ls);
+__device__ __forceinline__ void sweep_line_direct(const Model<T>& m, int tp, int tq, const T* fac,
+                                                  const LineSlots& ls, const FieldView<T>& E,
+                                                  const FieldView<const T>& S) {
+    Line<T, D> ln(m, tp, tq);
+    LineAddr<T, D> a(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
+    Direct<T, D> ld(a, ln);
+    sweep_line<T, D>(ln, a, ld);
+}
+
+
+// ---- kernels ---------------------------------------------------------------
+// thread t of parity class c  <->  slot off[c] + t  <->  line (1 + cp + 2 a, 1 + cq + 2 b)
+__device__ __forceinline__ bool class_line(const LineSlots& ls, int c, int t, int& tp, int& tq) {
+    if (t >= ls.cnt[c]) return false;
+    const int cp = c & 1, cq = c >> 1;
+    tp = 1 + cp + 2 * (t % ls.na[cp]);
+    tq = 1 + cq + 2 * (t / ls.na[cp]);
+    return true;
 }
 
 template <typename T, int D>
-__global__ void __launch_bounds__(128)
-gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int fp, int fq,
-                     int cp, int cq) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y * blockDim.y + threadIdx.y;
-    if (a >= cp || b >= cq) return;
+__global__ void __launch_bounds__(64)
+line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c) {
+    int tp, tq;
+    if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
+    factor_line<T, D>(m, tp, tq, fac, ls);
+}
+
+#ifndef EMG_LINE_STAGED
+#define EMG_LINE_STAGED 0
+#endif
+
+template <typename T, int D>
+__global__ void __launch_bounds__(64)
+gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c) {
+    int tp, tq;
+    if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
-    sweep_line<T, D>(m, fp + 2 * a, fq + 2 * b, fac, ls, E, S);
+    Line<T, D> ln(m, tp, tq);
+    LineAddr<T, D> ad(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
+#if EMG_LINE_STAGED
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    const int nt = blockDim.x;
+    T* smT = reinterpret_cast<T*>(ring_raw) + threadIdx.x;
+    double* smZ = reinterpret_cast<double*>(reinterpret_cast<T*>(ring_raw) +
+                                            (size_t)LINE_STAGES * FWD_WORDS * nt) + threadIdx.x;
+    Staged<T, D, LINE_STAGES> ld(ad, ln, smT, smZ, nt);
+#else
+    Direct<T, D> ld(ad, ln);
+#endif
+    sweep_line<T, D>(ln, ad, ld);
 }
 
 template <typename T, int D>
@@ -505,7 +745,7 @@ gs_line_front_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, i
     if (tp < 1 || tp >= m.d.n[A::p]) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
-    sweep_line<T, D>(m, tp, tq, fac, ls, E, S);
+    sweep_line_direct<T, D>(m, tp, tq, fac, ls, E, S);
 }
 
 template <typename T, int D>
@@ -524,17 +764,17 @@ gs_line_small_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, i
                 const int t = back ? tmax + tmin - tt : tt;
                 for (int b = threadIdx.x; b < nqi; b += blockDim.x) {
                     const int tq = 1 + b, tp = t - 2 * tq;
-                    if (tp >= 1 && tp <= npi) sweep_line<T, D>(m, tp, tq, fac, ls, E, S);
+                    if (tp >= 1 && tp <= npi) sweep_line_direct<T, D>(m, tp, tq, fac, ls, E, S);
                 }
                 __syncthreads();
             }
         } else {
             for (int cc = 0; cc < 4; ++cc) {
                 const int c = back ? 3 - cc : cc;
-                for (int l = threadIdx.x; l < npi * nqi; l += blockDim.x) {
-                    const int tp = 1 + l % npi, tq = 1 + l / npi;
-                    if (((tp - 1) & 1) == (c & 1) && ((tq - 1) & 1) == (c >> 1))
-                        sweep_line<T, D>(m, tp, tq, fac, ls, E, S);
+                for (int t = threadIdx.x; t < ls.cnt[c]; t += blockDim.x) {
+                    int tp, tq;
+                    class_line(ls, c, t, tp, tq);
+                    sweep_line_direct<T, D>(m, tp, tq, fac, ls, E, S);
                 }
                 __syncthreads();
             }
@@ -544,7 +784,9 @@ gs_line_small_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, i
 
 int64_t line_factor_elems(const Dims& d, int dir) {
     const int p = dir == 0 ? 1 : 0, q = dir == 2 ? 1 : 2;
-    return (int64_t)15 * d.n[dir] * (d.n[p] - 1) * (d.n[q] - 1);
+    if (d.n[p] < 2 || d.n[q] < 2) return 0;
+    LineSlots ls(d.n[p] - 1, d.n[q] - 1);
+    return (int64_t)FAC_BS * d.n[dir] * (ls.nl / 32);
 }
 
 template <typename T, int D>
@@ -553,9 +795,10 @@ static void factor_dir(const Model<T>& m, T* fac, cudaStream_t st) {
     const int npi = m.d.n[A::p] - 1, nqi = m.d.n[A::q] - 1;
     if (npi < 1 || nqi < 1) return;
     LineSlots ls(npi, nqi);
-    dim3 b(32, 4);
-    dim3 g((npi + b.x - 1) / b.x, (nqi + b.y - 1) / b.y);
-    ++g_launch_count; line_factor_kernel<T, D><<<g, b, 0, st>>>(m, fac, ls, npi, nqi);
+    for (int c = 0; c < 4; ++c) {
+        if (ls.cnt[c] == 0) continue;
+        ++g_launch_count; line_factor_kernel<T, D><<<(ls.cnt[c] + 63) / 64, 64, 0, st>>>(m, fac, ls, c);
+    }
 }
 
 template <typename T>
@@ -574,7 +817,7 @@ static void gs_dir(const Model<T>& m, const T* fac, T* e, const T* s, int nu, in
     LineSlots ls(npi, nqi);
     if ((int64_t)npi * nqi <= 1024) {
         int threads = 32;
-        const int want = order == ORDER_LEX ? nqi : npi * nqi;
+        const int want = order == ORDER_LEX ? nqi : (npi * nqi + 3) / 4;
         while (threads < 256 && threads < want) threads <<= 1;
         ++g_launch_count; gs_line_small_kernel<T, D><<<1, threads, 0, st>>>(m, fac, ls, e, s, nu, order);
         return;
@@ -593,12 +836,19 @@ static void gs_dir(const Model<T>& m, const T* fac, T* e, const T* s, int nu, in
         } else {
             for (int cc = 0; cc < 4; ++cc) {
                 const int c = back ? 3 - cc : cc;
-                const int fp = 1 + (c & 1), fq = 1 + (c >> 1);
-                const int cp = (npi - (fp - 1) + 1) / 2, cq = (nqi - (fq - 1) + 1) / 2;
-                if (cp <= 0 || cq <= 0) continue;
-                dim3 b(32, 2);
-                dim3 g((cp + b.x - 1) / b.x, (cq + b.y - 1) / b.y);
-                ++g_launch_count; gs_line_color_kernel<T, D><<<g, b, 0, st>>>(m, fac, ls, e, s, fp, fq, cp, cq);
+                if (ls.cnt[c] == 0) continue;
+                const int threads = EMG_LINE_STAGED ? 32 : 64;
+                size_t smem = 0;
+#if EMG_LINE_STAGED
+                smem = (size_t)LINE_STAGES * threads * (FWD_WORDS * sizeof(T) + 4 * sizeof(double));
+                static bool attr_set = false;       // per template instance
+                if (!attr_set) {
+                    cudaFuncSetAttribute(gs_line_color_kernel<T, D>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_set = true;
+                }
+#endif
+                ++g_launch_count; gs_line_color_kernel<T, D><<<(ls.cnt[c] + threads - 1) / threads, threads, smem, st>>>(m, fac, ls, e, s, c);
             }
         }
     }
