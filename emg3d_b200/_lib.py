@@ -80,6 +80,8 @@ _SIGNATURES = {
     'emg3d_b200_restrict': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_prolong': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_restrict_cells': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'emg3d_b200_volume_model': (c_int, [c_void_p, c_int, c_double, c_double, c_double, c_double,
+                                        c_int] + [c_void_p] * 9),
     'emg3d_b200_pec_zero': (c_int, [c_void_p, c_void_p]),
     'emg3d_b200_dot': (c_int, [c_int, c_longlong, c_void_p, c_void_p, c_int, c_void_p]),
     'emg3d_b200_dot_host': (c_int, [c_int, c_longlong, c_void_p, c_void_p, c_int,

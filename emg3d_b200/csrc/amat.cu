@@ -145,6 +145,166 @@ residual_kernel(Model<T> m, const T* s, const T* __restrict__ e,
     }
 }
 
+// ---- plane-streaming variant for large grids ----------------------------------
+// Each flux (zeta-weighted curl through a face) enters the residual of four
+// edges; the simple kernel above recomputes it for each of them (9 fluxes, ~80
+// loads per node).  Here a block of 32 x 8 threads owns an (x, y) tile and
+// marches through KZ node planes: every thread computes the three fluxes at its
+// own node once (18 loads) and obtains the neighbours'
+//   -z : from its own registers (previous plane),
+//   -x : by warp shuffle (a warp is one x-row of the tile),
+//   -y : through a double-buffered shared-memory row exchange,
+// recomputing only on the low tile faces.  DRAM traffic stays at the algorithmic
+// 200 B per cell; L1 traffic drops by more than half.
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ cplx shfl_up1(cplx v) {
+    return make_c(__shfl_up_sync(0xffffffffu, v.re, 1), __shfl_up_sync(0xffffffffu, v.im, 1));
+}
+
+#ifndef EMG_RZ_BY
+#define EMG_RZ_BY 8
+#endif
+#ifndef EMG_RZ_MINB
+#define EMG_RZ_MINB 4
+#endif
+#ifndef EMG_RZ_KZ
+#define EMG_RZ_KZ 16
+#endif
+constexpr int RZ_BX = 32, RZ_BY = EMG_RZ_BY;
+
+template <typename T>
+__global__ void __launch_bounds__(RZ_BX * RZ_BY, EMG_RZ_MINB)
+residual_zmarch_kernel(Model<T> m, const T* s, const T* __restrict__ e, T* r,
+                       double* __restrict__ partial, int apply_only, int kz) {
+    const int nx = m.d.n[0], ny = m.d.n[1], nz = m.d.n[2];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * RZ_BX, y0 = blockIdx.y * RZ_BY;
+    const int ix = x0 + tx, iy = y0 + ty;
+    const int k0 = blockIdx.z * kz, k1 = min(k0 + kz, nz + 1);
+    const bool node = ix <= nx && iy <= ny;
+    const bool cellxy = ix < nx && iy < ny;
+    __shared__ T sFz[2][RZ_BY + 1][RZ_BX];
+    __shared__ T sFx[2][RZ_BY + 1][RZ_BX];
+
+    Flux<T> F(m, e);
+    FieldView<const T> S(s, m.d);
+    FieldView<T> R(r, m.d);
+    const int64_t cs1 = nx, cs2 = (int64_t)nx * ny;
+    const int ixm = max(ix - 1, 0), iym = max(iy - 1, 0);
+    const double rhx = ix < nx ? ldg(m.rh[0] + ix) : 0.0, rhxm = ldg(m.rh[0] + ixm);
+    const double rhy = iy < ny ? ldg(m.rh[1] + iy) : 0.0, rhym = ldg(m.rh[1] + iym);
+
+    // fluxes of the plane below the first one (needed by x- and y-edges)
+    T fx_dn = zero_<T>(), fy_dn = zero_<T>();
+    if (cellxy && k0 > 0) {
+        if (ix > 0) fx_dn = F.fx(ix, iy, k0 - 1);
+        if (iy > 0) fy_dn = F.fy(ix, iy, k0 - 1);
+    }
+    double acc = 0.0;
+    for (int k = k0; k < k1; ++k) {
+        const int buf = (k - k0) & 1;
+        const bool cell = cellxy && k < nz;          // the edges the reference touches
+        const int km = max(k - 1, 0);
+        // own fluxes
+        T fx = zero_<T>(), fy = zero_<T>(), fz = zero_<T>();
+        if (cell) {
+            if (ix > 0) fx = F.fx(ix, iy, k);
+            if (iy > 0) fy = F.fy(ix, iy, k);
+            if (k > 0) fz = F.fz(ix, iy, k);
+        }
+        // -x neighbours by shuffle; the first lane of the row recomputes
+        T fz_xm = shfl_up1(fz), fy_xm = shfl_up1(fy);
+        if (tx == 0) {
+            fz_xm = zero_<T>();
+            fy_xm = zero_<T>();
+            if (cell && ix > 0) {
+                if (k > 0) fz_xm = F.fz(ix - 1, iy, k);
+                if (iy > 0) fy_xm = F.fy(ix - 1, iy, k);
+            }
+        }
+        // -y neighbours through shared memory; row 0 holds the tile's lower halo
+        sFz[buf][ty + 1][tx] = fz;
+        sFx[buf][ty + 1][tx] = fx;
+        if (ty == 0) {
+            T hz = zero_<T>(), hx = zero_<T>();
+            if (cell && iy > 0) {
+                if (k > 0) hz = F.fz(ix, iy - 1, k);
+                if (ix > 0) hx = F.fx(ix, iy - 1, k);
+            }
+            sFz[buf][0][tx] = hz;
+            sFx[buf][0][tx] = hx;
+        }
+        __syncthreads();
+        const T fz_ym = sFz[buf][ty][tx], fx_ym = sFx[buf][ty][tx];
+
+        if (node) {
+            const double rhz = k < nz ? ldg(m.rh[2] + k) : 0.0, rhzm = ldg(m.rh[2] + km);
+            // x-edge (ix, iy, k)
+            if (ix < nx) {
+                const int64_t id = S.idx(0, ix, iy, k);
+                T val = apply_only ? zero_<T>() : ldg(S.p[0] + id);
+                if (cell) {
+                    T cc = zero_<T>();
+                    if (iy > 0 && k > 0) cc = rhy * fz - rhym * fz_ym - rhz * fy + rhzm * fy_dn;
+                    const T* et = m.eta[0];
+                    const T st = ldg(et + ix + cs1 * iym + cs2 * km) + ldg(et + ix + cs1 * iym + cs2 * k) +
+                                 ldg(et + ix + cs1 * iy + cs2 * km) + ldg(et + ix + cs1 * iy + cs2 * k);
+                    val -= 0.5 * cc - 0.25 * (st * F.E(0, ix, iy, k));
+                }
+                if (apply_only) val = -val;
+                if (r) R.p[0][id] = val;
+                acc += abs2(val);
+            }
+            // y-edge
+            if (iy < ny) {
+                const int64_t id = S.idx(1, ix, iy, k);
+                T val = apply_only ? zero_<T>() : ldg(S.p[1] + id);
+                if (cell) {
+                    T cc = zero_<T>();
+                    if (ix > 0 && k > 0) cc = rhz * fx - rhzm * fx_dn - rhx * fz + rhxm * fz_xm;
+                    const T* et = m.eta[1];
+                    const T st = ldg(et + ixm + cs1 * iy + cs2 * km) + ldg(et + ix + cs1 * iy + cs2 * km) +
+                                 ldg(et + ixm + cs1 * iy + cs2 * k) + ldg(et + ix + cs1 * iy + cs2 * k);
+                    val -= 0.5 * cc - 0.25 * (st * F.E(1, ix, iy, k));
+                }
+                if (apply_only) val = -val;
+                if (r) R.p[1][id] = val;
+                acc += abs2(val);
+            }
+            // z-edge
+            if (k < nz) {
+                const int64_t id = S.idx(2, ix, iy, k);
+                T val = apply_only ? zero_<T>() : ldg(S.p[2] + id);
+                if (cell) {
+                    T cc = zero_<T>();
+                    if (ix > 0 && iy > 0) cc = rhx * fy - rhxm * fy_xm - rhy * fx + rhym * fx_ym;
+                    const T* et = m.eta[2];
+                    const T st = ldg(et + ixm + cs1 * iym + cs2 * k) + ldg(et + ix + cs1 * iym + cs2 * k) +
+                                 ldg(et + ixm + cs1 * iy + cs2 * k) + ldg(et + ix + cs1 * iy + cs2 * k);
+                    val -= 0.5 * cc - 0.25 * (st * F.E(2, ix, iy, k));
+                }
+                if (apply_only) val = -val;
+                if (r) R.p[2][id] = val;
+                acc += abs2(val);
+            }
+        }
+        fx_dn = fx;
+        fy_dn = fy;
+    }
+    if (partial) {
+        __shared__ double red[RZ_BX * RZ_BY / 32];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        const int tid = tx + RZ_BX * ty;
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < RZ_BX * RZ_BY / 32; ++w) t += red[w];
+            partial[blockIdx.x + gridDim.x * (blockIdx.y + (int64_t)gridDim.y * blockIdx.z)] = t;
+        }
+    }
+}
+
 // single-block deterministic sum of the per-block partials
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __restrict__ p, int64_t n,
                                                            double* __restrict__ out) {
@@ -161,13 +321,23 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __rest
     }
 }
 
+constexpr int64_t ZMARCH_MIN_CELLS = 64 * 64 * 64;
+constexpr int ZMARCH_KZ = EMG_RZ_KZ;
+
 template <typename T>
 void launch_residual(const Model<T>& m, const T* s, const T* e, T* r, double* norm2_out,
                      double* scratch, int apply_only, cudaStream_t st) {
     dim3 b(32, 4, 2);
     dim3 g((m.d.n[0] + 1 + b.x - 1) / b.x, (m.d.n[1] + 1 + b.y - 1) / b.y,
            (m.d.n[2] + 1 + b.z - 1) / b.z);
-    ++g_launch_count; residual_kernel<T><<<g, b, 0, st>>>(m, s, e, r, norm2_out ? scratch : nullptr, apply_only);
+    if (n_cells(m.d) >= ZMARCH_MIN_CELLS) {
+        b = dim3(RZ_BX, RZ_BY, 1);
+        g = dim3((m.d.n[0] + RZ_BX) / RZ_BX, (m.d.n[1] + RZ_BY) / RZ_BY,
+                 (m.d.n[2] + ZMARCH_KZ) / ZMARCH_KZ);
+        ++g_launch_count; residual_zmarch_kernel<T><<<g, b, 0, st>>>(m, s, e, r, norm2_out ? scratch : nullptr, apply_only, ZMARCH_KZ);
+    } else {
+        ++g_launch_count; residual_kernel<T><<<g, b, 0, st>>>(m, s, e, r, norm2_out ? scratch : nullptr, apply_only);
+    }
     if (norm2_out) {
         int64_t nb = (int64_t)g.x * g.y * g.z;
         ++g_launch_count; sum_partials_kernel<<<1, 1024, 0, st>>>(scratch, nb, norm2_out);
@@ -175,7 +345,7 @@ void launch_residual(const Model<T>& m, const T* s, const T* e, T* r, double* no
 }
 
 int64_t residual_scratch_doubles(const Dims& d) {
-    dim3 b(32, 4, 2);
+    dim3 b(32, 4, 2);     // the simple kernel has the finer grid of the two variants
     return (int64_t)((d.n[0] + 1 + b.x - 1) / b.x) * ((d.n[1] + 1 + b.y - 1) / b.y) *
            ((d.n[2] + 1 + b.z - 1) / b.z);
 }

@@ -438,6 +438,26 @@ int emg3d_b200_restrict_cells(emg3d_b200_level* c, int is_cplx, const void* p_fi
     return 0;
 }
 
+int emg3d_b200_volume_model(emg3d_b200_level* lv, int is_cplx, double c_re, double c_im, double s_re,
+                            double s_im, int map_code, const double* prop_x, const double* prop_y,
+                            const double* prop_z, const double* mu_r, const double* eps_r, void* eta_x,
+                            void* eta_y, void* eta_z, double* zeta) {
+    NEED_INIT();
+    if (map_code < 0 || map_code > 5) return fail_msg("volume_model: unknown property mapping");
+    if (!prop_x || !eta_x || !zeta) return fail_msg("volume_model: prop_x, eta_x and zeta are required");
+    const double eps0 = 1.0;   // the caller passes s * eps_0 (its own CODATA value) as (s_re, s_im)
+    if (is_cplx)
+        launch_volume_model<cplx>(lv->d, lv->h[0], lv->h[1], lv->h[2], c_re, c_im, s_re, s_im, eps0, map_code,
+                                  prop_x, prop_y, prop_z, mu_r, eps_r, (cplx*)eta_x, (cplx*)eta_y,
+                                  (cplx*)eta_z, zeta, g_stream);
+    else
+        launch_volume_model<double>(lv->d, lv->h[0], lv->h[1], lv->h[2], c_re, c_im, s_re, s_im, eps0,
+                                    map_code, prop_x, prop_y, prop_z, mu_r, eps_r, (double*)eta_x,
+                                    (double*)eta_y, (double*)eta_z, zeta, g_stream);
+    CK_LAUNCH("volume_model");
+    return 0;
+}
+
 int emg3d_b200_pec_zero(emg3d_b200_level* lv, void* e) {
     NEED_MODEL(lv);
     if (lv->cplx) launch_pec_zero<cplx>(lv->d, (cplx*)e, g_stream);

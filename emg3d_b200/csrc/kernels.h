@@ -47,6 +47,13 @@ void launch_restrict_cells(const Dims& fine, const int* cflag, const T* p, T* cp
 template <typename T>
 void launch_band_solve(int n, T* a, T* b, cudaStream_t st);
 
+// eta / zeta from property arrays (models.VolumeModel)
+template <typename T>
+void launch_volume_model(const Dims& d, const double* hx, const double* hy, const double* hz,
+                         double cr, double ci, double sr, double si, double eps0, int map,
+                         const double* px, const double* py, const double* pz, const double* mu,
+                         const double* eps, T* ex, T* ey, T* ez, double* zeta, cudaStream_t st);
+
 // vector helpers
 template <typename T>
 void launch_pec_zero(const Dims& d, T* e, cudaStream_t st);

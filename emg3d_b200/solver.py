@@ -27,12 +27,13 @@ from typing import Union
 
 import numpy as np
 import scipy.sparse.linalg as _ssl
+from scipy.constants import epsilon_0
 
 from emg3d_b200 import _lib, core, fields, meshes, models
 
 __all__ = ['solve', 'solve_source', 'multigrid', 'krylov', 'smoothing',
            'restriction', 'prolongation', 'residual', 'MGParameters',
-           'RegularGridProlongator']
+           'RegularGridProlongator', 'Workspace']
 
 __version__ = '0.1.0'
 
@@ -136,6 +137,49 @@ class _Level:
             grid = meshes.BaseMesh(grid.h, grid.origin)
         return cls(grid, dtype, getattr(vmodel, 'case', 'triaxial'), devs, zeta)
 
+    _MAPS = {'Conductivity': 0, 'Resistivity': 1, 'LgConductivity': 2, 'LnConductivity': 3,
+             'LgResistivity': 4, 'LnResistivity': 5}
+
+    @classmethod
+    def from_model(cls, model, sfield):
+        """Build eta/zeta on the device from a Model (models.VolumeModel, 654-691).
+
+        Only the real property arrays cross PCIe; falls back to the host
+        ``VolumeModel`` for property maps the device kernel does not know.
+        """
+        map_name = getattr(model.map, 'name', None)
+        dtype = np.dtype(np.asarray(sfield.field).dtype)
+        if map_name not in cls._MAPS:
+            return cls.from_volume_model(models.VolumeModel(model, sfield), dtype)
+        grid = meshes.BaseMesh(model.grid.h, model.grid.origin)
+        handle = _lib.LevelHandle(grid.h)
+        n = grid.n_cells
+
+        def up(arr):
+            return None if arr is None else _lib.DeviceArray.from_host(
+                np.asarray(arr, dtype=np.float64))
+
+        props = [up(model.property_x), up(model.property_y), up(model.property_z),
+                 up(model.mu_r), up(model.epsilon_r)]
+        eta_x = _lib.DeviceArray(n, dtype)
+        eta_y = _lib.DeviceArray(n, dtype) if props[1] is not None else eta_x
+        eta_z = _lib.DeviceArray(n, dtype) if props[2] is not None else eta_x
+        zeta = _lib.DeviceArray(n, np.float64)
+        c = complex(-sfield.smu0)
+        se = complex(sfield.sval * epsilon_0)
+        ptr = lambda a: None if a is None else a.ptr
+        _lib.check(_lib.load().emg3d_b200_volume_model(
+            handle.ptr, int(dtype.kind == 'c'), c.real, c.imag, se.real, se.imag,
+            cls._MAPS[map_name], *[ptr(p) for p in props], eta_x.ptr, eta_y.ptr, eta_z.ptr,
+            zeta.ptr))
+        self = cls.__new__(cls)
+        self.grid, self.dtype, self.cplx, self.case = grid, dtype, dtype.kind == 'c', model.case
+        self.eta, self.zeta, self.handle = [eta_x, eta_y, eta_z], zeta, handle
+        handle.set_model(self.cplx, eta_x, eta_y, eta_z, zeta)
+        self.children, self._res, self.sc_to_parent = {}, None, None
+        self.s = self.e = None
+        return self
+
     def coarse(self, sc_dir):
         """Coarse level for the (current) semicoarsening pattern; cached."""
         sc_dir = int(sc_dir)
@@ -185,6 +229,63 @@ class _Level:
         child.e = child.new_field()
         self.children[sc_dir] = child
         return child
+
+
+class Workspace:
+    """Device-resident state that can be reused by consecutive :func:`solve` calls.
+
+    ``solve(model, sfield, workspace=ws)`` keeps the coefficient arrays, the
+    coarse-grid hierarchy and the cached line factorisations of ``model`` on the
+    GPU, keyed by the model object, the Laplace parameter of ``sfield`` and the
+    dtype.  A cheap fingerprint of the property arrays (buffer address, shape and
+    a strided checksum) guards against models that were modified in place.
+    """
+
+    def __init__(self, max_models=2, pinned_result=False):
+        self.max_models = int(max_models)
+        self._levels = {}
+        # With ``pinned_result=True`` a solve without ``efield=`` returns a Field
+        # whose data live in a page-locked buffer owned by this workspace (fast
+        # device-to-host copy).  The buffer is reused: the returned field is only
+        # valid until the next solve with this workspace -- copy it to keep it.
+        self.pinned_result = bool(pinned_result)
+        self._result = None
+
+    @staticmethod
+    def _fingerprint(model):
+        fp = [tuple(float(h.sum()) for h in model.grid.h)]
+        for name in ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r'):
+            a = getattr(model, name, None)
+            if a is None:
+                fp.append(None)
+            else:
+                a = np.asarray(a)
+                flat = a.reshape(-1, order='A')
+                fp.append((a.ctypes.data, a.shape, float(flat[::4099].sum()), float(flat[-1])))
+        fp.append(getattr(model.map, 'name', None))
+        return tuple(fp)
+
+    def level(self, model, sfield):
+        key = (id(model), complex(sfield.sval), np.dtype(np.asarray(sfield.field).dtype).str)
+        fp = self._fingerprint(model)
+        hit = self._levels.get(key)
+        if hit is not None and hit[0] == fp:
+            return hit[1]
+        while len(self._levels) >= self.max_models:
+            self._levels.pop(next(iter(self._levels)))
+        lv = _Level.from_model(model, sfield)
+        self._levels[key] = (fp, lv)
+        return lv
+
+    def result_buffer(self, size, dtype):
+        if (self._result is None or self._result.size != size or
+                self._result.dtype != np.dtype(dtype)):
+            self._result = _lib.PinnedArray(size, dtype)
+        return self._result.array
+
+    def clear(self):
+        self._levels.clear()
+        self._result = None
 
 
 def _order(var):
@@ -243,6 +344,10 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     order : {'color', 'lex'}
         Gauss-Seidel ordering inside the smoothers; default from
         ``emg3d_b200.core.ORDER`` (environment ``EMG3D_B200_ORDER``, 'color').
+    workspace : Workspace, optional
+        Keeps the device-resident coefficients, grid hierarchy and line
+        factorisations of ``model`` alive between calls (many sources or
+        restarts on one model and frequency).
     """
     always_return = kwargs.pop('always_return', False)
     if kwargs.pop('plain', False):
@@ -251,6 +356,7 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
         linerelaxation = False if linerelaxation is True else linerelaxation
     efield = kwargs.pop('efield', None)
     order = kwargs.pop('order', None)
+    workspace = kwargs.pop('workspace', None)
     core.order_id(order)  # validate early
 
     var = MGParameters(
@@ -263,24 +369,37 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
                f"v{__version__}\n", 2)
     var.cprint(var, 2)
 
-    var.l2_refe = float(np.linalg.norm(sfield.field))
-    var.error_at_cycle[0] = var.l2_refe
-
     if sfield.frequency is None:
+        # (the reference evaluates the source norm first; a Field without
+        # frequency fails either way)
         raise ValueError(
             "Source field is missing frequency information; Create "
             "it with `emg3d.fields.get_source_field`, or initiate it "
             "with `emg3d.fields.Field`, providing frequency information."
         )
 
-    vmodel = models.VolumeModel(model, sfield)
+    # Coefficients to the device: eta/zeta are computed there from the property
+    # arrays (models.VolumeModel, emg3d/models.py:654-691); a workspace keeps
+    # them (and the whole level hierarchy) alive across calls.
     dtype = sfield.field.dtype
-    level = _Level.from_volume_model(vmodel, dtype)
+    if workspace is not None:
+        level = workspace.level(model, sfield)
+    else:
+        level = _Level.from_model(model, sfield)
     d_s = _lib.DeviceArray.from_host(np.asarray(sfield.field))
     info = ""
 
+    # Reference error for the tolerance: ||b||_2 (solver.py:312), on the device.
+    var.l2_refe = _Vec(level.cplx, level.n_edges).norm(d_s)
+    var.error_at_cycle[0] = var.l2_refe
+
     if efield is None:
-        efield = fields.Field(model.grid, dtype=dtype, frequency=sfield._frequency)
+        if workspace is not None and workspace.pinned_result:
+            # result lands in a page-locked buffer owned by the workspace
+            efield = fields.Field(model.grid, workspace.result_buffer(level.n_edges, dtype),
+                                  frequency=sfield._frequency)
+        else:
+            efield = fields.Field(model.grid, dtype=dtype, frequency=sfield._frequency)
         d_e = level.new_field()
         var.do_return = True
     else:

@@ -116,6 +116,19 @@ int emg3d_b200_prolong(emg3d_b200_level* coarse, void* e_fine, const void* e_coa
  * solver._restrict_model_parameters (solver.py:1667-1718).                     */
 int emg3d_b200_restrict_cells(emg3d_b200_level* coarse, int cplx, const void* p_fine,
                               void* p_coarse);
+/* Volume-averaged coefficients from property arrays, on the device.  Replaces
+ * models.VolumeModel.__init__ (emg3d/models.py:654-691):
+ *   eta_a = c * V * (sigma_a + (s eps_0) * eps_r),  zeta = V / mu_r,
+ * c = -s mu_0 (c_re, c_im), (s_re, s_im) = s * eps_0, V from the level's widths,
+ * sigma_a = backward map of prop_a (map_code 0 Conductivity, 1 Resistivity,
+ * 2 LgConductivity, 3 LnConductivity, 4 LgResistivity, 5 LnResistivity).
+ * prop_y, prop_z, mu_r, eps_r may be NULL; eta_y / eta_z are written only when
+ * the corresponding property is given.  All arrays float64 (nx, ny, nz).       */
+int emg3d_b200_volume_model(emg3d_b200_level* lv, int cplx, double c_re, double c_im,
+                            double s_re, double s_im, int map_code, const double* prop_x,
+                            const double* prop_y, const double* prop_z, const double* mu_r,
+                            const double* eps_r, void* eta_x, void* eta_y, void* eta_z,
+                            double* zeta);
 /* zero the tangential boundary edges (solver.py:350-355) */
 int emg3d_b200_pec_zero(emg3d_b200_level* lv, void* e);
 

@@ -73,7 +73,8 @@ def test_amat_x_golden(core, golden):
 def test_amat_x_random_boundaries(core):
     """Non-zero boundary values of e and s exercise the reference's boundary rules."""
     rng = np.random.default_rng(11)
-    for shape, cplx in (((9, 7, 5), True), ((33, 6, 10), False), ((40, 37, 35), True)):
+    for shape, cplx in (((9, 7, 5), True), ((33, 6, 10), False), ((40, 37, 35), True),
+                        ((70, 66, 65), True), ((65, 97, 50), False)):   # plane-streaming kernel
         c = random_case(rng, shape, cplx)
         e = rng.standard_normal(c['e'].size) + (1j * rng.standard_normal(c['e'].size) if cplx else 0)
         r1, r2 = c['s'].copy(), c['s'].copy()
@@ -273,3 +274,50 @@ def test_residual_and_smoothing_wrappers(golden):
             ovm = mg.VolumeModel.from_arrays(g, c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'])
             mg.smoothing(ovm, c['s'], e2, 2, lr_dir)
             assert rel_err(e1.field, e2) < 1e-11, (k, lr_dir)
+
+
+def test_volume_model_on_device(golden):
+    """Device-side eta/zeta (csrc/model.cu) against the reference's VolumeModel."""
+    import emg3d_b200 as eb
+    from emg3d_b200 import solver
+    gh = golden('host')
+    grid = eb.TensorMesh([gh['hx'], gh['hy'], gh['hz']], gh['origin'])
+    props = {k: gh['vm_' + k] for k in ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r')}
+    cases = {'iso': ['property_x'], 'vti': ['property_x', 'property_z'],
+             'hti': ['property_x', 'property_y'],
+             'tri': ['property_x', 'property_y', 'property_z'], 'full': list(props)}
+    for case, keys in cases.items():
+        model = eb.Model(grid, **{k: props[k] for k in keys})
+        for freq in (0.7, -3.0):
+            lv = solver._Level.from_model(model, eb.Field(grid, frequency=freq))
+            for k, n in enumerate(('eta_x', 'eta_y', 'eta_z')):
+                want = gh[f'vm_{case}_f{freq}_{n}'].ravel('F')
+                assert rel_err(lv.eta[k].download(), want) < 1e-15, (case, freq, n)
+            assert rel_err(lv.zeta.download(), gh[f'vm_{case}_f{freq}_zeta'].ravel('F')) < 1e-15
+            assert (lv.eta[1] is lv.eta[0]) == (case in ('iso', 'vti'))
+            assert (lv.eta[2] is lv.eta[0]) == (case in ('iso', 'hti'))
+    # other property maps
+    for mapping, arr in (('Conductivity', 1 / props['property_x']),
+                         ('LgResistivity', np.log10(props['property_x'])),
+                         ('LnConductivity', -np.log(props['property_x']))):
+        model = eb.Model(grid, property_x=arr, mapping=mapping)
+        lv = solver._Level.from_model(model, eb.Field(grid, frequency=0.7))
+        assert rel_err(lv.eta[0].download(), gh['vm_iso_f0.7_eta_x'].ravel('F')) < 1e-14
+
+
+def test_workspace_reuse(golden):
+    import emg3d_b200 as eb
+    from helpers import solve_case
+    c = solve_case(golden('solves'), 'config2_')
+    grid = eb.TensorMesh([c['hx'], c['hy'], c['hz']], c['origin'])
+    model = eb.Model(grid, **c['model'])
+    sfield = eb.Field(grid, c['sfield'].copy(), frequency=c['frequency'])
+    ws = eb.Workspace()
+    e1 = eb.solve(model, sfield, order='lex', workspace=ws, **c['kwargs'])
+    lv = ws.level(model, sfield)
+    e2 = eb.solve(model, sfield, order='lex', workspace=ws, **c['kwargs'])
+    assert ws.level(model, sfield) is lv                # hierarchy was reused
+    assert np.array_equal(e1.field, e2.field)
+    assert rel_err(e1.field, c['efield']) < 1e-8
+    model.property_x[...] *= 2.0                         # in-place change -> rebuilt
+    assert ws.level(model, sfield) is not lv
