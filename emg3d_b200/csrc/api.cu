@@ -58,6 +58,7 @@ struct emg3d_b200_level {
     const void* eta[3];
     const double* zeta;
     void* fac[3];        // cached line factorisations (device), per direction
+    void* diag;          // cached diagonal of A per edge (device), point smoother
     double* scratch;     // residual-norm partials
     double* norm2;       // device scalar
     // link to the parent (fine) level
@@ -79,6 +80,7 @@ static Model<T> model_of(const emg3d_b200_level* lv) {
         m.rh[a] = lv->rh[a];
     }
     m.zeta = lv->zeta;
+    m.diag = (const T*)lv->diag;
     return m;
 }
 
@@ -248,6 +250,8 @@ int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz, cons
 }
 
 int emg3d_b200_level_drop_factors(emg3d_b200_level* lv) {
+    if (lv->diag) cudaFree(lv->diag);
+    lv->diag = nullptr;
     for (int a = 0; a < 3; ++a) {
         if (lv->fac[a]) cudaFree(lv->fac[a]);
         lv->fac[a] = nullptr;
@@ -371,6 +375,13 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
     if (order != ORDER_LEX && order != ORDER_COLOR) return fail_msg("gauss_seidel: unknown order");
     if (nu <= 0) return 0;
     if (ldir == 0) {
+        if (!lv->diag) {
+            const size_t el = lv->cplx ? sizeof(cplx) : sizeof(double);
+            CK(cudaMalloc(&lv->diag, (size_t)n_edges(lv->d) * el));
+            if (lv->cplx) launch_edge_diag<cplx>(model_of<cplx>(lv), (cplx*)lv->diag, g_stream);
+            else launch_edge_diag<double>(model_of<double>(lv), (double*)lv->diag, g_stream);
+            CK_LAUNCH("edge_diag");
+        }
         if (lv->cplx)
             launch_gs_point<cplx>(model_of<cplx>(lv), (cplx*)e, (const cplx*)s, nu, order, g_stream);
         else

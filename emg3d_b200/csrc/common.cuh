@@ -69,6 +69,7 @@ struct Model {
     const double* zeta;
     const double* h[3];    // widths
     const double* rh[3];   // 1 / widths
+    const T* diag;         // diagonal of A per edge, field layout (point smoother; may be null)
 };
 
 // F-order extents of the three field components

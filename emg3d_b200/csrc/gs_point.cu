@@ -73,18 +73,16 @@ struct Faces {
         const T eq = E.p[Q][E.idx(Q, ro)];
         const T out = al_p * ep + al_q * eq;   // = -(c_out . e_out)
         constexpr int kq = 2 * (Q - 1) + (1 - SQ);      // transverse index of the Q-edge
+        // (diagonal entries come precombined from m.diag, see edge_diag_kernel)
         if (P == 0) {
             constexpr int j = 1 - SP;                   // which x-edge
-            add_real(n.dX[j], g * al_p * al_p);
             n.B[j][kq] += g * al_p * al_q;
             n.bX[j] += (g * al_p) * out;
         } else {
             constexpr int kp = 1 - SP;                  // P == 1: a y-edge
-            add_real(n.dT[kp], g * al_p * al_p);
             n.cyz[1 - SQ][1 - SP] += g * al_p * al_q;
             n.bT[kp] += (g * al_p) * out;
         }
-        add_real(n.dT[kq], g * al_q * al_q);
         n.bT[kq] += (g * al_q) * out;
     }
     template <int P, int Q>
@@ -130,23 +128,22 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
         for (int k = 0; k < 4; ++k) n.B[j][k] = 0.0;
     n.cyz[0][0] = n.cyz[0][1] = n.cyz[1][0] = n.cyz[1][1] = 0.0;
 
-    // diagonal: -1/4 sum of eta over the four cells around each local edge; rhs: source
+    // diagonal of A at the six local edges (precombined per level: four face terms
+    // minus 1/4 of the eta sum, see edge_diag_kernel); rhs: source
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const int u = (c + 1) % 3, v = (c + 2) % 3;
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-            const int64_t base = c0 + cs[c] * sg;
-            const T st = ldg(m.eta[c] + base) + ldg(m.eta[c] + base + cs[u]) +
-                         ldg(m.eta[c] + base + cs[v]) + ldg(m.eta[c] + base + cs[u] + cs[v]);
             int q[3] = {ix, iy, iz};
             q[c] += sg - 1;
-            const T src = ldg(S.p[c] + S.idx(c, q));
+            const int64_t id = S.idx(c, q);
+            const T src = ldg(S.p[c] + id);
+            const T dg = ldg(m.diag + (S.p[c] - S.p[0]) + id);
             if (c == 0) {
-                n.dX[sg] = -0.25 * st;
+                n.dX[sg] = dg;
                 n.bX[sg] = src;
             } else {
-                n.dT[2 * (c - 1) + sg] = -0.25 * st;
+                n.dT[2 * (c - 1) + sg] = dg;
                 n.bT[2 * (c - 1) + sg] = src;
             }
         }
@@ -243,6 +240,54 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
 }
 
 #undef SS
+
+// ---- precombined diagonal ------------------------------------------------------
+// diag(edge) = sum over the 4 faces around the edge of 1/2 M_f / h^2  -  1/4 sum
+// of eta over the 4 cells around it: the diagonal of A.  It depends on the grid
+// and the model only, so it is computed once per level; the point smoother then
+// loads 6 numbers per node instead of 24 eta values (and skips 12 updates).
+// Only interior edges (the unknowns) are filled; the rest is zero.
+template <typename T>
+__global__ void __launch_bounds__(256) edge_diag_kernel(Model<T> m, T* __restrict__ diag) {
+    int nd[3];
+    nd[0] = blockIdx.x * blockDim.x + threadIdx.x;
+    nd[1] = blockIdx.y * blockDim.y + threadIdx.y;
+    nd[2] = blockIdx.z * blockDim.z + threadIdx.z;
+    if (nd[0] > m.d.n[0] || nd[1] > m.d.n[1] || nd[2] > m.d.n[2]) return;
+    FieldView<T> D(diag, m.d);
+    const int64_t cs[3] = {1, m.d.n[0], (int64_t)m.d.n[0] * m.d.n[1]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int u = (c + 1) % 3, v = (c + 2) % 3;
+        if (nd[c] >= m.d.n[c]) continue;
+        T val = zero_<T>();
+        if (nd[u] >= 1 && nd[u] < m.d.n[u] && nd[v] >= 1 && nd[v] < m.d.n[v]) {
+            const int64_t c00 = cs[c] * nd[c] + cs[u] * (nd[u] - 1) + cs[v] * (nd[v] - 1);
+            const double z00 = ldg(m.zeta + c00), z10 = ldg(m.zeta + c00 + cs[u]),
+                         z01 = ldg(m.zeta + c00 + cs[v]), z11 = ldg(m.zeta + c00 + cs[u] + cs[v]);
+            const double ru0 = ldg(m.rh[u] + nd[u] - 1), ru1 = ldg(m.rh[u] + nd[u]);
+            const double rv0 = ldg(m.rh[v] + nd[v] - 1), rv1 = ldg(m.rh[v] + nd[v]);
+            // faces spanned by (c, u): at u-cell 0/1, zeta summed over the two v-cells
+            const double acc = 0.5 * (z00 + z01) * ru0 * ru0 + 0.5 * (z10 + z11) * ru1 * ru1 +
+                               0.5 * (z00 + z10) * rv0 * rv0 + 0.5 * (z01 + z11) * rv1 * rv1;
+            const T st = ldg(m.eta[c] + c00) + ldg(m.eta[c] + c00 + cs[u]) +
+                         ldg(m.eta[c] + c00 + cs[v]) + ldg(m.eta[c] + c00 + cs[u] + cs[v]);
+            val = -0.25 * st;
+            add_real(val, acc);
+        }
+        D.p[c][D.idx(c, nd)] = val;
+    }
+}
+
+template <typename T>
+void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st) {
+    dim3 b(32, 4, 2);
+    dim3 g((m.d.n[0] + 1 + b.x - 1) / b.x, (m.d.n[1] + 1 + b.y - 1) / b.y,
+           (m.d.n[2] + 1 + b.z - 1) / b.z);
+    ++g_launch_count; edge_diag_kernel<T><<<g, b, 0, st>>>(m, diag);
+}
+template void launch_edge_diag<double>(const Model<double>&, double*, cudaStream_t);
+template void launch_edge_diag<cplx>(const Model<cplx>&, cplx*, cudaStream_t);
 
 // ---- schedules ---------------------------------------------------------------
 

@@ -24,6 +24,9 @@ int64_t residual_scratch_doubles(const Dims& d);
 
 template <typename T>
 void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cudaStream_t st);
+// diagonal of A per edge (field layout), read by the point smoother through m.diag
+template <typename T>
+void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st);
 
 // line smoothers: factor once per (level, direction), then sweep
 int64_t line_factor_elems(const Dims& d, int dir);     // number of T elements
