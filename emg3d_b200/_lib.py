@@ -91,6 +91,13 @@ _SIGNATURES = {
     'emg3d_b200_host_amat_x': (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 13),
     'emg3d_b200_host_gauss_seidel': (c_int, [c_int] * 6 + [c_void_p] * 13 + [c_int]),
     'emg3d_b200_host_solve': (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    'emg3d_b200_comm_unique_id': (c_int, [c_void_p]),
+    'emg3d_b200_comm_init': (c_int, [c_void_p, c_int, c_int]),
+    'emg3d_b200_comm_size': (c_int, [POINTER(c_int), POINTER(c_int)]),
+    'emg3d_b200_comm_destroy': (c_int, []),
+    'emg3d_b200_comm_sendrecv': (c_int, [c_int, POINTER(c_void_p), POINTER(c_size_t),
+                                         POINTER(c_int), POINTER(c_int)]),
+    'emg3d_b200_comm_allreduce_sum': (c_int, [c_void_p, c_int]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -86,6 +86,10 @@ static Model<T> model_of(const emg3d_b200_level* lv) {
 
 extern "C" {
 
+// hooks for comm.cu (not part of the public header)
+int emg3d_b200_internal_fail(const char* msg) { return fail_msg(msg); }
+void* emg3d_b200_internal_stream(void) { return (void*)g_stream; }
+
 int emg3d_b200_abi_version(void) { return 1; }
 
 const char* emg3d_b200_last_error(void) { return g_err.c_str(); }
@@ -372,7 +376,9 @@ int emg3d_b200_residual_norm(emg3d_b200_level* lv, const void* s, const void* e,
 int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu, int ldir, int order) {
     NEED_MODEL(lv);
     if (ldir < 0 || ldir > 3) return fail_msg("gauss_seidel: ldir must be 0..3");
-    if (order != ORDER_LEX && order != ORDER_COLOR) return fail_msg("gauss_seidel: unknown order");
+    // bits 8+ of `order` carry the number of sweeps already done (sweep direction phase)
+    if ((order & 0xff) != ORDER_LEX && (order & 0xff) != ORDER_COLOR)
+        return fail_msg("gauss_seidel: unknown order");
     if (nu <= 0) return 0;
     if (ldir == 0) {
         if (!lv->diag) {

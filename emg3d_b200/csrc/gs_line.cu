@@ -755,7 +755,8 @@ gs_line_small_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, i
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
     const int npi = m.d.n[A::p] - 1, nqi = m.d.n[A::q] - 1;
-    bool back = false;
+    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
         if (order == ORDER_LEX) {
@@ -822,7 +823,8 @@ static void gs_dir(const Model<T>& m, const T* fac, T* e, const T* s, int nu, in
         ++g_launch_count; gs_line_small_kernel<T, D><<<1, threads, 0, st>>>(m, fac, ls, e, s, nu, order);
         return;
     }
-    bool back = false;
+    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
         if (order == ORDER_LEX) {

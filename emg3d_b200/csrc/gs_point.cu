@@ -365,7 +365,8 @@ gs_point_small_kernel(Model<T> m, T* e, const T* s, int nu, int order) {
     FieldView<const T> S(s, m.d);
     const int nx = m.d.n[0], ny = m.d.n[1], nz = m.d.n[2];
     const int nint = (nx - 1) * (ny - 1) * (nz - 1);
-    bool back = false;
+    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;                       // first sweep runs descending (core.py:301,311)
         if (order == ORDER_LEX) {
@@ -408,7 +409,8 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
         ++g_launch_count; gs_point_small_kernel<T><<<1, threads, 0, st>>>(m, e, s, nu, order);
         return;
     }
-    bool back = false;
+    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
         if (order == ORDER_LEX) {

@@ -142,6 +142,21 @@ int emg3d_b200_dot_host(int cplx, long long n, const void* x, const void* y, int
 int emg3d_b200_axpby(int cplx, long long n, double a_re, double a_im, const void* x,
                      double b_re, double b_im, void* y);
 
+/* ---- multi-GPU: z-slab decomposition (new functionality) ------
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, distributes it
+ * by any means (e.g. torch.distributed / a file), every rank calls comm_init.
+ * comm_sendrecv posts n point-to-point transfers of raw bytes (device pointers)
+ * in one NCCL group on the library stream: the halo exchange of the E-field
+ * edges between smoothing sweeps.  comm_allreduce_sum sums doubles in place
+ * (norms, dot products).  libnccl.so.2 is opened at run time.                  */
+int emg3d_b200_comm_unique_id(void* out128);
+int emg3d_b200_comm_init(const void* unique_id128, int nranks, int rank);
+int emg3d_b200_comm_size(int* nranks, int* rank);
+int emg3d_b200_comm_destroy(void);
+int emg3d_b200_comm_sendrecv(int n, void* const* ptrs, const size_t* nbytes, const int* peers,
+                             const int* is_send);
+int emg3d_b200_comm_allreduce_sum(double* dev, int n);
+
 /* ---- host-array convenience entry points ----------------------------------
  * Exact signatures of the reference kernels on HOST arrays (upload, run,
  * download); these are what a ctypes/cffi shim inside emg3d/core.py would

@@ -1,0 +1,192 @@
+"""CPU tests of the z-slab decomposition logic (emg3d_b200/parallel.py).
+
+The index arithmetic (ownership, local grids, halo-exchange and gather plans) is
+independent of the transport.  It is checked (i) in one process with a virtual
+transport that pairs every send with the peer's receive, for several rank counts
+and levels, and (ii) with real point-to-point messages between two ``gloo`` ranks.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from emg3d_b200 import parallel
+
+
+def field_sizes(nx, ny, nzc):
+    return nx * (ny + 1) * (nzc + 1) + (nx + 1) * ny * (nzc + 1) + (nx + 1) * (ny + 1) * nzc
+
+
+def global_field(nx, ny, nz):
+    """A field whose value encodes (component, ix, iy, iz): easy to verify."""
+    out = []
+    for c, shp in enumerate(((nx, ny + 1, nz + 1), (nx + 1, ny, nz + 1), (nx + 1, ny + 1, nz))):
+        i, j, k = np.meshgrid(*[np.arange(n) for n in shp], indexing='ij')
+        out.append((1e6 * (c + 1) + 1e4 * k + 1e2 * j + i + 0.5j * (k + 1)).ravel('F'))
+    return np.concatenate(out)
+
+
+def local_from_global(part, level, rank, nx, ny, gfield, owned_only):
+    """Rank-local field: owned part from the global field, NaN elsewhere (or the whole slab)."""
+    lo, hi = part.local(level, rank)
+    loc = np.full(field_sizes(nx, ny, hi - lo), np.nan + 0j)
+    if owned_only:
+        nzl = part.nz_level(level)
+        copies, _, _ = parallel.gather_plan(part, level, rank, nx, ny)
+        for loff, goff, n in copies:
+            loc[loff:loff + n] = gfield[goff:goff + n]
+    else:
+        for goff, loff, n in parallel.scatter_ranges(part, level, rank, nx, ny):
+            loc[loff:loff + n] = gfield[goff:goff + n]
+    return loc
+
+
+@pytest.mark.parametrize('nz,nranks,n_dist', [(64, 2, 3), (64, 4, 2), (256, 8, 3), (96, 3, 2),
+                                               (32, 2, 1), (512, 8, 4)])
+def test_partition_is_consistent(nz, nranks, n_dist):
+    part = parallel.SlabPartition(nz, nranks, n_dist)
+    for level in range(n_dist + 1):
+        b = part.bounds(level)
+        nzl = part.nz_level(level)
+        assert b[0] == 0 and b[-1] == nzl + 1 and all(x < y for x, y in zip(b[:-1], b[1:]))
+        for r in range(nranks):
+            lo, hi = part.local(level, r)
+            p0, p1 = part.owned(level, r)
+            assert 0 <= lo <= p0 and p1 - 1 <= hi <= nzl
+            if level < n_dist:
+                # local grids coarsen onto the next level's local grids
+                assert lo % 2 == 0 and (hi - lo) % 2 == 0
+                clo, chi = part.local(level + 1, r)
+                assert (clo, chi) == (lo // 2, hi // 2)
+                # ownership coarsens consistently: even owned planes <-> coarse owned planes
+                c0, c1 = part.owned(level + 1, r)
+                assert c0 == (p0 + 1) // 2 and c1 - 1 == (p1 - 1) // 2
+            # halo: one plane above, >= 1 below
+            if r > 0:
+                assert p0 - lo == 2 ** (n_dist - level)
+            if r < nranks - 1:
+                assert hi == p1
+
+
+def test_partition_rejects_bad_input():
+    with pytest.raises(ValueError):
+        parallel.SlabPartition(60, 2, 3)        # not a multiple of 8
+    with pytest.raises(ValueError):
+        parallel.SlabPartition(16, 4, 3)        # 2 aligned blocks for 4 ranks
+
+
+@pytest.mark.parametrize('nz,nranks,n_dist', [(64, 2, 3), (64, 4, 2), (96, 3, 2)])
+def test_exchange_and_gather_plans_virtual(nz, nranks, n_dist):
+    """All ranks in one process; sends are paired with the peers' receives in order."""
+    nx, ny = 6, 4
+    part = parallel.SlabPartition(nz, nranks, n_dist)
+    for level in range(n_dist + 1):
+        sx, sy = nx, ny                                   # x, y extents do not matter here
+        nzl = part.nz_level(level)
+        g = global_field(sx, sy, nzl)
+        locs = [local_from_global(part, level, r, sx, sy, g, owned_only=True) for r in range(nranks)]
+        plans = [parallel.exchange_plan(part, level, r, sx, sy) for r in range(nranks)]
+        # pair sends and receives per (src, dst), in order
+        for src in range(nranks):
+            for dst in range(nranks):
+                sends = [(o, n) for s, p, o, n in plans[src] if s and p == dst]
+                recvs = [(o, n) for s, p, o, n in plans[dst] if not s and p == src]
+                assert [n for _, n in sends] == [n for _, n in recvs]
+                for (so, n), (ro, _) in zip(sends, recvs):
+                    locs[dst][ro:ro + n] = locs[src][so:so + n]
+        for r in range(nranks):
+            want = local_from_global(part, level, r, sx, sy, g, owned_only=False)
+            lo, hi = part.local(level, r)
+            p0, p1 = part.owned(level, r)
+            px, py, pz = sx * (sy + 1), (sx + 1) * sy, (sx + 1) * (sy + 1)
+            ox, oy, oz = 0, px * (hi - lo + 1), px * (hi - lo + 1) + py * (hi - lo + 1)
+            # planes the smoother / residual / transfer operators read around the owned block
+            for p in range(max(p0 - 1, lo), min(p1, hi) + 1):
+                for off, sz in ((ox, px), (oy, py)):
+                    a = off + sz * (p - lo)
+                    np.testing.assert_array_equal(locs[r][a:a + sz], want[a:a + sz])
+            first_layer = max(p0 - 2, lo) if level < n_dist else max(p0 - 1, lo)
+            for k in range(first_layer, min(p1, hi)):
+                a = oz + pz * (k - lo)
+                np.testing.assert_array_equal(locs[r][a:a + pz], want[a:a + pz])
+        # gather: every global element is owned by exactly one rank
+        out = np.full(g.size, np.nan + 0j)
+        cover = np.zeros(g.size, dtype=int)
+        for r in range(nranks):
+            copies, sends, recvs = parallel.gather_plan(part, level, r, sx, sy)
+            for loff, goff, n in copies:
+                out[goff:goff + n] = locs[r][loff:loff + n]
+                cover[goff:goff + n] += 1
+            # what r sends to q is what q expects from r
+            for q in range(nranks):
+                if q == r:
+                    continue
+                _, _, qrecvs = parallel.gather_plan(part, level, q, sx, sy)
+                assert [n for p, _, n in sends if p == q] == [n for p, _, n in qrecvs if p == r]
+        assert np.all(cover == 1)
+        np.testing.assert_array_equal(out, g)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, nz, n_dist, nx, ny, results):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        part = parallel.SlabPartition(nz, world, n_dist)
+        ok = True
+        for level in range(n_dist + 1):
+            nzl = part.nz_level(level)
+            g = global_field(nx, ny, nzl)
+            loc = local_from_global(part, level, rank, nx, ny, g, owned_only=True)
+            view = torch.from_numpy(loc.view(np.float64))           # (re, im) pairs
+            reqs = []
+            for is_send, peer, off, n in parallel.exchange_plan(part, level, rank, nx, ny):
+                t = view[2 * off:2 * (off + n)]
+                reqs.append(dist.isend(t, peer) if is_send else dist.irecv(t, peer))
+            for q in reqs:
+                q.wait()
+            want = local_from_global(part, level, rank, nx, ny, g, owned_only=False)
+            lo, hi = part.local(level, rank)
+            p0, p1 = part.owned(level, rank)
+            px = nx * (ny + 1)
+            for p in range(max(p0 - 1, lo), min(p1, hi) + 1):
+                a = px * (p - lo)
+                ok &= bool(np.array_equal(loc[a:a + px], want[a:a + px]))
+            # all-gather into the global layout
+            out = np.full(g.size, np.nan + 0j)
+            oview = torch.from_numpy(out.view(np.float64))
+            copies, sends, recvs = parallel.gather_plan(part, level, rank, nx, ny)
+            for loff, goff, n in copies:
+                out[goff:goff + n] = loc[loff:loff + n]
+            reqs = [dist.isend(view[2 * o:2 * (o + n)], p) for p, o, n in sends]
+            reqs += [dist.irecv(oview[2 * o:2 * (o + n)], p) for p, o, n in recvs]
+            for q in reqs:
+                q.wait()
+            ok &= bool(np.array_equal(out, g))
+            # owned sums add up to the global sum (norms)
+            s = sum(float(np.sum(np.abs(loc[o:o + n]) ** 2))
+                    for o, n in parallel.owned_ranges(part, level, rank, nx, ny))
+            t = torch.tensor([s], dtype=torch.float64)
+            dist.all_reduce(t)
+            ok &= bool(abs(t.item() - float(np.sum(np.abs(g) ** 2))) <= 1e-12 * t.item())
+        results[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_and_gather_with_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as manager:
+        results = manager.dict()
+        mp.spawn(_gloo_worker, args=(world, port, 32, 2, 5, 3, results), nprocs=world, join=True)
+        assert dict(results) == {0: True, 1: True}
