@@ -66,6 +66,7 @@ _SIGNATURES = {
     'emg3d_b200_level_destroy': (c_int, [c_void_p]),
     'emg3d_b200_level_set_model': (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                            c_void_p, c_void_p]),
+    'emg3d_b200_level_window': (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
     'emg3d_b200_level_factor_bytes': (c_int, [c_void_p, c_int, POINTER(c_size_t)]),
     'emg3d_b200_level_drop_factors': (c_int, [c_void_p]),
     'emg3d_b200_level_link': (c_int, [c_void_p, c_void_p, POINTER(c_int),
@@ -347,6 +348,15 @@ class LevelHandle:
             keep += [li, fr]
             lp[a], fp[a] = li.ctypes.data, fr.ctypes.data
         check(load().emg3d_b200_level_link(self.ptr, fine.ptr, cf, wp, lp, fp))
+
+    def window(self, z0, nz):
+        """View on cells [z0, z0 + nz) along z (model must be set); see the header."""
+        p = c_void_p(0)
+        check(load().emg3d_b200_level_window(byref(p), self.ptr, int(z0), int(nz)))
+        w = LevelHandle.__new__(LevelHandle)
+        w.ptr, w.shape = p.value, (self.shape[0], self.shape[1], int(nz))
+        w._keep = self              # the parent owns the arrays the window points into
+        return w
 
     def factor_bytes(self, ldir):
         n = c_size_t(0)

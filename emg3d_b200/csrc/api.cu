@@ -68,6 +68,7 @@ struct emg3d_b200_level {
     double* w[9];        // device weights
     int* lo[3];
     double* fr[3];
+    int is_window;       // z-window of another level: h / rh are borrowed
 };
 
 template <typename T>
@@ -80,7 +81,9 @@ static Model<T> model_of(const emg3d_b200_level* lv) {
         m.rh[a] = lv->rh[a];
     }
     m.zeta = lv->zeta;
-    m.diag = (const T*)lv->diag;
+    // the point smoother addresses the diagonal relative to the x-component of the
+    // (windowed) field view, so the window offset of that component is applied here
+    m.diag = lv->diag ? (const T*)lv->diag + (int64_t)lv->d.n[0] * (lv->d.n[1] + 1) * lv->d.zoff : nullptr;
     return m;
 }
 
@@ -267,8 +270,10 @@ int emg3d_b200_level_destroy(emg3d_b200_level* lv) {
     if (!lv) return 0;
     emg3d_b200_level_drop_factors(lv);
     for (int a = 0; a < 3; ++a) {
-        cudaFree(lv->h[a]);
-        cudaFree(lv->rh[a]);
+        if (!lv->is_window) {
+            cudaFree(lv->h[a]);
+            cudaFree(lv->rh[a]);
+        }
         cudaFree(lv->lo[a]);
         cudaFree(lv->fr[a]);
     }
@@ -286,6 +291,33 @@ int emg3d_b200_level_set_model(emg3d_b200_level* lv, int cplx, const void* eta_x
     lv->cplx = cplx ? 1 : 0;
     lv->eta[0] = eta_x; lv->eta[1] = eta_y; lv->eta[2] = eta_z;
     lv->zeta = zeta;
+    return 0;
+}
+
+int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* parent, int z0, int nz) {
+    NEED_INIT();
+    if (parent->is_window) return fail_msg("level_window: parent is a window itself");
+    if (parent->cplx < 0) return fail_msg("level_window: parent has no model");
+    if (z0 < 0 || nz < 1 || z0 + nz > parent->d.n[2]) return fail_msg("level_window: range outside the parent");
+    emg3d_b200_level* lv = new emg3d_b200_level();
+    memset(lv, 0, sizeof *lv);
+    lv->is_window = 1;
+    lv->d = parent->d;
+    lv->d.n[2] = nz;
+    lv->d.zoff = z0;
+    lv->d.nzf = parent->d.n[2];
+    for (int a = 0; a < 3; ++a) {
+        lv->h[a] = parent->h[a] + (a == 2 ? z0 : 0);
+        lv->rh[a] = parent->rh[a] + (a == 2 ? z0 : 0);
+    }
+    lv->cplx = parent->cplx;
+    const size_t el = parent->cplx ? sizeof(cplx) : sizeof(double);
+    const size_t coff = (size_t)parent->d.n[0] * parent->d.n[1] * z0;
+    for (int a = 0; a < 3; ++a) lv->eta[a] = (const char*)parent->eta[a] + coff * el;
+    lv->zeta = parent->zeta + coff;
+    CK(cudaMalloc(&lv->scratch, sizeof(double) * residual_scratch_doubles(lv->d)));
+    CK(cudaMalloc(&lv->norm2, sizeof(double) * 2));
+    *out = lv;
     return 0;
 }
 

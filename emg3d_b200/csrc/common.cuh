@@ -60,7 +60,13 @@ __device__ __forceinline__ cplx ldg(const cplx* p) {
 // ---- grid / model description passed by value to kernels -------------------
 struct Dims {
     int n[3];          // cells per axis
+    // z-window (multi-GPU slabs): the arrays hold `nzf` cells along z (0 = no
+    // window, i.e. n[2]); this view starts at cell / node plane `zoff` of them and
+    // spans n[2] cells.  z is the slowest axis, so a window of a component or of a
+    // cell array is a contiguous range: only base pointers move.
+    int zoff, nzf;
 };
+__host__ __device__ __forceinline__ int full_nz(const Dims& d) { return d.nzf > 0 ? d.nzf : d.n[2]; }
 
 template <typename T>
 struct Model {
@@ -75,7 +81,7 @@ struct Model {
 // F-order extents of the three field components
 __host__ __device__ __forceinline__ int64_t comp_d0(const Dims& d, int c) { return d.n[0] + (c != 0); }
 __host__ __device__ __forceinline__ int64_t comp_d1(const Dims& d, int c) { return d.n[1] + (c != 1); }
-__host__ __device__ __forceinline__ int64_t comp_d2(const Dims& d, int c) { return d.n[2] + (c != 2); }
+__host__ __device__ __forceinline__ int64_t comp_d2(const Dims& d, int c) { return full_nz(d) + (c != 2); }
 __host__ __device__ __forceinline__ int64_t comp_size(const Dims& d, int c) {
     return comp_d0(d, c) * comp_d1(d, c) * comp_d2(d, c);
 }
@@ -98,9 +104,9 @@ struct FieldView {
     __host__ __device__ FieldView(T* base, const Dims& d) {
         int64_t o = 0;
         for (int c = 0; c < 3; ++c) {
-            p[c] = base ? base + o : nullptr;
             s1[c] = comp_d0(d, c);
             s2[c] = comp_d0(d, c) * comp_d1(d, c);
+            p[c] = base ? base + o + s2[c] * d.zoff : nullptr;
             o += comp_size(d, c);
         }
     }

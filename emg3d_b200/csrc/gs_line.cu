@@ -572,9 +572,14 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a, Loader
     T eo[4];                             // parallel neighbours of L_i
 #pragma unroll
     for (int k = 0; k < 4; ++k) eo[k] = a.ed[a.oLn[k]];
-    T wT[4];                             // transverse part of previous block's solution
-#pragma unroll
-    for (int k = 0; k < 4; ++k) wT[k] = zero_<T>();
+    // transverse part of the previous block's solution; for the first block the
+    // (fixed) transverse edges on the line's start plane: zero on a PEC boundary,
+    // halo data of the neighbouring slab on a multi-GPU z-window
+    T wT[4];
+    wT[0] = a.ep[a.oP[0][1]];
+    wT[1] = a.ep[a.oP[1][1]];
+    wT[2] = a.eq[a.oQ[0][1]];
+    wT[3] = a.eq[a.oQ[1][1]];
 
     for (int i = 0; i < N; ++i) {
         const bool last = (i == N - 1);
@@ -596,11 +601,14 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a, Loader
             f[k] = -gs[k] * ln.a_side(k) * rd;
             dk[k] = -gs[k] * rd * rd;
         }
-        if (i > 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[0] -= f[k] * wT[k];
-        }
+        for (int k = 0; k < 4; ++k) y[0] -= f[k] * wT[k];
         if (last) {
+            // coupling to the fixed transverse edges on the line's end plane
+            const T tN[4] = {a.ep[a.oP[0][1] + a.sp * N], a.ep[a.oP[1][1] + a.sp * N],
+                             a.eq[a.oQ[0][1] + a.sq * N], a.eq[a.oQ[1][1] + a.sq * N]};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[0] += f[k] * tN[k];
             a.ed[a.oL + a.sd * i] = y[0] * w[0];
             break;
         }
@@ -627,9 +635,14 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a, Loader
                 y[1 + jp] += (g * ap) * out;
                 y[3 + jq] += (g * aq) * out;
             }
-        if (i > 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[1 + k] -= dk[k] * wT[k];
+        for (int k = 0; k < 4; ++k) y[1 + k] -= dk[k] * wT[k];
+        if (i == N - 2) {
+            // last interior node: its neighbours on the end plane are fixed data
+            const T tN[4] = {a.ep[a.oP[0][1] + a.sp * N], a.ep[a.oP[1][1] + a.sp * N],
+                             a.eq[a.oQ[0][1] + a.sq * N], a.eq[a.oQ[1][1] + a.sq * N]};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[1 + k] += (gn[k] * rdn * rdn) * tN[k];
         }
         solve5<T>(w, y, false);
         a.ed[a.oL + a.sd * i] = y[0];

@@ -74,7 +74,7 @@ restrict_kernel(Dims fine, Dims coarse, Axis3 cf, const T* __restrict__ r, T* __
 template <typename T>
 void launch_restrict(const Dims& fine, const int* cflag, const T* r, T* cr, const double* const* wl,
                      const double* const* w0, const double* const* wr, cudaStream_t st) {
-    Dims coarse;
+    Dims coarse = {};
     Axis3 cf;
     WPtrs w;
     for (int a = 0; a < 3; ++a) {
@@ -131,7 +131,7 @@ prolong_kernel(Dims fine, Dims coarse, Axis3 cf, T* __restrict__ e, const T* __r
 template <typename T>
 void launch_prolong(const Dims& fine, const int* cflag, T* e, const T* ce, const int* const* lo,
                     const double* const* frac, cudaStream_t st) {
-    Dims coarse;
+    Dims coarse = {};
     Axis3 cf;
     IPtrs ip;
     for (int a = 0; a < 3; ++a) {
@@ -174,7 +174,7 @@ restrict_cells_kernel(Dims fine, Dims coarse, Axis3 cf, const T* __restrict__ p,
 
 template <typename T>
 void launch_restrict_cells(const Dims& fine, const int* cflag, const T* p, T* cp, cudaStream_t st) {
-    Dims coarse;
+    Dims coarse = {};
     Axis3 cf;
     for (int a = 0; a < 3; ++a) {
         cf.v[a] = cflag[a];

@@ -257,6 +257,15 @@ class _DLevel:
         self.index, self.lv = level, lv
         self.plan = exchange_plan(part, level, rank, nx, ny)
         self.owned = owned_ranges(part, level, rank, nx, ny)
+        # Smoother and residual run on the z-window [p0 - 1, hi] of the local grid:
+        # one halo plane on either side, refreshed by the exchange and fixed during a
+        # sweep.  The deeper halo planes below only exist to keep the local grids
+        # nested under coarsening; no kernel result ever depends on them.
+        lo, hi = part.local(level, rank)
+        p0, _ = part.owned(level, rank)
+        z0 = 0 if rank == 0 else p0 - 1 - lo
+        self.win = lv.handle if z0 == 0 else lv.handle.window(z0, hi - lo - z0)
+        lv.res_buffer().zero()
 
 
 class DistributedMultigrid:
@@ -413,7 +422,7 @@ class DistributedMultigrid:
     def residual(self, dl, s, e, norm=False):
         lib = self._lib.load()
         r = dl.lv.res_buffer()
-        self._lib.check(lib.emg3d_b200_residual(dl.lv.handle.ptr, s.ptr, e.ptr, r.ptr, None))
+        self._lib.check(lib.emg3d_b200_residual(dl.win.ptr, s.ptr, e.ptr, r.ptr, None))
         if norm:
             return float(np.sqrt(self.sum_owned(dl, r).real))
         self.exchange(dl, r)
@@ -423,12 +432,10 @@ class DistributedMultigrid:
         solver, lib = self._solver, self._lib.load()
         c_lr_dir = int(solver._current_lr_dir(lr_dir, dl.lv.grid))
         dirs = solver._LR_DIRS[c_lr_dir] or (0,)
-        if 3 in dirs:
-            raise NotImplementedError("z-line relaxation is not distributed (lines cross slabs)")
         for ldir in dirs:
             for sweep in range(int(nu)):
                 self._lib.check(lib.emg3d_b200_gauss_seidel(
-                    dl.lv.handle.ptr, e.ptr, s.ptr, 1, ldir, self.order | (sweep << 8)))
+                    dl.win.ptr, e.ptr, s.ptr, 1, ldir, self.order | (sweep << 8)))
                 self.exchange(dl, e)
 
     # ---- the cycle ---------------------------------------------------------------------

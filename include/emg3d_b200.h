@@ -72,6 +72,13 @@ int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz,
 int emg3d_b200_level_destroy(emg3d_b200_level* lv);
 int emg3d_b200_level_set_model(emg3d_b200_level* lv, int cplx, const void* eta_x,
                                const void* eta_y, const void* eta_z, const double* zeta);
+/* z-window of a level that has its model set (multi-GPU slabs): a
+ * view on cells [z0, z0 + nz) along z of the parent's arrays.  Field pointers
+ * passed to kernels on the window are the PARENT's full arrays; the kernels
+ * touch the window only, its first and last node plane acting as fixed boundary
+ * data (halo planes).  Owns its cached factorisations; destroy before the parent. */
+int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* parent, int z0,
+                            int nz);
 /* bytes of the cached factorisation of line direction ldir (1, 2, 3) */
 int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes);
 int emg3d_b200_level_drop_factors(emg3d_b200_level* lv);

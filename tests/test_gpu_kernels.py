@@ -139,6 +139,25 @@ def test_single_block_exactness(core, order):
         assert np.linalg.norm(inner) < 1e-12 * np.linalg.norm(c['s'])
 
 
+@pytest.mark.parametrize('order', ['lex', 'color'])
+def test_single_block_exactness_nonzero_boundary(core, order):
+    """Same with non-zero values on ALL boundary edges, including the planes at the
+    ends of a line: the boundary planes of a z-slab are halo data of the neighbouring
+    GPU, not PEC zeros, and every smoother must treat them as Dirichlet data."""
+    rng = np.random.default_rng(17)
+    for ldir, shape in ((0, (2, 2, 2)), (1, (7, 2, 2)), (2, (2, 6, 2)), (3, (2, 2, 5))):
+        c = random_case(rng, shape, True)
+        n = c['e'].size
+        e = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        getattr(core, GS[ldir])(*split_field(shape, e), *split_field(shape, c['s']), *_margs(c), 1,
+                                order=order)
+        r = c['s'].copy()
+        core.amat_x(*split_field(shape, r), *split_field(shape, e), *_margs(c))
+        rx, ry, rz = split_field(shape, r)
+        inner = np.r_[rx[:, 1:-1, 1:-1].ravel(), ry[1:-1, :, 1:-1].ravel(), rz[1:-1, 1:-1, :].ravel()]
+        assert np.linalg.norm(inner) < 1e-11 * np.linalg.norm(c['s']), ldir
+
+
 def test_line_equals_point_on_degenerate_grids(core):
     """With a single interior node along the line a line sweep is a point sweep
     (the reference's own test of the line smoothers, tests/test_core.py:88-139)."""
@@ -321,3 +340,65 @@ def test_workspace_reuse(golden):
     assert rel_err(e1.field, c['efield']) < 1e-8
     model.property_x[...] *= 2.0                         # in-place change -> rebuilt
     assert ws.level(model, sfield) is not lv
+
+
+@pytest.mark.parametrize('cplx', [True, False])
+def test_z_window_equals_subgrid(core, cplx):
+    """Kernels on a z-window of a level (multi-GPU slabs) == kernels on the sub-grid.
+
+    The smoothers and the residual run on cells [z0, z0 + nz) of the full arrays;
+    the result must equal the same kernel on arrays sliced out on the host, and
+    nothing outside the window may change.
+    """
+    from emg3d_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    shape, z0, nzw = (10, 7, 13), 4, 6
+    c = random_case(rng, shape, cplx, aliased=True)
+    dt = c['e'].dtype
+    nx, ny, nz = shape
+    n = c['e'].size
+    e0 = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)   # non-zero halos
+    handle = _lib.LevelHandle((c['hx'], c['hy'], c['hz']))
+    d_eta = _lib.DeviceArray.from_host(np.asfortranarray(c['eta_x']).ravel('F').astype(dt))
+    d_zeta = _lib.DeviceArray.from_host(np.asfortranarray(c['zeta']).ravel('F'))
+    handle.set_model(cplx, d_eta, d_eta, d_eta, d_zeta)
+    win = handle.window(z0, nzw)
+    d_s = _lib.DeviceArray.from_host(c['s'])
+
+    def sub(f):        # sliced copies (fx, fy, fz) of a full field for the window
+        fx, fy, fz = split_field(shape, f)
+        return [np.asfortranarray(fx[:, :, z0:z0 + nzw + 1]), np.asfortranarray(fy[:, :, z0:z0 + nzw + 1]),
+                np.asfortranarray(fz[:, :, z0:z0 + nzw])]
+
+    def scatter(full, parts):
+        out = full.copy()
+        fx, fy, fz = split_field(shape, out)
+        fx[:, :, z0:z0 + nzw + 1], fy[:, :, z0:z0 + nzw + 1], fz[:, :, z0:z0 + nzw] = parts
+        return out
+
+    sl = np.s_[:, :, z0:z0 + nzw]
+    margs = (np.asfortranarray(c['eta_x'][sl]),) * 3 + (np.asfortranarray(c['zeta'][sl]),
+                                                         c['hx'], c['hy'], c['hz'][z0:z0 + nzw])
+    margs = (margs[0], margs[0], margs[0]) + margs[3:]
+    for ldir, name in enumerate(GS):
+        for order in ('lex', 'color'):
+            d_e = _lib.DeviceArray.from_host(e0)
+            _lib.check(lib.emg3d_b200_gauss_seidel(win.ptr, d_e.ptr, d_s.ptr, 2, ldir,
+                                                   core.order_id(order)))
+            got = d_e.download()
+            es = sub(e0)
+            getattr(core, name)(*es, *sub(c['s']), *margs, 2, order=order)
+            want = scatter(e0, es)
+            assert rel_err(got, want) < 1e-12, (name, order)
+    # residual: interior planes of the window agree with the sub-grid residual
+    d_e = _lib.DeviceArray.from_host(e0)
+    d_r = _lib.DeviceArray(n, dt)
+    d_r.zero()
+    _lib.check(lib.emg3d_b200_residual(win.ptr, d_s.ptr, d_e.ptr, d_r.ptr, None))
+    got = d_r.download()
+    rs = sub(c['s'])
+    core.amat_x(*rs, *sub(e0), *margs)
+    want = scatter(np.zeros(n, dtype=dt), rs)
+    assert rel_err(got, want) < 1e-13
+    win.free()

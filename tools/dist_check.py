@@ -23,6 +23,7 @@ from emg3d_b200 import _lib, parallel, recipes  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     cycle = sys.argv[2] if len(sys.argv) > 2 else 'V'
+    lr = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local_rank = int(os.environ.get('LOCAL_RANK', rank))
     dist.init_process_group('gloo')
@@ -43,7 +44,7 @@ def main():
     _lib.sync()
     dist.barrier()
     t0 = time.perf_counter()
-    info = dmg.solve(cycle=cycle, tol=1e-9, maxit=40)
+    info = dmg.solve(cycle=cycle, tol=1e-9, maxit=40, linerelaxation=lr)
     _lib.sync()
     dt = time.perf_counter() - t0
     out = np.zeros(grid.n_edges, dtype=complex)
@@ -54,12 +55,12 @@ def main():
     if rank == 0:
         t0 = time.perf_counter()
         e1, i1 = eb.solve(model, sfield, plain=True, cycle=cycle, tol=1e-9, maxit=40,
-                          return_info=True)
+                          linerelaxation=lr, return_info=True)
         _lib.sync()
         dt1 = time.perf_counter() - t0
         err = np.linalg.norm(out - e1.field) / np.linalg.norm(e1.field)
         print(json.dumps({
-            'shape': grid.shape_cells, 'nranks': world, 'n_dist': dmg.n_dist, 'cycle': cycle,
+            'shape': grid.shape_cells, 'nranks': world, 'n_dist': dmg.n_dist, 'cycle': cycle, 'lr': lr,
             'dist': {'it_mg': info['it_mg'], 'rel_error': info['rel_error'],
                      'exit': info['exit_message'], 'wall_s': round(dt, 3),
                      'err_hist': [float(f"{v:.3e}") for v in info['error_at_cycle'] / info['ref_error']]},
