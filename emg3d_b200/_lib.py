@@ -53,6 +53,7 @@ _SIGNATURES = {
     'emg3d_b200_d2d': (c_int, [c_void_p, c_void_p, c_size_t]),
     'emg3d_b200_host_alloc': (c_int, [POINTER(c_void_p), c_size_t]),
     'emg3d_b200_host_free': (c_int, [c_void_p]),
+    'emg3d_b200_h2d_sparse': (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_int)]),
     'emg3d_b200_event_create': (c_int, [POINTER(c_void_p)]),
     'emg3d_b200_event_record': (c_int, [c_void_p]),
     'emg3d_b200_event_elapsed_ms': (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
@@ -196,6 +197,17 @@ class DeviceArray:
         if arr.size != self.size:
             raise ValueError(f"size mismatch: {arr.size} != {self.size}")
         check(init().emg3d_b200_h2d(self.ptr, _hptr(arr), self.nbytes))
+
+    def upload_sparse(self, arr):
+        """Upload of a mostly-zero array (source fields): see emg3d_b200_h2d_sparse.
+        Returns True if only the non-zeros crossed PCIe."""
+        arr = np.ascontiguousarray(arr.ravel('F') if arr.ndim > 1 else arr, dtype=self.dtype)
+        if arr.size != self.size:
+            raise ValueError(f"size mismatch: {arr.size} != {self.size}")
+        used = c_int(0)
+        check(init().emg3d_b200_h2d_sparse(self.ptr, _hptr(arr), self.size, self.dtype.itemsize,
+                                           byref(used)))
+        return bool(used.value)
 
     def upload_ptr(self, hptr, nbytes=None):
         check(init().emg3d_b200_h2d(self.ptr, hptr, self.nbytes if nbytes is None else nbytes))

@@ -1,8 +1,11 @@
 // C ABI of the emg3d_b200 library (see include/emg3d_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/emg3d_b200.h"
@@ -173,6 +176,159 @@ int emg3d_b200_d2d(void* dst, const void* src, size_t nbytes) {
     CK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, g_stream));
     return 0;
 }
+// ---- sparse upload ---------------------------------------------------------------
+// Source fields of dipoles and wires are constant (zero, or -0.0 after the scaling
+// by -s mu_0) except on a handful of edges (emg3d/fields.py:386-519), yet they
+// arrive as dense host arrays of n_edges values (0.8 GB at 256^3).  The host array
+// is compared against its background BIT PATTERN by a few threads at memory
+// bandwidth; if only a small fraction differs, the device array is filled with the
+// background and the (index, value) pairs are scattered into it, so that only
+// those cross PCIe.  The device array is bit-identical to a plain copy.
+extern "C++" {
+namespace {
+template <typename V>
+__global__ void scatter_kernel(V* __restrict__ dst, const long long* __restrict__ idx,
+                               const V* __restrict__ val, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = val[i];
+}
+template <typename V>
+__global__ void fill_kernel(V* __restrict__ dst, V v, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) dst[i] = v;
+}
+struct SparseStage {
+    void* host = nullptr;     // pinned: [idx (8 B) x cap | values (elsize) x cap]
+    void* dev = nullptr;
+    size_t cap = 0, elsize = 0;
+} g_stage;
+
+// indices of the elements (WPE 64-bit words each) that differ from bg; gives up
+// (returns false) as soon as more than cap were found
+template <int WPE>
+bool scan_sparse(const uint64_t* w, size_t n, const uint64_t* bg, size_t cap, int nt,
+                 std::vector<std::vector<long long>>& found) {
+    std::atomic<int> dense(0);
+    auto scan = [&](int t) {
+        const size_t e0 = n * t / nt, e1 = n * (t + 1) / nt;
+        std::vector<long long>& out = found[t];
+        const size_t B = 64 / WPE;                    // elements per 512-byte block
+        for (size_t e = e0; e < e1;) {
+            const size_t eb = e + B < e1 ? e + B : e1;
+            uint64_t any = 0;
+            for (size_t i = e; i < eb; ++i)
+                for (int k = 0; k < WPE; ++k) any |= w[i * WPE + k] ^ bg[k];
+            if (any) {
+                for (size_t i = e; i < eb; ++i) {
+                    uint64_t a = 0;
+                    for (int k = 0; k < WPE; ++k) a |= w[i * WPE + k] ^ bg[k];
+                    if (a) out.push_back((long long)i);
+                }
+                if (out.size() > cap) { dense.store(1); return; }
+            }
+            e = eb;
+            if ((e & 0xfffff) < B && dense.load(std::memory_order_relaxed)) return;
+        }
+    };
+    if (nt == 1) scan(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(scan, t);
+        for (auto& x : th) x.join();
+    }
+    size_t cnt = 0;
+    for (auto& v : found) cnt += v.size();
+    return !dense.load() && cnt <= cap;
+}
+}  // namespace
+}  // extern "C++"
+
+int emg3d_b200_h2d_sparse(void* dst, const void* src, size_t n, int elsize, int* used_sparse) {
+    NEED_INIT();
+    if (elsize != 8 && elsize != 16) return fail_msg("h2d_sparse: elsize must be 8 or 16");
+    if (used_sparse) *used_sparse = 0;
+    if (n == 0) return 0;
+    const size_t cap = (n / 64 + 1024) & ~(size_t)1;   // beyond ~1.5 % a plain copy is as good
+    const int wpe = elsize / 8;                        // 64-bit words per element
+    const uint64_t* w = (const uint64_t*)src;
+    // background = the most frequent pattern among five probes
+    uint64_t bg[2] = {0, 0};
+    {
+        const size_t cand[5] = {0, n / 4, n / 2, n - 1 - n / 4, n - 1};
+        int pick = 0, best = -1;
+        for (int i = 0; i < 5; ++i) {
+            int votes = 0;
+            for (int j = 0; j < 5; ++j)
+                votes += memcmp(w + cand[i] * wpe, w + cand[j] * wpe, elsize) == 0;
+            if (votes > best) { best = votes; pick = i; }
+        }
+        memcpy(bg, w + cand[pick] * wpe, elsize);
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw ? hw : 8);
+    if (nt > 32) nt = 32;
+    if (n < (size_t)1 << 20) nt = 1;
+    std::vector<std::vector<long long>> found(nt);
+    const bool sparse = wpe == 2 ? scan_sparse<2>(w, n, bg, cap, nt, found)
+                                 : scan_sparse<1>(w, n, bg, cap, nt, found);
+    size_t cnt = 0;
+    for (auto& v : found) cnt += v.size();
+    if (getenv("EMG3D_B200_DEBUG"))
+        fprintf(stderr, "h2d_sparse: n=%zu elsize=%d threads=%d differing=%zu cap=%zu sparse=%d\n", n,
+                elsize, nt, cnt, cap, (int)sparse);
+    if (!sparse) return emg3d_b200_h2d(dst, src, n * (size_t)elsize);
+    emg3d_b200_sync();                                // staging buffer free again
+    if (g_stage.cap < cap || g_stage.elsize != (size_t)elsize) {
+        if (g_stage.host) cudaFreeHost(g_stage.host);
+        if (g_stage.dev) cudaFree(g_stage.dev);
+        g_stage.host = g_stage.dev = nullptr;
+        g_stage.cap = 0;
+        CK(cudaMallocHost(&g_stage.host, cap * (8 + (size_t)elsize)));
+        CK(cudaMalloc(&g_stage.dev, cap * (8 + (size_t)elsize)));
+        g_stage.cap = cap;
+        g_stage.elsize = elsize;
+    }
+    long long* hidx = (long long*)g_stage.host;
+    char* hval = (char*)g_stage.host + 8 * g_stage.cap;
+    size_t k = 0;
+    for (auto& v : found)
+        for (long long i : v) {
+            hidx[k] = i;
+            memcpy(hval + k * elsize, (const char*)src + (size_t)i * elsize, elsize);
+            ++k;
+        }
+    const int bs = 256;
+    ++emg::g_launch_count;
+    if (elsize == 16) {
+        double2 v;
+        memcpy(&v, bg, 16);
+        fill_kernel<double2><<<148 * 8, bs, 0, g_stream>>>((double2*)dst, v, (long long)n);
+    } else {
+        double v;
+        memcpy(&v, bg, 8);
+        fill_kernel<double><<<148 * 8, bs, 0, g_stream>>>((double*)dst, v, (long long)n);
+    }
+    CK_LAUNCH("fill");
+    if (cnt) {
+        CK(cudaMemcpyAsync(g_stage.dev, hidx, 8 * cnt, cudaMemcpyHostToDevice, g_stream));
+        char* dval = (char*)g_stage.dev + 8 * g_stage.cap;
+        CK(cudaMemcpyAsync(dval, hval, cnt * (size_t)elsize, cudaMemcpyHostToDevice, g_stream));
+        const unsigned gs = (unsigned)((cnt + bs - 1) / bs);
+        ++emg::g_launch_count;
+        if (elsize == 16)
+            scatter_kernel<double2><<<gs, bs, 0, g_stream>>>((double2*)dst, (const long long*)g_stage.dev,
+                                                             (const double2*)dval, (long long)cnt);
+        else
+            scatter_kernel<double><<<gs, bs, 0, g_stream>>>((double*)dst, (const long long*)g_stage.dev,
+                                                            (const double*)dval, (long long)cnt);
+        CK_LAUNCH("scatter");
+    }
+    CK(cudaStreamSynchronize(g_stream));              // the staging buffer is reused
+    if (used_sparse) *used_sparse = 1;
+    return 0;
+}
+
 int emg3d_b200_host_alloc(void** hptr, size_t nbytes) {
     CK(cudaMallocHost(hptr, nbytes ? nbytes : 16));
     return 0;

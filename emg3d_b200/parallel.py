@@ -280,8 +280,8 @@ class DistributedMultigrid:
         The GLOBAL source field.
     comm : NcclComm
     n_dist : int, optional
-        Number of distributed levels; default: as many as keep at least 4 owned
-        planes per rank on the coarsest distributed level.
+        Number of distributed levels; default: the levels with more than about a
+        million cells (the coarser ones are replicated on every GPU).
     """
 
     def __init__(self, model, sfield, comm, n_dist=None, order=None):
@@ -292,9 +292,13 @@ class DistributedMultigrid:
         self.gshape = tuple(model.grid.shape_cells)
         nx, ny, nz = self.gshape
         if n_dist is None:
+            # distribute the levels that are worth it (more than ~1 M cells: below that
+            # a level is launch-latency bound and replicating it is cheaper than
+            # exchanging its halos), as long as every rank keeps two owned planes
             n_dist = 1
             while (nz % (1 << (n_dist + 1)) == 0 and (nz >> (n_dist + 1)) // self.nranks >= 2
-                   and min(nx, ny) >> (n_dist + 1) >= 2):
+                   and min(nx, ny) >> (n_dist + 1) >= 2
+                   and (nx * ny * nz) >> (3 * n_dist) > 1_000_000):
                 n_dist += 1
         self.n_dist = n_dist
         self.part = part = SlabPartition(nz, self.nranks, n_dist)

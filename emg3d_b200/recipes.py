@@ -54,13 +54,18 @@ def model_marine(h, origin, rho_air=1e8):
     """Air / sea / VTI sediment with a thin resistor (configs 3, 4)."""
     cx, cy, cz = _centers(h, origin)
     shape = (cx.size, cy.size, cz.size)
-    X = cx[:, None, None] * np.ones(shape)
-    Y = cy[None, :, None] * np.ones(shape)
-    Z = cz[None, None, :] * np.ones(shape)
-    rh = np.where(Z > 0, rho_air, np.where(Z > -1000, 0.3, 1.0))
-    rv = np.where(Z > 0, rho_air, np.where(Z > -1000, 0.3, 2.0))
-    tgt = (abs(X) < 2500) & (abs(Y) < 2500) & (Z < -1900) & (Z > -2000)
-    rh[tgt] = rv[tgt] = 100.
+    rh1 = np.where(cz > 0, rho_air, np.where(cz > -1000, 0.3, 1.0))
+    rv1 = np.where(cz > 0, rho_air, np.where(cz > -1000, 0.3, 2.0))
+    rh = np.empty(shape, order='F')
+    rv = np.empty(shape, order='F')
+    rh[:] = rh1[None, None, :]
+    rv[:] = rv1[None, None, :]
+    ix = np.flatnonzero(abs(cx) < 2500)
+    iy = np.flatnonzero(abs(cy) < 2500)
+    iz = np.flatnonzero((cz < -1900) & (cz > -2000))
+    if ix.size and iy.size and iz.size:
+        rh[np.ix_(ix, iy, iz)] = 100.
+        rv[np.ix_(ix, iy, iz)] = 100.
     return {'property_x': rh, 'property_z': rv}
 
 
@@ -110,3 +115,23 @@ def config(name, n=None):
                     source=(0., 0., -950., 0., 0.), frequency=1.0,
                     solver=dict(cycle='W', sslsolver=False))
     raise ValueError(f"unknown configuration {name!r}")
+
+
+def bench_grid(n_gpus, n=256):
+    """Weak-scaling workload of bench.py: the marine model on n^3 cells per GPU.
+
+    1 GPU: n^3 (BASELINE.json configs[2]); the cell count doubles with the GPU
+    count along x, then y, then z: 2: 2n x n x n, 4: 2n x 2n x n (configs[3] shape),
+    8: (2n)^3 (configs[4] shape).  Decomposed into z-slabs.
+    """
+    shape = [n, n, n]
+    k, a = n_gpus, 0
+    while k > 1:
+        shape[a % 3] *= 2
+        k //= 2
+        a += 1
+    alpha = [{512: 1.02, 256: 1.03, 128: 1.04, 64: 1.06, 32: 1.10}.get(m, 1.02 if m > 512 else 1.10)
+             for m in shape]
+    h, origin = grid_arrays(*shape, *alpha)
+    return dict(h=h, origin=origin, model=model_marine(h, origin),
+                source=(0., 0., -950., 0., 0.), frequency=1.0)

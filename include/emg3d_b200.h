@@ -48,6 +48,13 @@ int emg3d_b200_memset(void* dptr, int byte, size_t nbytes);
 int emg3d_b200_h2d(void* dst_dev, const void* src_host, size_t nbytes);
 int emg3d_b200_d2h(void* dst_host, const void* src_dev, size_t nbytes);
 int emg3d_b200_d2d(void* dst_dev, const void* src_dev, size_t nbytes);
+/* Upload of a mostly-zero host array of n elements of elsize 8 or 16 bytes (source
+ * fields, emg3d/fields.py:386-519): the host array is scanned and, if fewer than
+ * ~1.5 % of the elements have a non-zero bit pattern, only (index, value) pairs
+ * cross PCIe and are scattered into the cleared device array; otherwise a plain
+ * copy.  The device array is bit-identical to emg3d_b200_h2d either way.       */
+int emg3d_b200_h2d_sparse(void* dst_dev, const void* src_host, size_t n_elems, int elsize,
+                          int* used_sparse);
 int emg3d_b200_host_alloc(void** hptr, size_t nbytes);   /* pinned host memory */
 int emg3d_b200_host_free(void* hptr);
 

@@ -402,3 +402,32 @@ def test_z_window_equals_subgrid(core, cplx):
     want = scatter(np.zeros(n, dtype=dt), rs)
     assert rel_err(got, want) < 1e-13
     win.free()
+
+
+def test_sparse_upload_is_bit_identical():
+    """emg3d_b200_h2d_sparse: same device bytes as a plain copy, for sparse sources
+    (incl. -0.0 and NaN payloads, real and complex) and for dense arrays (fallback)."""
+    from emg3d_b200 import _lib
+    _lib.init()
+    rng = np.random.default_rng(3)
+    for dtype, n, bgv in ((np.complex128, 3_000_001, 0), (np.float64, 2_500_003, 0),
+                          (np.complex128, 100_000, complex(0.0, -0.0)), (np.float64, 70_001, 3.25)):
+        a = np.full(n, bgv, dtype=dtype)
+        idx = rng.choice(n, size=min(37, n // 8), replace=False)
+        a[idx] = rng.standard_normal(idx.size) + (1j * rng.standard_normal(idx.size)
+                                                  if dtype is np.complex128 else 0)
+        a[idx[0]] = -0.0
+        a[idx[1]] = np.nan
+        a[-1] = -2.5
+        if n % 2:
+            a[0] = 1.5
+        d = _lib.DeviceArray(n, dtype)
+        assert d.upload_sparse(a)
+        assert d.download().tobytes() == a.tobytes()
+        dense = rng.standard_normal(n).astype(dtype)
+        assert not d.upload_sparse(dense)
+        assert d.download().tobytes() == dense.tobytes()
+    z = np.zeros(5000)
+    d = _lib.DeviceArray(z.size, z.dtype)
+    d.upload(np.ones(5000))
+    assert d.upload_sparse(z) and not d.download().any()
