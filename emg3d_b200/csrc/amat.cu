@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __rest
     }
 }
 
-constexpr int64_t ZMARCH_MIN_CELLS = 64 * 64 * 64;
+constexpr int64_t ZMARCH_MIN_CELLS = 100 * 100 * 100;   // below: too few blocks to march
 constexpr int ZMARCH_KZ = EMG_RZ_KZ;
 
 template <typename T>

@@ -360,8 +360,17 @@ int emg3d_b200_event_destroy(void* ev) {
     CK(cudaEventDestroy((cudaEvent_t)ev));
     return 0;
 }
+// A captured graph remembers how many kernel launches it holds, so that the
+// launch counter keeps counting kernels when a graph is replayed.
+struct GraphHandle {
+    cudaGraphExec_t exec;
+    long long launches;
+};
+static long long g_capture_start = 0;
+
 int emg3d_b200_graph_begin(void) {
     NEED_INIT();
+    g_capture_start = emg::g_launch_count;
     CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
     return 0;
 }
@@ -373,16 +382,23 @@ int emg3d_b200_graph_end(void** graph_exec) {
     cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail("cudaGraphInstantiate", e);
-    *graph_exec = (void*)ge;
+    GraphHandle* h = new GraphHandle{ge, emg::g_launch_count - g_capture_start};
+    emg::g_launch_count = g_capture_start;            // nothing ran during the capture
+    *graph_exec = (void*)h;
     return 0;
 }
 int emg3d_b200_graph_launch(void* graph_exec) {
     NEED_INIT();
-    CK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, g_stream));
+    GraphHandle* h = (GraphHandle*)graph_exec;
+    CK(cudaGraphLaunch(h->exec, g_stream));
+    emg::g_launch_count += h->launches;
     return 0;
 }
 int emg3d_b200_graph_destroy(void* graph_exec) {
-    CK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    GraphHandle* h = (GraphHandle*)graph_exec;
+    if (!h) return 0;
+    cudaGraphExecDestroy(h->exec);
+    delete h;
     return 0;
 }
 

@@ -8,9 +8,10 @@ enum { ORDER_LEX = 0, ORDER_COLOR = 1 };
 
 extern long long g_launch_count;   // kernel launches issued (host-side counter)
 
-// grids with at most this many interior nodes (or lines) are smoothed by one
-// thread block in a single launch
-constexpr int64_t SMALL_GRID_NODES = 4096;
+// grids with at most this many interior nodes are smoothed by one thread block in
+// a single launch (8^3 and below; a colour phase of one block costs ~4 us, and
+// beyond ~500 nodes one launch per colour with more blocks is faster)
+constexpr int64_t SMALL_GRID_NODES = 512;
 // point smoother, multicolour order: grids with more interior nodes than this
 // (working set beyond the 126 MB L2) use the tile-fused schedule
 constexpr int64_t TILE_MIN_NODES = 300000;

@@ -20,6 +20,7 @@ the attributes of ``emg3d.Field`` / ``emg3d.models.VolumeModel``): data are then
 uploaded, processed and written back in place.
 """
 import itertools
+import os
 from dataclasses import dataclass
 from datetime import datetime, timedelta
 from time import perf_counter
@@ -710,8 +711,7 @@ def _multigrid(lv, s, e, var, level=0, new_cycmax=0):
             sc_dir = _current_sc_dir(var.sc_dir, lv.grid)
             res = _dev_residual(lv, s, e)
             child = _dev_restriction(lv, res, sc_dir)
-            _multigrid(child, child.s, child.e, var, level=level + 1,
-                       new_cycmax=cycmax - cyc)
+            _subcycle(child, var, level + 1, cycmax - cyc)
             _dev_prolongation(child, e)
 
             if var.first_cycle and var.verb > 3:
@@ -740,6 +740,40 @@ def _multigrid(lv, s, e, var, level=0, new_cycmax=0):
                 break
 
     var.l2 = l2_last
+
+
+# Coarse sub-cycles as CUDA graphs.  Below the finest level a visit is a fixed
+# sequence of launches on level-owned buffers (no norms, no host decisions), and
+# the coarse levels are launch-latency bound: W-cycles visit level l 2^l times.
+# The first visit of a (level, settings) combination runs eagerly (it creates the
+# child levels, cached diagonals and factorisations), the second is captured, and
+# from then on the graph is replayed.  EMG3D_B200_GRAPHS=0 disables this.
+GRAPHS = os.environ.get('EMG3D_B200_GRAPHS', '1') != '0'
+# only levels at or below this many cells are worth a graph of their own
+_GRAPH_MAX_CELLS = 160 ** 3
+
+
+def _subcycle(child, var, level, new_cycmax):
+    use = (GRAPHS and var.verb <= 3 and not getattr(var, '_capturing', False)
+           and child.grid.n_cells <= _GRAPH_MAX_CELLS)
+    if not use:
+        return _multigrid(child, child.s, child.e, var, level=level, new_cycmax=new_cycmax)
+    key = (level, int(new_cycmax), var.cycle, int(var.sc_dir), int(var.lr_dir), _order(var),
+           int(var.nu_pre), int(var.nu_post), int(var.nu_coarse), tuple(var.clevel))
+    graphs = child.__dict__.setdefault('_graphs', {})
+    g = graphs.get(key)
+    if g is None:                                   # first visit: eager, builds the caches
+        graphs[key] = False
+        return _multigrid(child, child.s, child.e, var, level=level, new_cycmax=new_cycmax)
+    if g is False:                                  # second visit: capture
+        var._capturing = True
+        try:
+            with _lib.Graph() as g:
+                _multigrid(child, child.s, child.e, var, level=level, new_cycmax=new_cycmax)
+        finally:
+            var._capturing = False
+        graphs[key] = g
+    g.launch()
 
 
 class _Vec:

@@ -223,3 +223,28 @@ def test_full_size_properties(eb):
                            order=order)
         err = info['error_at_cycle']
         assert err[2] < 0.2 * err[1] < 0.2 * err[0]
+
+
+@pytest.mark.parametrize('cycle,kw', [('W', dict(plain=True)), ('F', dict(sslsolver=False)),
+                                      ('V', dict())])
+def test_cuda_graph_replay_equals_eager(cycle, kw):
+    """Coarse sub-cycles replayed as CUDA graphs give bit-identical results."""
+    import emg3d_b200 as eb
+    from emg3d_b200 import recipes, solver
+    cfg = recipes.config('config2', 32)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    sfield = eb.get_source_field(grid, cfg['source'], cfg['frequency'])
+    out = {}
+    for graphs in (False, True):
+        solver.GRAPHS = graphs
+        try:
+            ws = eb.Workspace()
+            e, info = eb.solve(model, sfield, cycle=cycle, maxit=4, tol=1e-12, return_info=True,
+                               workspace=ws, **kw)
+            out[graphs] = (e.field.copy(), info)
+        finally:
+            solver.GRAPHS = True
+    assert np.array_equal(out[False][0], out[True][0])
+    assert out[False][1]['it_mg'] == out[True][1]['it_mg']
+    assert out[False][1]['abs_error'] == out[True][1]['abs_error']

@@ -36,14 +36,21 @@ def main():
         _lib.sync()
         free0, total = _lib.mem_info()
         t0 = time.perf_counter()
-        efield, info = eb.solve(model, sfield, return_info=True, order=order, **kw)
+        ws = eb.Workspace()
+        efield, info = eb.solve(model, sfield, return_info=True, order=order, workspace=ws, **kw)
         _lib.sync()
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        efield, info2 = eb.solve(model, sfield, return_info=True, order=order, workspace=ws, **kw)
+        _lib.sync()
+        dt2 = time.perf_counter() - t0
         free1, _ = _lib.mem_info()
         print(json.dumps({
             'config': name, 'shape': grid.shape_cells, 'order': order, 'solver': kw,
             'exit_message': info['exit_message'], 'it_mg': info['it_mg'], 'it_ssl': info['it_ssl'],
-            'rel_error': info['rel_error'], 'wall_s': round(dt, 3),
+            'rel_error': info['rel_error'], 'wall_s': round(dt, 3), 'wall_s_warm': round(dt2, 3),
+            'cycle_s': [round(float(b - a), 4) for a, b in zip([0] + list(info['runtime_at_cycle'][:-1]), info['runtime_at_cycle'])],
+            'cycle_s_warm': [round(float(b - a), 4) for a, b in zip([0] + list(info2['runtime_at_cycle'][:-1]), info2['runtime_at_cycle'])],
             'error_at_cycle_rel': [float(f"{v:.3e}") for v in info['error_at_cycle'] / info['ref_error']],
             'efield_norm': float(np.linalg.norm(efield.field)),
             'device_free_GB_before': round(free0 / 1e9, 1)}), flush=True)
