@@ -438,11 +438,15 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
     kw = dict(verb=0, sslsolver=False, semicoarsening=False, linerelaxation=False,
               shape_cells=shape, cycle='V', maxit=1)
 
+    l2_refe = float(np.sqrt(dmg.sum_owned(dmg.levels[0], dmg.s).real))
+
     def step():
+        # same region as the single-GPU step: zero start field, ||r|| = ||b|| known
         var = solver.MGParameters(**kw)
         var.order = args.order
-        var.l2_refe = 1.0
+        var.l2_refe = l2_refe
         dmg.e.zero()
+        var.e_is_zero, var.s_norm = True, l2_refe
         dmg.multigrid(var)
         return var
 

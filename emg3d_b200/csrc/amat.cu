@@ -63,6 +63,7 @@ residual_kernel(Model<T> m, const T* s, const T* __restrict__ e,
         FieldView<const T> S(s, m.d);
         FieldView<T> R(r, m.d);
         const bool inner = ix < nx && iy < ny && iz < nz;   // edges the reference touches
+        const bool own_xy = owns_plane(m.d, iz), own_z = owns_layer(m.d, iz);
         const int64_t cs1 = nx, cs2 = (int64_t)nx * ny;
         const int ixm = max(ix - 1, 0), iym = max(iy - 1, 0), izm = max(iz - 1, 0);
         T fzpp = zero_<T>(), fypp = zero_<T>(), fxpp = zero_<T>();
@@ -88,7 +89,7 @@ residual_kernel(Model<T> m, const T* s, const T* __restrict__ e,
             }
             if (apply_only) val = -val;
             if (r) R.p[0][id] = val;
-            acc += abs2(val);
+            if (own_xy) acc += abs2(val);
         }
         // y-edge
         if (iy < ny) {
@@ -107,7 +108,7 @@ residual_kernel(Model<T> m, const T* s, const T* __restrict__ e,
             }
             if (apply_only) val = -val;
             if (r) R.p[1][id] = val;
-            acc += abs2(val);
+            if (own_xy) acc += abs2(val);
         }
         // z-edge
         if (iz < nz) {
@@ -126,7 +127,7 @@ residual_kernel(Model<T> m, const T* s, const T* __restrict__ e,
             }
             if (apply_only) val = -val;
             if (r) R.p[2][id] = val;
-            acc += abs2(val);
+            if (own_z) acc += abs2(val);
         }
     }
     if (partial) {
@@ -239,6 +240,7 @@ residual_zmarch_kernel(Model<T> m, const T* s, const T* __restrict__ e, T* r,
 
         if (node) {
             const double rhz = k < nz ? ldg(m.rh[2] + k) : 0.0, rhzm = ldg(m.rh[2] + km);
+            const bool own_xy = owns_plane(m.d, k), own_z = owns_layer(m.d, k);
             // x-edge (ix, iy, k)
             if (ix < nx) {
                 const int64_t id = S.idx(0, ix, iy, k);
@@ -253,7 +255,7 @@ residual_zmarch_kernel(Model<T> m, const T* s, const T* __restrict__ e, T* r,
                 }
                 if (apply_only) val = -val;
                 if (r) R.p[0][id] = val;
-                acc += abs2(val);
+                if (own_xy) acc += abs2(val);
             }
             // y-edge
             if (iy < ny) {
@@ -269,7 +271,7 @@ residual_zmarch_kernel(Model<T> m, const T* s, const T* __restrict__ e, T* r,
                 }
                 if (apply_only) val = -val;
                 if (r) R.p[1][id] = val;
-                acc += abs2(val);
+                if (own_xy) acc += abs2(val);
             }
             // z-edge
             if (k < nz) {
@@ -285,7 +287,7 @@ residual_zmarch_kernel(Model<T> m, const T* s, const T* __restrict__ e, T* r,
                 }
                 if (apply_only) val = -val;
                 if (r) R.p[2][id] = val;
-                acc += abs2(val);
+                if (own_z) acc += abs2(val);
             }
         }
         fx_dn = fx;

@@ -493,6 +493,14 @@ int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* pare
     return 0;
 }
 
+int emg3d_b200_level_set_owned(emg3d_b200_level* lv, int plane0, int plane1) {
+    if (plane0 < 0 || plane1 < plane0 || plane1 > lv->d.n[2] + 1)
+        return fail_msg("level_set_owned: plane range outside the level");
+    lv->d.own0 = plane0;
+    lv->d.own1 = plane1;
+    return 0;
+}
+
 int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes) {
     if (ldir < 1 || ldir > 3) return fail_msg("level_factor_bytes: ldir must be 1, 2 or 3");
     const size_t el = lv->cplx == 0 ? sizeof(double) : sizeof(cplx);

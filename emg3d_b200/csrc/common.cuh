@@ -31,10 +31,27 @@ __host__ __device__ __forceinline__ cplx& operator-=(cplx& a, cplx b) { a.re -= 
 __host__ __device__ __forceinline__ cplx& operator*=(cplx& a, cplx b) { a = a * b; return a; }
 __host__ __device__ __forceinline__ cplx& operator*=(cplx& a, double b) { a.re *= b; a.im *= b; return a; }
 
-// reciprocal of a pivot
-__host__ __device__ __forceinline__ double rcp(double a) { return 1.0 / a; }
+// reciprocal of a pivot.  On the device: hardware seed (MUFU.RCP64H, ~20 bits) and
+// two Newton steps -- full double precision to within an ulp, a third of the
+// instructions of the IEEE division sequence and no slow-path branch (pivots are
+// finite, normal numbers).  Off by default (measured r1: no gain, the smoothers are bound by the memory system); -DEMG_FAST_RCP=1 enables it.
+#ifndef EMG_FAST_RCP
+#define EMG_FAST_RCP 0
+#endif
+__host__ __device__ __forceinline__ double rcp(double a) {
+#if defined(__CUDA_ARCH__) && EMG_FAST_RCP
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / a;
+#endif
+}
 __host__ __device__ __forceinline__ cplx rcp(cplx a) {
-    double d = 1.0 / (a.re * a.re + a.im * a.im);
+    double d = rcp(a.re * a.re + a.im * a.im);
     return make_c(a.re * d, -a.im * d);
 }
 __host__ __device__ __forceinline__ double abs2(double a) { return a * a; }
@@ -57,6 +74,23 @@ __device__ __forceinline__ cplx ldg(const cplx* p) {
     return make_c(v.x, v.y);
 }
 
+// ---- cp.async (LDGSTS): global -> shared without a register round trip --------
+__device__ __forceinline__ void cp_async(cplx* dst, const cplx* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 // ---- grid / model description passed by value to kernels -------------------
 struct Dims {
     int n[3];          // cells per axis
@@ -65,7 +99,18 @@ struct Dims {
     // spans n[2] cells.  z is the slowest axis, so a window of a component or of a
     // cell array is a contiguous range: only base pointers move.
     int zoff, nzf;
+    // planes of this view whose edges count in norms (multi-GPU: the planes a rank
+    // owns; own1 == 0: all).  x/y-edges on node plane k count iff own0 <= k < own1,
+    // z-edges of cell layer k iff own0 <= k + 1 < own1 (a layer belongs to the
+    // owner of its upper plane).
+    int own0, own1;
 };
+__host__ __device__ __forceinline__ bool owns_plane(const Dims& d, int k) {
+    return d.own1 == 0 || (k >= d.own0 && k < d.own1);
+}
+__host__ __device__ __forceinline__ bool owns_layer(const Dims& d, int k) {
+    return d.own1 == 0 || (k + 1 >= d.own0 && k + 1 < d.own1);
+}
 __host__ __device__ __forceinline__ int full_nz(const Dims& d) { return d.nzf > 0 ? d.nzf : d.n[2]; }
 
 template <typename T>

@@ -307,19 +307,6 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
 // cp.async (LDGSTS) into a shared-memory ring [stage][word][thread], STAGES
 // blocks ahead, without touching the register file; `Direct` loads on demand
 // (used by the small-grid and hyperplane kernels).
-__device__ __forceinline__ void cp_async(cplx* dst, const cplx* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async(double* dst, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
 constexpr int FWD_WORDS = 32;   // T-words per forward stage: 15 + 5 + 4 + 8
 constexpr int BWD_WORDS = 20;   // 15 + 5
 

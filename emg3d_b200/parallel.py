@@ -35,7 +35,7 @@ the transport is pluggable (:class:`NcclComm` on device pointers,
 """
 import numpy as np
 
-__all__ = ['SlabPartition', 'exchange_plan', 'gather_plan', 'owned_ranges', 'NcclComm',
+__all__ = ['SlabPartition', 'exchange_plan', 'pull_plan', 'gather_plan', 'owned_ranges', 'NcclComm',
            'DistributedMultigrid']
 
 
@@ -156,6 +156,28 @@ def exchange_plan(part, level, rank, nx, ny):
     return plan
 
 
+def pull_plan(part, level, rank, nx, ny):
+    """The halo exchange of :func:`exchange_plan` seen from the receiving side.
+
+    Returns ``[(from_upper, my_offset, peer_offset, count)]``: the ``count`` elements
+    at ``peer_offset`` of the neighbour's local field (``rank + 1`` if ``from_upper``
+    else ``rank - 1``) belong at ``my_offset`` of this rank's.  A rank's receives
+    from a neighbour are matched, in order, with that neighbour's sends to it.
+    """
+    mine = exchange_plan(part, level, rank, nx, ny)
+    out = []
+    for q in (rank - 1, rank + 1):
+        if q < 0 or q >= part.nranks:
+            continue
+        recvs = [(off, cnt) for s, p, off, cnt in mine if not s and p == q]
+        sends = [(off, cnt) for s, p, off, cnt in exchange_plan(part, level, q, nx, ny)
+                 if s and p == rank]
+        if [c for _, c in recvs] != [c for _, c in sends]:
+            raise AssertionError("halo plans of neighbouring ranks do not match")
+        out += [(int(q > rank), ro, so, cnt) for (ro, cnt), (so, _) in zip(recvs, sends)]
+    return out
+
+
 def gather_plan(part, level, rank, nx, ny):
     """All-gather of the owned parts of a local field into the global layout.
 
@@ -242,8 +264,50 @@ class NcclComm:
         snd = (ctypes.c_int * n)(*[x[0] for x in plan_ptrs])
         self._lib.check(self._lib.load().emg3d_b200_comm_sendrecv(n, ptrs, nbytes, peers, snd))
 
-    def allreduce_sum(self, dev_array):
-        self._lib.check(self._lib.load().emg3d_b200_comm_allreduce_sum(dev_array.ptr, dev_array.size))
+    # ---- halo exchange over peer memory (one kernel per exchange, csrc/comm.cu) ----
+    def p2p_enable(self):
+        """Collective.  True if every rank can map its neighbours' memory (CUDA IPC)."""
+        import ctypes
+        import os
+        if os.environ.get('EMG3D_B200_P2P', '1') == '0' or self.nranks < 2:
+            self.p2p = False
+            return False
+        on = ctypes.c_int(0)
+        self._lib.check(self._lib.load().emg3d_b200_p2p_init(ctypes.byref(on)))
+        self.p2p = bool(on.value)
+        return self.p2p
+
+    def p2p_register(self, ptr):
+        """Collective, same order on all ranks.  Slot id, or -1 (use sendrecv)."""
+        import ctypes
+        slot = ctypes.c_int(-1)
+        self._lib.check(self._lib.load().emg3d_b200_p2p_register(ptr, ctypes.byref(slot)))
+        return slot.value
+
+    @staticmethod
+    def p2p_args(pulls, itemsize):
+        """ctypes argument arrays of p2p_exchange for a :func:`pull_plan`."""
+        import ctypes
+        n = len(pulls)
+        A = ctypes.c_size_t * n
+        return (n, A(*[mo * itemsize for _, mo, _, _ in pulls]),
+                A(*[po * itemsize for _, _, po, _ in pulls]),
+                A(*[c * itemsize for _, _, _, c in pulls]),
+                (ctypes.c_int * n)(*[u for u, _, _, _ in pulls]))
+
+    def p2p_exchange(self, slot, args):
+        if args[0]:
+            self._lib.check(self._lib.load().emg3d_b200_p2p_exchange(slot, *args))
+
+    def p2p_status(self):
+        import ctypes
+        st = ctypes.c_int(0)
+        self._lib.check(self._lib.load().emg3d_b200_p2p_status(ctypes.byref(st)))
+        return st.value
+
+    def allreduce_sum(self, dev_array, n=None):
+        self._lib.check(self._lib.load().emg3d_b200_comm_allreduce_sum(
+            dev_array.ptr, dev_array.size if n is None else int(n)))
 
     def destroy(self):
         self._lib.load().emg3d_b200_comm_destroy()
@@ -256,6 +320,8 @@ class _DLevel:
         nx, ny = lv.shape[0], lv.shape[1]
         self.index, self.lv = level, lv
         self.plan = exchange_plan(part, level, rank, nx, ny)
+        self.pulls = pull_plan(part, level, rank, nx, ny)
+        self.pull_args = None                        # ctypes arrays, built on first use
         self.owned = owned_ranges(part, level, rank, nx, ny)
         # Smoother and residual run on the z-window [p0 - 1, hi] of the local grid:
         # one halo plane on either side, refreshed by the exchange and fixed during a
@@ -263,8 +329,12 @@ class _DLevel:
         # nested under coarsening; no kernel result ever depends on them.
         lo, hi = part.local(level, rank)
         p0, _ = part.owned(level, rank)
+        p0, p1 = part.owned(level, rank)
         z0 = 0 if rank == 0 else p0 - 1 - lo
         self.win = lv.handle if z0 == 0 else lv.handle.window(z0, hi - lo - z0)
+        # norms evaluated by the residual kernel on the window count owned edges only
+        from emg3d_b200 import _lib
+        _lib.check(_lib.load().emg3d_b200_level_set_owned(self.win.ptr, p0 - lo - z0, p1 - lo - z0))
         lv.res_buffer().zero()
 
 
@@ -288,6 +358,9 @@ class DistributedMultigrid:
         from emg3d_b200 import _lib, core, fields, meshes, models, solver
         self._lib, self._solver = _lib, solver
         self.comm, self.rank, self.nranks = comm, comm.rank, comm.nranks
+        self._slots = {}                             # device pointer -> peer-memory slot
+        if not getattr(comm, 'p2p', False) and hasattr(comm, 'p2p_enable'):
+            comm.p2p_enable()
         self.order = core.order_id(order)
         self.gshape = tuple(model.grid.shape_cells)
         nx, ny, nz = self.gshape
@@ -409,6 +482,16 @@ class DistributedMultigrid:
 
     # ---- distributed building blocks -------------------------------------------------
     def exchange(self, dl, field):
+        """Refresh the halo planes of `field` (a local field of level `dl`)."""
+        if self.comm.p2p:
+            slot = self._slots.get(field.ptr)
+            if slot is None:                         # first exchange of this array: collective
+                slot = self._slots[field.ptr] = self.comm.p2p_register(field.ptr)
+            if slot >= 0:
+                if dl.pull_args is None:
+                    dl.pull_args = self.comm.p2p_args(dl.pulls, self.dtype.itemsize)
+                self.comm.p2p_exchange(slot, dl.pull_args)
+                return
         self.comm.sendrecv(field.ptr, self.dtype.itemsize, dl.plan)
 
     def sum_owned(self, dl, x, y=None):
@@ -425,10 +508,14 @@ class DistributedMultigrid:
 
     def residual(self, dl, s, e, norm=False):
         lib = self._lib.load()
+        if norm:
+            # norm only: no residual is written; the kernel sums |r|^2 over the owned
+            # edges of the window (level_set_owned) into a device scalar, all-reduced
+            self._lib.check(lib.emg3d_b200_residual(dl.win.ptr, s.ptr, e.ptr, None, self._sums.ptr))
+            self.comm.allreduce_sum(self._sums, 1)
+            return float(np.sqrt(self._sums.download()[0]))
         r = dl.lv.res_buffer()
         self._lib.check(lib.emg3d_b200_residual(dl.win.ptr, s.ptr, e.ptr, r.ptr, None))
-        if norm:
-            return float(np.sqrt(self.sum_owned(dl, r).real))
         self.exchange(dl, r)
         return r
 
@@ -455,7 +542,11 @@ class DistributedMultigrid:
         else:
             cycmax = new_cycmax
         cyc = 0
-        l2_last = self.residual(dl, s, e, norm=True) if level == 0 else 0.0
+        if level == 0 and getattr(var, 'e_is_zero', False):
+            l2_last = float(var.s_norm)              # zero start field: ||r|| = ||s||
+            var.e_is_zero = False
+        else:
+            l2_last = self.residual(dl, s, e, norm=True) if level == 0 else 0.0
         l2_stag = np.ones(var.maxcycle) * l2_last
         if level == 0 and var.nu_init > 0:
             self.smoothing(dl, s, e, var.nu_init, var.lr_dir)
@@ -513,10 +604,11 @@ class DistributedMultigrid:
         var.order = {0: 'lex', 1: 'color'}[self.order]
         if var.clevel[0] <= self.n_dist:
             raise ValueError("grid too small for the requested number of distributed levels")
-        if zero_start:
-            self.e.zero()
         var.l2_refe = float(np.sqrt(self.sum_owned(self.levels[0], self.s).real))
         var.error_at_cycle[0] = var.l2_refe
+        if zero_start:
+            self.e.zero()
+            var.e_is_zero, var.s_norm = True, var.l2_refe
         self.multigrid(var)
         return {'exit': int(var.exit_message != 'CONVERGED'), 'exit_message': var.exit_message,
                 'abs_error': var.l2, 'rel_error': var.l2 / var.l2_refe, 'ref_error': var.l2_refe,

@@ -86,6 +86,12 @@ int emg3d_b200_level_set_model(emg3d_b200_level* lv, int cplx, const void* eta_x
  * data (halo planes).  Owns its cached factorisations; destroy before the parent. */
 int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* parent, int z0,
                             int nz);
+/* Norms on this level (emg3d_b200_residual with norm2_dev) count only the edges a
+ * multi-GPU rank owns: x/y-edges on node planes [plane0, plane1) of the level (or
+ * window) and z-edges of the cell layers whose upper plane is in that range.
+ * plane1 == 0 (default): all edges, i.e. the reference's np.linalg.norm
+ * (emg3d/solver.py:1066). */
+int emg3d_b200_level_set_owned(emg3d_b200_level* lv, int plane0, int plane1);
 /* bytes of the cached factorisation of line direction ldir (1, 2, 3) */
 int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes);
 int emg3d_b200_level_drop_factors(emg3d_b200_level* lv);
@@ -170,6 +176,22 @@ int emg3d_b200_comm_destroy(void);
 int emg3d_b200_comm_sendrecv(int n, void* const* ptrs, const size_t* nbytes, const int* peers,
                              const int* is_send);
 int emg3d_b200_comm_allreduce_sum(double* dev, int n);
+
+/* ---- halo exchange over peer memory (NVLink, CUDA IPC) ------------------------
+ * Replaces the NCCL send/recv group of a halo exchange by ONE kernel that pulls the
+ * z-neighbours' boundary planes with remote loads and synchronises with them
+ * through flags in peer memory (csrc/comm.cu).  p2p_init and p2p_register are
+ * collective (they use the NCCL communicator to publish IPC handles); every rank
+ * registers the arrays it exchanges in the same order.  *enabled == 0 / *slot < 0:
+ * peer mapping is not possible here, keep using comm_sendrecv.  p2p_exchange pulls
+ * n (<= 8) byte ranges from the array the neighbour registered in the same slot.
+ * New functionality (the reference has no distributed solve). */
+int emg3d_b200_p2p_init(int* enabled);
+int emg3d_b200_p2p_register(void* dev_ptr, int* slot);
+int emg3d_b200_p2p_exchange(int slot, int n, const size_t* my_off, const size_t* peer_off,
+                            const size_t* nbytes, const int* from_upper);
+int emg3d_b200_p2p_status(int* status);
+int emg3d_b200_p2p_shutdown(void);
 
 /* ---- host-array convenience entry points ----------------------------------
  * Exact signatures of the reference kernels on HOST arrays (upload, run,

@@ -128,6 +128,34 @@ def test_exchange_and_gather_plans_virtual(nz, nranks, n_dist):
         np.testing.assert_array_equal(out, g)
 
 
+@pytest.mark.parametrize('nz,nranks,n_dist', [(64, 2, 3), (64, 4, 2), (96, 3, 2)])
+def test_pull_plan_equals_send_recv_pairs(nz, nranks, n_dist):
+    """The peer-memory exchange (one kernel pulling from the neighbours) moves exactly
+    what the NCCL send/recv plan moves."""
+    nx, ny = 5, 3
+    part = parallel.SlabPartition(nz, nranks, n_dist)
+    for level in range(n_dist):
+        g = global_field(nx, ny, part.nz_level(level))
+        base = [local_from_global(part, level, r, nx, ny, g, owned_only=True) for r in range(nranks)]
+        a = [b.copy() for b in base]
+        plans = [parallel.exchange_plan(part, level, r, nx, ny) for r in range(nranks)]
+        for src in range(nranks):
+            for dst in range(nranks):
+                sends = [(o, n) for s, p, o, n in plans[src] if s and p == dst]
+                recvs = [(o, n) for s, p, o, n in plans[dst] if not s and p == src]
+                for (so, n), (ro, _) in zip(sends, recvs):
+                    a[dst][ro:ro + n] = base[src][so:so + n]
+        b = [x.copy() for x in base]
+        for r in range(nranks):
+            pulls = parallel.pull_plan(part, level, r, nx, ny)
+            assert len(pulls) <= 8                        # P2P_MAX_SEG of csrc/comm.cu
+            for from_upper, mo, po, n in pulls:
+                q = r + 1 if from_upper else r - 1
+                b[r][mo:mo + n] = base[q][po:po + n]
+        for r in range(nranks):
+            np.testing.assert_array_equal(a[r], b[r])
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
