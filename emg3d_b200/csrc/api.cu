@@ -74,6 +74,40 @@ struct emg3d_b200_level {
     int is_window;       // z-window of another level: h / rh are borrowed
 };
 
+// Every live level, so that a failed allocation can reclaim cached line
+// factorisations anywhere in the hierarchy (they are recomputed on demand).
+static std::vector<emg3d_b200_level*> g_levels;
+// levels at or below this many cells may be baked into CUDA graphs of the host
+// driver (solver._GRAPH_MAX_CELLS): their cached arrays must keep their addresses
+static const int64_t EVICT_MIN_CELLS = (int64_t)160 * 160 * 160 + 1;
+
+// cudaMalloc that, when out of memory, frees cached factorisations -- largest
+// first, never those of `keep` in direction `keep_dir` -- and retries.
+static cudaError_t malloc_evicting(void** p, size_t nbytes, const emg3d_b200_level* keep, int keep_dir) {
+    cudaError_t e = cudaMalloc(p, nbytes);
+    while (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        emg3d_b200_level* best = nullptr;
+        int best_dir = -1;
+        size_t best_bytes = 0;
+        for (emg3d_b200_level* lv : g_levels) {
+            if (n_cells(lv->d) < EVICT_MIN_CELLS) continue;
+            const size_t el = lv->cplx == 0 ? sizeof(double) : sizeof(cplx);
+            for (int a = 0; a < 3; ++a) {
+                if (!lv->fac[a] || (lv == keep && a == keep_dir)) continue;
+                const size_t b = (size_t)line_factor_elems(lv->d, a) * el;
+                if (b > best_bytes) { best = lv; best_dir = a; best_bytes = b; }
+            }
+        }
+        if (!best) return cudaErrorMemoryAllocation;
+        cudaStreamSynchronize(g_stream);
+        cudaFree(best->fac[best_dir]);
+        best->fac[best_dir] = nullptr;
+        e = cudaMalloc(p, nbytes);
+    }
+    return e;
+}
+
 template <typename T>
 static Model<T> model_of(const emg3d_b200_level* lv) {
     Model<T> m;
@@ -146,7 +180,10 @@ int emg3d_b200_launch_count(long long* count) {
 int emg3d_b200_malloc(void** dptr, size_t nbytes) {
     NEED_INIT();
     *dptr = nullptr;
-    CK(cudaMalloc(dptr, nbytes ? nbytes : 16));
+    {
+        cudaError_t me = malloc_evicting(dptr, nbytes ? nbytes : 16, nullptr, -1);
+        if (me != cudaSuccess) return fail("cudaMalloc", me);
+    }
     return 0;
 }
 int emg3d_b200_free(void* dptr) {
@@ -424,6 +461,7 @@ int emg3d_b200_level_create(emg3d_b200_level** out, int nx, int ny, int nz, cons
     }
     CK(cudaMalloc(&lv->scratch, sizeof(double) * residual_scratch_doubles(lv->d)));
     CK(cudaMalloc(&lv->norm2, sizeof(double) * 2));
+    g_levels.push_back(lv);
     *out = lv;
     return 0;
 }
@@ -440,6 +478,8 @@ int emg3d_b200_level_drop_factors(emg3d_b200_level* lv) {
 
 int emg3d_b200_level_destroy(emg3d_b200_level* lv) {
     if (!lv) return 0;
+    for (size_t i = 0; i < g_levels.size(); ++i)
+        if (g_levels[i] == lv) { g_levels.erase(g_levels.begin() + i); break; }
     emg3d_b200_level_drop_factors(lv);
     for (int a = 0; a < 3; ++a) {
         if (!lv->is_window) {
@@ -489,6 +529,7 @@ int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* pare
     lv->zeta = parent->zeta + coff;
     CK(cudaMalloc(&lv->scratch, sizeof(double) * residual_scratch_doubles(lv->d)));
     CK(cudaMalloc(&lv->norm2, sizeof(double) * 2));
+    g_levels.push_back(lv);
     *out = lv;
     return 0;
 }
@@ -612,7 +653,11 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
         size_t nbytes;
         emg3d_b200_level_factor_bytes(lv, ldir, &nbytes);
         if (nbytes == 0) return 0;
-        CK(cudaMalloc(&lv->fac[dir], nbytes));
+        {
+            // out of memory: reclaim cached factorisations elsewhere (recomputed when needed)
+            cudaError_t me = malloc_evicting(&lv->fac[dir], nbytes, lv, dir);
+            if (me != cudaSuccess) { lv->fac[dir] = nullptr; return fail("cudaMalloc (line factorisation)", me); }
+        }
         if (lv->cplx)
             launch_line_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac[dir], g_stream);
         else

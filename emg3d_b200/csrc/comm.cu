@@ -187,15 +187,21 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ u64 ld_relaxed_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// poll with relaxed loads, acquire once the value is there
 __device__ __forceinline__ void spin_until(const u64* p, u64 want, int* status) {
     const long long t0 = clock64();
-    while (ld_acquire_sys(p) < want) {
+    while (ld_relaxed_sys(p) < want) {
         if (clock64() - t0 > 20000000000ll) {   // ~10 s: the neighbour is gone
             atomicExch(status, 1);
             break;
         }
-        __nanosleep(100);
     }
+    (void)ld_acquire_sys(p);
 }
 
 __global__ void __launch_bounds__(256) halo_pull_kernel(P2pArgs a) {
@@ -203,7 +209,6 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(P2pArgs a) {
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
             // my planes are final: everything before this kernel in the stream is done
-            __threadfence_system();
             if (a.peer_flags[0]) st_release_sys(a.peer_flags[0] + 1, seq);   // I am its upper
             if (a.peer_flags[1]) st_release_sys(a.peer_flags[1] + 0, seq);   // I am its lower
         }
@@ -239,7 +244,6 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(P2pArgs a) {
         if (prev == gridDim.x - 1) {                     // last block: everything is copied
             *a.counter = 0;
             *a.seq = seq + 1;
-            __threadfence_system();
             if (a.peer_flags[0]) st_release_sys(a.peer_flags[0] + 3, seq);
             if (a.peer_flags[1]) st_release_sys(a.peer_flags[1] + 2, seq);
             if (a.peer_flags[0]) spin_until(a.my_flags + 2, seq, a.status);

@@ -359,6 +359,7 @@ class DistributedMultigrid:
         self._lib, self._solver = _lib, solver
         self.comm, self.rank, self.nranks = comm, comm.rank, comm.nranks
         self._slots = {}                             # device pointer -> peer-memory slot
+        self._graphs = {}                            # captured visits of level 1
         if not getattr(comm, 'p2p', False) and hasattr(comm, 'p2p_enable'):
             comm.p2p_enable()
         self.order = core.order_id(order)
@@ -559,11 +560,7 @@ class DistributedMultigrid:
             child = self.levels[level + 1]
             self._lib.check(lib.emg3d_b200_restrict(child.lv.handle.ptr, res.ptr, child.lv.s.ptr))
             child.lv.e.zero()
-            if level + 1 < self.n_dist:
-                self.multigrid(var, level + 1, cycmax - cyc)
-                self.exchange(child, child.lv.e)
-            else:
-                self._coarse_replicated(var, child, level + 1, cycmax - cyc)
+            self._descend(var, child, level + 1, cycmax - cyc)
             self._lib.check(lib.emg3d_b200_prolong(child.lv.handle.ptr, e.ptr, child.lv.e.ptr))
             self.exchange(dl, e)
             if var.nu_post > 0:
@@ -578,6 +575,50 @@ class DistributedMultigrid:
                 if solver._terminate(var, l2_last, l2_stag[(it - 1) % var.maxcycle], it):
                     break
         var.l2 = l2_last
+
+    def _descend(self, var, child, level, new_cycmax):
+        """Everything between restriction to and prolongation from `child`.
+
+        Below the finest level a visit is a fixed sequence of launches (smoothers,
+        transfer kernels, halo-exchange kernels, the gather and the replicated coarse
+        sub-cycle; no norms, no host decisions), so the visit of level 1 is captured
+        into ONE CUDA graph per rank and replayed: the first visit runs eagerly (it
+        builds caches and registers the exchanged arrays with the neighbours), the
+        second is captured.  The exchange kernels keep their sequence number in device
+        memory.  OFF by default (EMG3D_B200_DIST_GRAPHS=1 enables it): with the NCCL
+        gather of the replicated levels inside the captured region the replay hung on
+        2 B200s in r1; until the gather runs over peer memory as well, the distributed
+        levels are launched eagerly (the replicated coarse levels still replay the
+        single-GPU graphs of solver._subcycle).
+        """
+        def run():
+            if level < self.n_dist:
+                self.multigrid(var, level, new_cycmax)
+                self.exchange(child, child.lv.e)
+            else:
+                self._coarse_replicated(var, child, level, new_cycmax)
+
+        solver = self._solver
+        import os
+        if not (level == 1 and solver.GRAPHS and os.environ.get('EMG3D_B200_DIST_GRAPHS', '0') == '1'
+                and var.verb <= 3
+                and not getattr(var, '_capturing', False)):
+            return run()
+        key = (int(new_cycmax), var.cycle, int(var.lr_dir), solver._order(var), int(var.nu_pre),
+               int(var.nu_post), int(var.nu_coarse), tuple(var.clevel))
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = False
+            return run()
+        if g is False:
+            var._capturing = True
+            try:
+                with self._lib.Graph() as g:
+                    run()
+            finally:
+                var._capturing = False
+            self._graphs[key] = g
+        g.launch()
 
     def _coarse_replicated(self, var, top, level, new_cycmax):
         """Gather the coarse source, solve the coarse sub-cycle redundantly, keep our slab."""

@@ -74,6 +74,28 @@ def main():
         out["exchange_ms"] = [timed(lambda dl=dl: dmg.exchange(dl, dl.lv.e if dl.index else dmg.e), 10)
                               for dl in dmg.levels[:dmg.n_dist]]
         out["local_shapes"] = [tuple(dl.lv.shape) for dl in dmg.levels]
+        # pieces of the level-0 visit
+        d0, d1 = dmg.levels[0], dmg.levels[1]
+        var = solver.MGParameters(**kw)
+        var.l2_refe = 1.0
+        lib = _lib.load()
+
+        def res_restrict():
+            r = dmg.residual(d0, dmg.s, dmg.e)
+            _lib.check(lib.emg3d_b200_restrict(d1.lv.handle.ptr, r.ptr, d1.lv.s.ptr))
+            d1.lv.e.zero()
+
+        def prolong():
+            _lib.check(lib.emg3d_b200_prolong(d1.lv.handle.ptr, dmg.e.ptr, d1.lv.e.ptr))
+            dmg.exchange(d0, dmg.e)
+
+        out["pieces_ms"] = {
+            "smoothing_nu2": timed(lambda: dmg.smoothing(d0, dmg.s, dmg.e, 2, 0)),
+            "residual_norm": timed(lambda: dmg.residual(d0, dmg.s, dmg.e, norm=True)),
+            "residual_restrict": timed(res_restrict),
+            "descend": timed(lambda: dmg._descend(var, d1, 1, var.cycmax)),
+            "prolong": timed(prolong),
+        }
         if rank == 0:
             print(json.dumps(out), flush=True)
         del dmg
