@@ -76,6 +76,7 @@ _SIGNATURES = {
                                       POINTER(c_void_p)]),
     'emg3d_b200_amat_x': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_apply': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'emg3d_b200_point_tile_schedule': (c_int, [POINTER(c_int)]),
     'emg3d_b200_residual': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_residual_norm': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                          POINTER(c_double)]),

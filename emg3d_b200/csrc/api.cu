@@ -674,6 +674,11 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
     return 0;
 }
 
+int emg3d_b200_point_tile_schedule(int* variant) {
+    *variant = point_tile_schedule();
+    return 0;
+}
+
 int emg3d_b200_restrict(emg3d_b200_level* c, const void* r_fine, void* s_coarse) {
     NEED_INIT();
     if (!c->linked) return fail_msg("restrict: coarse level is not linked to a fine level");

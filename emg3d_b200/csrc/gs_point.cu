@@ -342,6 +342,311 @@ gs_point_tile_kernel(Model<T> m, T* e, const T* s, int tcx, int tcy, int tcz, in
     }
 }
 
+// ---- y-marching variant of the tile-fused sweep ---------------------------------
+// ncu (r1): the tile kernel above is bound by the L1/LSU pipe (60 % of peak
+// wavefronts, 53 % of the warp stalls are waits on the load batch of a colour
+// phase): 50 loads per node, 42 of them 16-byte loads with stride 2 between
+// lanes.  Marching along y inside a tile removes 19 of them.  A tile is relaxed
+// by ONE warp; lane = one column (ix, iz) of the tile, columns coloured by the
+// parity of (ix, iz) (4 colours; columns of one colour are two nodes apart in x
+// or z and never interact, whatever their y positions), and every lane walks its
+// column in y, node after node -- a sequential Gauss-Seidel order along y.  What
+// two consecutive nodes of a column share stays in registers (MarchCarry): the
+// previous node's solved x- and z-edges are the outer edges of the next node's
+// low faces, the outer y-edges / zeta / 1/h_y of the cell row between them are
+// loaded once, and the y-edge between them is re-solved without being re-read.
+// Per node: 16 E loads instead of 24, 5 + 5 source / diagonal loads instead of
+// 6 + 6, 4 zeta instead of 8, 5 stores instead of 6; no block barriers (one
+// __syncwarp per column colour).  Odd sweeps run the colours and the columns in
+// the opposite direction, so that a pair of sweeps is a symmetric Gauss-Seidel.
+template <typename T>
+struct MarchCarry {
+    T xs[2];           // solved ex of the previous node, by side flag (0: x+, 1: x-)
+    T zs[2];           // solved ez of the previous node, by side flag (0: z+, 1: z-)
+    T eyx[2];          // ey of the cell row behind at x-node ix+1 (flag 0) / ix-1 (flag 1)
+    T eyz[2];          // ey of the cell row behind at z-node iz+1 (flag 0) / iz-1 (flag 1)
+    T sY, dY;          // source and diagonal of the y-edge behind
+    double zb[2][2];   // zeta of the cell row behind, [x-cell][z-cell]
+    double rhb;        // 1/h_y of the cell row behind
+};
+
+// same arithmetic as Faces::quad, outer edges passed by value
+template <typename T, int P, int Q, int SP, int SQ>
+__device__ __forceinline__ void face_acc(const double (&z)[2][2][2], const double (&rh)[3][2],
+                                         const T ep, const T eq, NodeSys<T>& n) {
+    constexpr int W = 3 - P - Q;
+    constexpr int i0x = P == 0 ? 1 - SP : Q == 0 ? 1 - SQ : 0;
+    constexpr int i0y = P == 1 ? 1 - SP : Q == 1 ? 1 - SQ : 0;
+    constexpr int i0z = P == 2 ? 1 - SP : Q == 2 ? 1 - SQ : 0;
+    constexpr int i1x = W == 0 ? 1 : i0x, i1y = W == 1 ? 1 : i0y, i1z = W == 2 ? 1 : i0z;
+    const double g = 0.5 * (z[i0x][i0y][i0z] + z[i1x][i1y][i1z]);
+    const double rp = rh[P][1 - SP], rq = rh[Q][1 - SQ];
+    const double al_p = SQ ? -rq : rq;
+    const double al_q = SP ? rp : -rp;
+    const T out = al_p * ep + al_q * eq;
+    constexpr int kq = 2 * (Q - 1) + (1 - SQ);
+    if (P == 0) {
+        constexpr int j = 1 - SP;
+        n.B[j][kq] += g * al_p * al_q;
+        n.bX[j] += (g * al_p) * out;
+    } else {
+        constexpr int kp = 1 - SP;
+        n.cyz[1 - SQ][1 - SP] += g * al_p * al_q;
+        n.bT[kp] += (g * al_p) * out;
+    }
+    n.bT[kq] += (g * al_q) * out;
+}
+
+#define SS(r, c) s4[((r) * ((r) + 1)) / 2 + (c)]
+// solve the assembled node system in place: n.bX, n.bT become the solution
+// (same elimination as node_update: x-edges first, then LDL^T of the 4x4 Schur
+// complement)
+template <typename T>
+__device__ __forceinline__ void node_eliminate(NodeSys<T>& n) {
+    T rX[2], tX[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        rX[j] = rcp(n.dX[j]);
+        tX[j] = rX[j] * n.bX[j];
+    }
+    T s4[10];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (l <= k) {
+                T v = (n.B[0][k] * n.B[0][l]) * rX[0] + (n.B[1][k] * n.B[1][l]) * rX[1];
+                T cc = zero_<T>();
+                if (k == l) cc = n.dT[k];
+                else if (k >= 2 && l < 2) add_real(cc, n.cyz[k - 2][l]);
+                SS(k, l) = cc - v;
+            }
+        }
+        n.bT[k] -= n.B[0][k] * tX[0] + n.B[1][k] * tX[1];
+    }
+    T dinv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T v[4];
+        T dj = SS(j, j);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < j) {
+                v[k] = SS(j, k) * SS(k, k);
+                dj -= SS(j, k) * v[k];
+            }
+        }
+        SS(j, j) = dj;
+        const T r = rcp(dj);
+        dinv[j] = r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i > j) {
+                T t = SS(i, j);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < j) t -= SS(i, k) * v[k];
+                SS(i, j) = t * r;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < j) n.bT[j] -= SS(j, k) * n.bT[k];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n.bT[j] = n.bT[j] * dinv[j];
+#pragma unroll
+    for (int j = 2; j >= 0; --j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k > j) n.bT[j] -= SS(k, j) * n.bT[k];
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        T acc = n.bX[j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc -= n.B[j][k] * n.bT[k];
+        n.bX[j] = rX[j] * acc;
+    }
+}
+#undef SS
+
+// One column (ix, iz), nodes iy = y_first, y_first + DIR, ... (count nodes).
+template <typename T, int DIR>
+__device__ __forceinline__ void march_column(const Model<T>& m, const FieldView<T>& E,
+                                             const FieldView<const T>& S, int ix, int iz,
+                                             int y_first, int count) {
+    constexpr int JA = DIR > 0 ? 1 : 0;     // index of the cell row / y-edge ahead (0: iy-1, 1: iy)
+    constexpr int JB = 1 - JA;
+    constexpr int SA = 1 - JA;              // side flag of the faces ahead (0: plus side)
+    constexpr int SB = 1 - SA;
+    const int64_t cs1 = m.d.n[0], cs2 = (int64_t)m.d.n[0] * m.d.n[1];
+    const T* const dg = m.diag;             // field layout, relative to the x-component
+    const int64_t dof[3] = {0, (int64_t)(S.p[1] - S.p[0]), (int64_t)(S.p[2] - S.p[0])};
+
+    double rhx[2], rhz[2];
+    rhx[0] = ldg(m.rh[0] + ix - 1); rhx[1] = ldg(m.rh[0] + ix);
+    rhz[0] = ldg(m.rh[2] + iz - 1); rhz[1] = ldg(m.rh[2] + iz);
+
+    // prologue: everything the first node needs from the row / cell row behind it
+    MarchCarry<T> cr;
+    {
+        const int iy = y_first, yb = iy - DIR, cb = iy - 1 + JB;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            cr.xs[f] = E.p[0][E.idx(0, ix - f, yb, iz)];
+            cr.zs[f] = E.p[2][E.idx(2, ix, yb, iz - f)];
+            cr.eyx[f] = E.p[1][E.idx(1, ix + (f ? -1 : 1), cb, iz)];
+            cr.eyz[f] = E.p[1][E.idx(1, ix, cb, iz + (f ? -1 : 1))];
+        }
+        const int64_t idb = S.idx(1, ix, cb, iz);
+        cr.sY = ldg(S.p[1] + idb);
+        cr.dY = ldg(dg + dof[1] + idb);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                cr.zb[i][k] = ldg(m.zeta + (ix - 1 + i) + cs1 * cb + cs2 * (iz - 1 + k));
+        cr.rhb = ldg(m.rh[1] + cb);
+    }
+
+    for (int step = 0; step < count; ++step) {
+        const int iy = y_first + DIR * step;
+        const int ya = iy + DIR, ca = iy - 1 + JA, cb = iy - 1 + JB;
+        const bool last = step == count - 1;
+
+        // ---- loads -------------------------------------------------------------------
+        T exA[2], eyxA[2], eyzA[2], ezA[2], exZ[2][2], ezX[2][2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            exA[f] = E.p[0][E.idx(0, ix - f, ya, iz)];
+            eyxA[f] = E.p[1][E.idx(1, ix + (f ? -1 : 1), ca, iz)];
+            eyzA[f] = E.p[1][E.idx(1, ix, ca, iz + (f ? -1 : 1))];
+            ezA[f] = E.p[2][E.idx(2, ix, ya, iz - f)];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                exZ[f][q] = E.p[0][E.idx(0, ix - f, iy, iz + (q ? -1 : 1))];
+                ezX[f][q] = E.p[2][E.idx(2, ix + (f ? -1 : 1), iy, iz - q)];
+            }
+        }
+        const int64_t idx0 = S.idx(0, ix - 1, iy, iz), idya = S.idx(1, ix, ca, iz),
+                      idz0 = S.idx(2, ix, iy, iz - 1);
+        const int64_t zst = S.s2[2];
+        NodeSys<T> n;
+        n.bX[0] = ldg(S.p[0] + idx0);      n.dX[0] = ldg(dg + idx0);
+        n.bX[1] = ldg(S.p[0] + idx0 + 1);  n.dX[1] = ldg(dg + idx0 + 1);
+        const T sYa = ldg(S.p[1] + idya), dYa = ldg(dg + dof[1] + idya);
+        n.bT[JA] = sYa;                    n.dT[JA] = dYa;
+        n.bT[JB] = cr.sY;                  n.dT[JB] = cr.dY;
+        n.bT[2] = ldg(S.p[2] + idz0);        n.dT[2] = ldg(dg + dof[2] + idz0);
+        n.bT[3] = ldg(S.p[2] + idz0 + zst);  n.dT[3] = ldg(dg + dof[2] + idz0 + zst);
+        double za[2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                za[i][k] = ldg(m.zeta + (ix - 1 + i) + cs1 * ca + cs2 * (iz - 1 + k));
+        const double rha = ldg(m.rh[1] + ca);
+
+        // ---- assemble ----------------------------------------------------------------
+        double z[2][2][2], rh[3][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                z[i][JA][k] = za[i][k];
+                z[i][JB][k] = cr.zb[i][k];
+            }
+        rh[0][0] = rhx[0]; rh[0][1] = rhx[1];
+        rh[2][0] = rhz[0]; rh[2][1] = rhz[1];
+        rh[1][JA] = rha;   rh[1][JB] = cr.rhb;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n.B[j][k] = 0.0;
+        n.cyz[0][0] = n.cyz[0][1] = n.cyz[1][0] = n.cyz[1][1] = 0.0;
+
+        // plane (x, y): faces ahead use loaded edges, faces behind the carried ones
+        face_acc<T, 0, 1, 0, SA>(z, rh, exA[0], eyxA[0], n);
+        face_acc<T, 0, 1, 1, SA>(z, rh, exA[1], eyxA[1], n);
+        face_acc<T, 0, 1, 0, SB>(z, rh, cr.xs[0], cr.eyx[0], n);
+        face_acc<T, 0, 1, 1, SB>(z, rh, cr.xs[1], cr.eyx[1], n);
+        // plane (x, z)
+        face_acc<T, 0, 2, 0, 0>(z, rh, exZ[0][0], ezX[0][0], n);
+        face_acc<T, 0, 2, 0, 1>(z, rh, exZ[0][1], ezX[0][1], n);
+        face_acc<T, 0, 2, 1, 0>(z, rh, exZ[1][0], ezX[1][0], n);
+        face_acc<T, 0, 2, 1, 1>(z, rh, exZ[1][1], ezX[1][1], n);
+        // plane (y, z)
+        face_acc<T, 1, 2, SA, 0>(z, rh, eyzA[0], ezA[0], n);
+        face_acc<T, 1, 2, SA, 1>(z, rh, eyzA[1], ezA[1], n);
+        face_acc<T, 1, 2, SB, 0>(z, rh, cr.eyz[0], cr.zs[0], n);
+        face_acc<T, 1, 2, SB, 1>(z, rh, cr.eyz[1], cr.zs[1], n);
+
+        node_eliminate<T>(n);
+
+        // ---- write back, carry ---------------------------------------------------------
+        E.p[0][idx0] = n.bX[0];
+        E.p[0][idx0 + 1] = n.bX[1];
+        E.p[2][idz0] = n.bT[2];
+        E.p[2][idz0 + zst] = n.bT[3];
+        E.p[1][E.idx(1, ix, cb, iz)] = n.bT[JB];
+        if (last) E.p[1][idya] = n.bT[JA];     // otherwise re-solved by the next node
+        cr.xs[0] = n.bX[1]; cr.xs[1] = n.bX[0];
+        cr.zs[0] = n.bT[3]; cr.zs[1] = n.bT[2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            cr.eyx[f] = eyxA[f];
+            cr.eyz[f] = eyzA[f];
+        }
+        cr.sY = sYa; cr.dY = dYa;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) cr.zb[i][k] = za[i][k];
+        cr.rhb = rha;
+    }
+}
+
+// Measured (r1, 256^3, B200; profiles/r1_notes.md): correct (parity-tested against
+// the oracle in the same order) but SLOWER than the 8-colour tile kernel, 0.298 ms
+// instead of 0.181 ms per tile-colour launch.  One warp per tile puts 8 tiles per
+// SM in flight, 1184 x 252 KB = 300 MB of tile footprints against 126 MB of L2: the
+// L2 hit rate drops from 47 % to 19 %, every step of a column waits for DRAM
+// (long-scoreboard stall 8.1 of 11 cycles per issued instruction) and nothing is
+// prefetched across steps.  Kept as an option (-DEMG_PT_MARCH=1), off by default.
+#ifndef EMG_PT_MARCH
+#define EMG_PT_MARCH 0            // 1: y-marching tile kernel, 0: 8-colour tile kernel
+#endif
+#ifndef EMG_MARCH_MINB
+#define EMG_MARCH_MINB 8
+#endif
+static_assert((TX / 2) * (TZ / 2) == 32, "the marching kernel maps one tile to one warp");
+
+template <typename T>
+__global__ void __launch_bounds__(32, EMG_MARCH_MINB)
+gs_point_march_kernel(Model<T> m, T* e, const T* s, int tcx, int tcy, int tcz, int back) {
+    const int x0 = 1 + (2 * blockIdx.x + tcx) * TX;
+    const int y0 = 1 + (2 * blockIdx.y + tcy) * TY;
+    const int z0 = 1 + (2 * blockIdx.z + tcz) * TZ;
+    const int i = threadIdx.x % (TX / 2), k = threadIdx.x / (TX / 2);
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    const int y1 = min(y0 + TY, m.d.n[1]) - 1;           // last node of the tile in y
+    const int count = y1 - y0 + 1;
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c = back ? 3 - cc : cc;
+        const int ix = x0 + 2 * i + (c & 1), iz = z0 + 2 * k + (c >> 1);
+        if (ix < m.d.n[0] && iz < m.d.n[2] && count > 0) {
+            if (back) march_column<T, -1>(m, E, S, ix, iz, y1, count);
+            else march_column<T, 1>(m, E, S, ix, iz, y0, count);
+        }
+        __syncwarp();      // the next column colour reads what this one wrote
+    }
+}
+
 // one hyperplane ix + 2 iy + 3 iz = t of the lexicographic sweep
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -429,7 +734,11 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
                 const int tcx = c & 1, tcy = (c >> 1) & 1, tcz = (c >> 2) & 1;
                 dim3 g((ntx - tcx + 1) / 2, (nty - tcy + 1) / 2, (ntz - tcz + 1) / 2);
                 if (g.x == 0 || g.y == 0 || g.z == 0) continue;
+#if EMG_PT_MARCH
+                ++g_launch_count; gs_point_march_kernel<T><<<g, 32, 0, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
+#else
                 ++g_launch_count; gs_point_tile_kernel<T><<<g, TILE_THREADS, 0, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
+#endif
             }
         } else {
             for (int cc = 0; cc < 8; ++cc) {
@@ -444,6 +753,8 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
         }
     }
 }
+
+int point_tile_schedule() { return EMG_PT_MARCH ? 1 : 0; }
 
 template void launch_gs_point<double>(const Model<double>&, double*, const double*, int, int, cudaStream_t);
 template void launch_gs_point<cplx>(const Model<cplx>&, cplx*, const cplx*, int, int, cudaStream_t);

@@ -25,6 +25,9 @@ int64_t residual_scratch_doubles(const Dims& d);
 
 template <typename T>
 void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cudaStream_t st);
+// order inside a tile of the tile-fused schedule: 0 = 8 node colours, 1 = 4 column
+// colours with a sequential march along y (tests build the oracle's sequence from it)
+int point_tile_schedule();
 // diagonal of A per edge (field layout), read by the point smoother through m.diag
 template <typename T>
 void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st);

@@ -127,6 +127,11 @@ int emg3d_b200_residual_norm(emg3d_b200_level* lv, const void* s, const void* e,
  * sweeps; COLOR = multicolour ordering (8 colours point, 4 colours lines).     */
 int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu, int ldir,
                             int order);
+/* Node order inside a tile of the point smoother's tile-fused multicolour schedule
+ * (grids beyond the L2): 0 = the 8 parity classes one after the other, 1 = 4 column
+ * colours (parity of ix, iz), every column relaxed sequentially along y
+ * (csrc/gs_point.cu).  Tests use it to run the oracle in the same order. */
+int emg3d_b200_point_tile_schedule(int* variant);
 /* coarse_s = R r_fine.  Replaces core.restrict (core.py:1620-1621).            */
 int emg3d_b200_restrict(emg3d_b200_level* coarse, const void* r_fine, void* s_coarse);
 /* e_fine += P e_coarse on interior edges.  Replaces solver.prolongation

@@ -189,12 +189,14 @@ TILE = (16, 8, 8)
 TILE_MIN_NODES = 300000
 
 
-def color_sequence(ldir, shape, nu):
+def color_sequence(ldir, shape, nu, tile_variant=0):
     """Block sequence of ``nu`` multicolour sweeps as the CUDA kernels run them.
 
     Point smoother: 8 parity classes of (ix-1, iy-1, iz-1), class index
     ``px + 2 py + 4 pz``; line smoothers: 4 classes ``pp + 2 pq`` of the
-    transverse node indices.  Odd sweeps run the classes in descending order,
+    transverse node indices (``tile_variant``: node order inside a tile of the
+    tile-fused point smoother, see emg3d_b200_point_tile_schedule in the C header).
+    Odd sweeps run the classes in descending order,
     even sweeps ascending (the first sweep of the reference is the descending
     one, core.py:301, 311).
     """
@@ -211,6 +213,24 @@ def color_sequence(ldir, shape, nu):
             tx, ty, tz = TILE
             ntile = [-(-(n - 1) // t) for n, t in zip(shape, TILE)]
             classes = list(range(7, -1, -1) if back else range(8))
+            if tile_variant == 1:
+                # y-marching tiles: per tile colour, 4 column colours (parity of ix,
+                # iz); a column is relaxed node after node along y (descending on
+                # odd sweeps); columns of one colour are independent
+                for tc in classes:
+                    for cc in (range(3, -1, -1) if back else range(4)):
+                        px, pz = cc & 1, cc >> 1
+                        for kz in range((tc >> 2) & 1, ntile[2], 2):
+                            for ky in range((tc >> 1) & 1, ntile[1], 2):
+                                for kx in range(tc & 1, ntile[0], 2):
+                                    ys = list(range(1 + ky * ty, min(ny, 1 + (ky + 1) * ty)))
+                                    if back:
+                                        ys.reverse()
+                                    for iz in range(1 + kz * tz + pz, min(nz, 1 + (kz + 1) * tz), 2):
+                                        for ix in range(1 + kx * tx + px, min(nx, 1 + (kx + 1) * tx), 2):
+                                            for iy in ys:
+                                                rows.append((ix, iy, iz))
+                continue
             for tc in classes:
                 for c in classes:
                     px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1

@@ -102,6 +102,14 @@ BIG = [((24, 20, 18), True), ((6, 40, 36), True), ((38, 5, 37), False), ((36, 35
        ((12, 11, 9), False)]
 
 
+def _tile_variant():
+    import ctypes
+    from emg3d_b200 import _lib
+    v = ctypes.c_int(0)
+    _lib.check(_lib.load().emg3d_b200_point_tile_schedule(ctypes.byref(v)))
+    return v.value
+
+
 @pytest.mark.parametrize('ldir', [0, 1, 2, 3])
 @pytest.mark.parametrize('order', ['lex', 'color'])
 def test_gauss_seidel_vs_oracle(core, ldir, order):
@@ -116,7 +124,7 @@ def test_gauss_seidel_vs_oracle(core, ldir, order):
             if order == 'lex':
                 ofn(*split_field(shape, e_cpu), *split_field(shape, c['s']), *_margs(c), nu)
             else:
-                seq = oracle.color_sequence(ldir, shape, nu)
+                seq = oracle.color_sequence(ldir, shape, nu, tile_variant=_tile_variant())
                 oracle.gs_sequence(ldir, *split_field(shape, e_cpu), *split_field(shape, c['s']),
                                    *_margs(c), seq)
             assert rel_err(e_gpu, e_cpu) < 1e-11, (shape, nu)
