@@ -555,10 +555,14 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
                        "l2": "working set 3.2 GB per GPU and step, far larger than the 126 MB L2",
                        "parallelism": f"one solve on {world} GPUs: z-slabs of {shape[2] // world} cell layers, "
                                       f"{dmg.n_dist} distributed levels, coarser levels replicated; halo "
-                                      "exchange of E (ncclSend/ncclRecv over NVLink) after every sweep, "
-                                      "residual and prolongation; norms all-reduced"},
+                                      "exchange of E after every sweep, residual and prolongation by "
+                                      + ("one peer-memory kernel per exchange (CUDA IPC mapping of the "
+                                         "neighbours' slabs, remote loads over NVLink, flag handshake)"
+                                         if comm.p2p else "ncclSend/ncclRecv over NVLink")
+                                      + "; norms all-reduced (NCCL)"},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
-            "halo_exchange": {"ms": halo_ms, "bytes_sent_per_rank": int(halo_bytes),
+            "halo_exchange": {"transport": "peer-memory kernel" if comm.p2p else "nccl", "ms": halo_ms,
+                              "bytes_sent_per_rank": int(halo_bytes),
                               "GBs_per_direction": halo_bytes / 2 / (halo_ms * 1e-3) / 1e9 if halo_ms else None},
             "gpu_launches": int(launches), "clocks": clocks, "device": _lib.device_name(),
         }

@@ -439,3 +439,51 @@ def test_sparse_upload_is_bit_identical():
     d = _lib.DeviceArray(z.size, z.dtype)
     d.upload(np.ones(5000))
     assert d.upload_sparse(z) and not d.download().any()
+
+
+def test_owned_planes_restrict_the_fused_norm():
+    """emg3d_b200_level_set_owned: the norm of the residual kernel counts x/y-edges on
+    the owned node planes and z-edges of the layers whose upper plane is owned (what a
+    multi-GPU rank contributes to ||r||); plane1 = 0 restores the full norm."""
+    from emg3d_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    for shape in ((12, 10, 9), (104, 100, 101)):          # simple and plane-streaming kernels
+        c = random_case(rng, shape, True, aliased=True)
+        nz = shape[2]
+        dt = c['e'].dtype
+        handle = _lib.LevelHandle((c['hx'], c['hy'], c['hz']))
+        d_eta = _lib.DeviceArray.from_host(np.asfortranarray(c['eta_x']).ravel('F').astype(dt))
+        d_zeta = _lib.DeviceArray.from_host(np.asfortranarray(c['zeta']).ravel('F'))
+        handle.set_model(True, d_eta, d_eta, d_eta, d_zeta)
+        d_s, d_e = _lib.DeviceArray.from_host(c['s']), _lib.DeviceArray.from_host(c['e'])
+        d_r = _lib.DeviceArray(c['e'].size, dt)
+        out = _lib.DeviceArray(2, np.float64)
+        _lib.check(lib.emg3d_b200_residual(handle.ptr, d_s.ptr, d_e.ptr, d_r.ptr, out.ptr))
+        full = out.download()[0]
+        r = d_r.download()
+        assert abs(full - np.vdot(r, r).real) <= 1e-12 * full
+        rx, ry, rz = split_field(shape, r)
+        p0, p1 = 3, nz - 2
+        _lib.check(lib.emg3d_b200_level_set_owned(handle.ptr, p0, p1))
+        _lib.check(lib.emg3d_b200_residual(handle.ptr, d_s.ptr, d_e.ptr, None, out.ptr))
+        want = (np.sum(np.abs(rx[:, :, p0:p1])**2) + np.sum(np.abs(ry[:, :, p0:p1])**2)
+                + np.sum(np.abs(rz[:, :, p0 - 1:p1 - 1])**2))
+        assert abs(out.download()[0] - want) <= 1e-12 * want
+        _lib.check(lib.emg3d_b200_level_set_owned(handle.ptr, 0, 0))
+        _lib.check(lib.emg3d_b200_residual(handle.ptr, d_s.ptr, d_e.ptr, None, out.ptr))
+        assert abs(out.download()[0] - full) <= 1e-14 * full
+
+
+def test_peer_memory_api_needs_a_communicator():
+    """The p2p entry points fail loudly (no silent fallback) without comm_init."""
+    import ctypes
+    from emg3d_b200 import _lib
+    lib = _lib.init()
+    on = ctypes.c_int(1)
+    assert lib.emg3d_b200_p2p_init(ctypes.byref(on)) != 0
+    slot = ctypes.c_int(0)
+    assert lib.emg3d_b200_p2p_register(None, ctypes.byref(slot)) != 0
+    st = ctypes.c_int(5)
+    _lib.check(lib.emg3d_b200_p2p_status(ctypes.byref(st)))
+    assert st.value == 0
