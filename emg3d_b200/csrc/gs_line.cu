@@ -516,6 +516,91 @@ struct Staged {
     }
 };
 
+// Factor stream through TMA: the factors of one block of the 32 lines of a warp are
+// ONE contiguous chunk of 15 * 32 words (layout above), so a single elected lane
+// fetches it with one cp.async.bulk (UBLKCP) into a per-warp shared-memory ring,
+// BULK_STAGES blocks ahead of the block being solved, completion on an mbarrier.
+// The fetch sequence runs through the forward pass (blocks 0 .. N-1) and straight on
+// into the backward pass (blocks N-2 .. 0), so the ring never drains between the
+// passes.  No registers and no LSU instructions are spent on the factor stream; the
+// strided E / S / zeta accesses stay ordinary loads through the L1.
+#ifndef EMG_LINE_BULK
+#define EMG_LINE_BULK 0
+#endif
+#ifndef EMG_LINE_BULK_STAGES
+#define EMG_LINE_BULK_STAGES 4
+#endif
+constexpr int BULK_STAGES = EMG_LINE_BULK_STAGES;
+
+template <typename T, int D>
+struct BulkFac {
+    using FwdView = RegWords<T, FWD_WORDS>;
+    using BwdView = RegWords<T, BWD_WORDS>;
+    static constexpr unsigned BYTES = FAC_BS * sizeof(T);
+    const LineAddr<T, D>& a;
+    const Line<T, D>& ln;
+    int N, lane, q;
+    unsigned mask;
+    T* ring;              // this warp's ring: [stage][entry][lane]
+    uint64_t* bars;       // this warp's mbarriers: [stage]
+    const T* gsrc;        // (block 0, entry 0, lane 0) of the warp's 32-line group
+    __device__ BulkFac(const LineAddr<T, D>& a_, const Line<T, D>& ln_, T* ring_, uint64_t* bars_,
+                       unsigned mask_)
+        : a(a_), ln(ln_), N(ln_.N), lane(threadIdx.x & 31), q(0), mask(mask_), ring(ring_), bars(bars_),
+          gsrc(a_.fac - (threadIdx.x & 31)) {}
+
+    // fetch number qq of the sequence: forward blocks 0 .. N-1, then backward N-2 .. 0
+    __device__ __forceinline__ void issue(int qq) {
+        if (qq > 2 * N - 2) return;
+        const int blk = qq < N ? qq : 2 * N - 2 - qq;
+        const int st = qq % BULK_STAGES;
+        mbar_expect_tx(bars + st, BYTES);
+        bulk_g2s(ring + st * FAC_BS, gsrc + (int64_t)blk * FAC_BS, BYTES, bars + st);
+    }
+    __device__ __forceinline__ void fwd_start() {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < BULK_STAGES; ++k) issue(k);
+        }
+    }
+    __device__ __forceinline__ void bwd_start() {}
+    template <class V>
+    __device__ __forceinline__ void factors(V& w) {
+        const int st = q % BULK_STAGES;
+        mbar_wait(bars + st, (q / BULK_STAGES) & 1);
+        const T* p = ring + st * FAC_BS + lane;
+#pragma unroll
+        for (int e = 0; e < 15; ++e) w.v[e] = p[e * FAC_ES];
+        __syncwarp(mask);                       // every lane has read the stage
+        if (lane == 0) {
+            fence_proxy_async_smem();
+            issue(q + BULK_STAGES);
+        }
+        ++q;
+    }
+    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
+        FwdView w;
+        factors(w);
+        w.v[15] = ldg(a.fwd_src(15, j));
+        if (j < N - 1) {
+#pragma unroll
+            for (int e = 16; e < 20; ++e) w.v[e] = ldg(a.fwd_src(e, j));
+#pragma unroll
+            for (int e = 20; e < FWD_WORDS; ++e) w.v[e] = *a.fwd_src(e, j);
+            ln.load_zeta(j + 1, zn);
+        }
+        return w;
+    }
+    __device__ __forceinline__ BwdView bwd_get(int, int i, double zc[2][2]) {
+        BwdView w;
+        factors(w);
+#pragma unroll
+        for (int e = 15; e < BWD_WORDS; ++e) w.v[e] = *a.bwd_src(e, i);
+        if (i > 0) ln.load_zeta(i, zc);
+        return w;
+    }
+};
+
 template <typename T, class W>
 __device__ __forceinline__ void solve5(const W& f, T y[5], bool first_zero) {
     T L[10], dinv[5];
@@ -717,12 +802,29 @@ template <typename T, int D>
 __global__ void __launch_bounds__(64)
 gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c) {
     int tp, tq;
-    if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
+    const bool valid = class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq);
+#if EMG_LINE_BULK && !EMG_LINE_STAGED
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+#endif
+    if (!valid) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
     Line<T, D> ln(m, tp, tq);
     LineAddr<T, D> ad(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
-#if EMG_LINE_STAGED
+#if EMG_LINE_BULK && !EMG_LINE_STAGED
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    T* ring = reinterpret_cast<T*>(ring_raw) + (size_t)warp * BULK_STAGES * FAC_BS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<T*>(ring_raw) +
+                                                 (size_t)nwarps * BULK_STAGES * FAC_BS) + warp * BULK_STAGES;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < BULK_STAGES; ++k) mbar_init(bars + k, 1);
+        mbar_init_fence();
+    }
+    __syncwarp(mask);
+    BulkFac<T, D> ld(ad, ln, ring, bars, mask);
+#elif EMG_LINE_STAGED
     extern __shared__ __align__(16) unsigned char ring_raw[];
     const int nt = blockDim.x;
     T* smT = reinterpret_cast<T*>(ring_raw) + threadIdx.x;
@@ -841,6 +943,15 @@ static void gs_dir(const Model<T>& m, const T* fac, T* e, const T* s, int nu, in
                 if (ls.cnt[c] == 0) continue;
                 const int threads = EMG_LINE_STAGED ? 32 : 64;
                 size_t smem = 0;
+#if EMG_LINE_BULK && !EMG_LINE_STAGED
+                smem = (size_t)(threads / 32) * BULK_STAGES * (FAC_BS * sizeof(T) + sizeof(uint64_t));
+                static bool bulk_attr_set = false;  // per template instance
+                if (!bulk_attr_set) {
+                    cudaFuncSetAttribute(gs_line_color_kernel<T, D>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    bulk_attr_set = true;
+                }
+#endif
 #if EMG_LINE_STAGED
                 smem = (size_t)LINE_STAGES * threads * (FWD_WORDS * sizeof(T) + 4 * sizeof(double));
                 static bool attr_set = false;       // per template instance

@@ -1,16 +1,16 @@
 #!/bin/bash
-# Prefetch-distance sweep of the line smoothers (run on the GPU box):
-#   tools/tune_line.sh "0 3 6 12"
-cd "$(dirname "$0")/../emg3d_b200/csrc" || exit 1
-for PF in ${1:-0 3 6 12}; do
-    touch gs_line.cu
-    make EXTRA="-DEMG_LINE_PREFETCH=$PF" > /dev/null 2>&1 || { echo "build failed"; exit 1; }
-    echo "== EMG_LINE_PREFETCH=$PF"
-    (cd ../.. && python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print({k:round(v.get('ms_nu2',v.get('ms')),3) for k,v in d['kernels'].items()})" ; python tools/run_configs.py config2:128 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('config2:128 warm cycles', d['cycle_s_warm'][1:4], 'it', d['it_mg'])")
-done
-touch gs_line.cu; make > /dev/null 2>&1
+# Line smoothers: factor stream through TMA bulk copies (EMG_LINE_BULK, ring depth) vs plain loads.
+cd "$(dirname "$0")/../emg3d_b200/csrc"
+while read -r a b; do
+  [ -z "$a" ] && continue
+  rm -f build/gs_line.o
+  make -s EXTRA="-DEMG_LINE_BULK=$a -DEMG_LINE_BULK_STAGES=$b -Xptxas -v" 2>&1 | grep -A2 "gs_line_color_kernelINS_4cplxELi0" | grep -E "registers|spill" | tr '\n' ' '
+  echo
+  (cd ../.. && python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('bulk stages = $a $b:', {k: round(v.get('ms_nu2', v.get('ms')), 3) for k, v in d['kernels'].items()})")
+done <<LIST
+${1:-1 4
+1 8
+1 2
+0 4}
+LIST
