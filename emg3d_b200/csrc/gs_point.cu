@@ -689,6 +689,7 @@ gs_point_small_kernel(Model<T> m, T* e, const T* s, int nu, int order) {
         } else {
             for (int cc = 0; cc < 8; ++cc) {
                 const int c = back ? 7 - cc : cc;
+                if (sw > 0 && cc == 0) continue;   // idempotent repeat, see launch_gs_point
                 const int px = c & 1, py = (c >> 1) & 1, pz = (c >> 2) & 1;
                 for (int q = threadIdx.x; q < nint; q += blockDim.x) {
                     const int ix = 1 + q % (nx - 1);
@@ -743,6 +744,10 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
         } else {
             for (int cc = 0; cc < 8; ++cc) {
                 const int c = back ? 7 - cc : cc;
+                // the first colour of a sweep is the last colour of the previous sweep
+                // (opposite order); nodes of one colour do not interact and nothing
+                // changed in between, so relaxing them again reproduces the same values
+                if (sw > 0 && cc == 0) continue;
                 const int fx = 1 + (c & 1), fy = 1 + ((c >> 1) & 1), fz = 1 + ((c >> 2) & 1);
                 const int cx = (nx - fx + 1) / 2, cy = (ny - fy + 1) / 2, cz = (nz - fz + 1) / 2;
                 if (cx <= 0 || cy <= 0 || cz <= 0) continue;

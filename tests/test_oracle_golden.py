@@ -40,6 +40,31 @@ def test_gauss_seidel(golden, ldir):
             assert rel_err(e, gk[c['prefix'] + f'gs{ldir}_nu{nu}']) < KTOL
 
 
+@pytest.mark.parametrize('ldir', [0, 1, 2, 3])
+def test_relaxing_one_colour_twice_changes_nothing(golden, ldir):
+    """Blocks of one colour class do not interact, so a second relaxation of the class
+    reproduces the first (to rounding).  The CUDA smoothers rely on this: consecutive
+    sweeps run the colours in opposite order and the repeated colour is skipped
+    (csrc/gs_line.cu gs_dir, csrc/gs_point.cu launch_gs_point)."""
+    gk = golden('kernels')
+    c = kernel_case(gk, 0)
+    shape = c['shape']
+    seq = oracle.color_sequence(ldir, shape, 2)           # sweep 1 descending, sweep 2 ascending
+    n = len(seq) // 2
+    par = seq % 2
+    k = 1                                                 # length of the first class of sweep 2
+    while k < n and np.array_equal(par[n + k], par[n]):
+        k += 1
+    # the class that ends sweep 1 is the class that starts sweep 2
+    assert {tuple(r) for r in seq[n - k:n]} == {tuple(r) for r in seq[n:n + k]}
+    args = (c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'], c['hx'], c['hy'], c['hz'])
+    e = c['e'].copy()
+    oracle.gs_sequence(ldir, *split_field(shape, e), *split_field(shape, c['s']), *args, seq[:n])
+    e2 = e.copy()
+    oracle.gs_sequence(ldir, *split_field(shape, e2), *split_field(shape, c['s']), *args, seq[n:n + k])
+    assert rel_err(e2, e) < 1e-13
+
+
 def test_solve_known_answer():
     # band LDL^T against a dense solve (the reference tests do the same,
     # tests/test_core.py:203-262), real and complex, n = 6 and a long band
