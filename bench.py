@@ -335,6 +335,15 @@ def main():
         gbs = (bytes_per_cell_sweep + 0) * cells / (t * 1e-3) / 1e9
         kernels['residual'] = {"ms": t, "cells_per_s": cells / (t * 1e-3),
                                "algorithmic_GBs": gbs, "frac": gbs / peak}
+        # H from E (fields.get_magnetic_field): E read 48 + zeta 8 + H write 48 B/cell
+        d_h = _lib.DeviceArray(int(np.prod(grid.shape_cells)) * 3 + sum(
+            int(np.prod(grid.shape_cells)) // n for n in grid.shape_cells), sfield.field.dtype)
+        t = time_call(lambda: _lib.check(lib.emg3d_b200_magnetic_field(
+            level.handle.ptr, d_e.ptr, d_h.ptr, 0.0, -1.0)))
+        gbs = 104 * cells / (t * 1e-3) / 1e9
+        kernels['magnetic_field'] = {"ms": t, "cells_per_s": cells / (t * 1e-3),
+                                     "algorithmic_GBs": gbs, "frac": gbs / peak}
+        del d_h
 
     # --- end to end through the public API with host buffers ----------------------
     # Every timed step copies that step's inputs (source field and start field) from

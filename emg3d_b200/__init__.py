@@ -6,11 +6,11 @@ Python host code calling hand-written sm_100a CUDA kernels through a C ABI
 """
 from emg3d_b200._lib import Emg3dB200Error
 from emg3d_b200.meshes import BaseMesh, TensorMesh
-from emg3d_b200.fields import Field, get_source_field
+from emg3d_b200.fields import Field, get_source_field, get_magnetic_field
 from emg3d_b200.models import Model, VolumeModel
 from emg3d_b200 import core, solver
 from emg3d_b200.solver import solve, solve_source, Workspace, __version__
 
 __all__ = ['solve', 'solve_source', 'Model', 'VolumeModel', 'Field',
-           'get_source_field', 'TensorMesh', 'BaseMesh', 'core', 'solver', 'Workspace',
+           'get_source_field', 'get_magnetic_field', 'TensorMesh', 'BaseMesh', 'core', 'solver', 'Workspace',
            'Emg3dB200Error']

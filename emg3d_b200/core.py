@@ -21,7 +21,7 @@ from emg3d_b200 import _lib
 
 __all__ = ['amat_x', 'gauss_seidel', 'gauss_seidel_x', 'gauss_seidel_y',
            'gauss_seidel_z', 'blocks_to_amat', 'solve', 'restrict',
-           'restrict_weights']
+           'restrict_weights', 'edge_curl_factor']
 
 ORDER = os.environ.get('EMG3D_B200_ORDER', 'color')
 _ORDERS = {'lex': _lib.ORDER_LEX, 'color': _lib.ORDER_COLOR}
@@ -75,6 +75,24 @@ def amat_x(rx, ry, rz, ex, ey, ez, eta_x, eta_y, eta_z, zeta, hx, hy, hz):
     _lib.check(_lib.init().emg3d_b200_host_amat_x(
         int(dt.kind == 'c'), hx.size, hy.size, hz.size, _p(r[0]), _p(r[1]), _p(r[2]),
         _p(e[0]), _p(e[1]), _p(e[2]), _p(a), _p(b), _p(c), _p(zt), _p(hx), _p(hy), _p(hz)))
+
+
+def edge_curl_factor(mx, my, mz, ex, ey, ez, hx, hy, hz, zeta):
+    """Curl of an edge field on the faces, times a two-cell average of ``zeta`` over the
+    dual-cell measure, into ``mx, my, mz`` (emg3d.fields._edge_curl_factor,
+    fields.py:941-1009; not in ``emg3d.core`` but the same stencil family as amat_x).
+    Faces on the grid boundary are set to zero (the reference leaves them untouched
+    in a pre-zeroed field)."""
+    dt = np.dtype(ex.dtype)
+    if dt not in (np.dtype(np.complex128), np.dtype(np.float64)):
+        raise TypeError(f"fields must be complex128 or float64, got {dt}")
+    hx, hy, hz = (np.ascontiguousarray(h, dtype=np.float64) for h in (hx, hy, hz))
+    m = [_farr(v, dt, n, True) for v, n in ((mx, 'mx'), (my, 'my'), (mz, 'mz'))]
+    e = [_farr(v, dt, n) for v, n in ((ex, 'ex'), (ey, 'ey'), (ez, 'ez'))]
+    zt = _farr(zeta, dt, 'zeta')
+    _lib.check(_lib.init().emg3d_b200_host_edge_curl_factor(
+        int(dt.kind == 'c'), hx.size, hy.size, hz.size, _p(m[0]), _p(m[1]), _p(m[2]),
+        _p(e[0]), _p(e[1]), _p(e[2]), _p(hx), _p(hy), _p(hz), _p(zt)))
 
 
 def _gs(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy, hz, nu,

@@ -839,6 +839,62 @@ int emg3d_b200_host_amat_x(int is_cplx, int nx, int ny, int nz, void* rx, void* 
     return field_io(false, is_cplx, hc.lv->d, r.p, rx, ry, rz);
 }
 
+// H = zeta_avg / (s mu_0) * curl E / dual measure on the level's grid (device pointers);
+// scale = 1 / (s mu_0) as (re, im), im ignored for real (Laplace-domain) fields
+int emg3d_b200_magnetic_field(emg3d_b200_level* lv, const void* e, void* hfield, double scale_re,
+                              double scale_im) {
+    NEED_MODEL(lv);
+    if (lv->is_window) return fail_msg("magnetic_field: not defined on a z-window");
+    if (lv->cplx)
+        launch_edge_curl<cplx, double>(lv->d, (const cplx*)e, (cplx*)hfield, lv->h[0], lv->h[1], lv->h[2],
+                                       lv->zeta, make_c(scale_re, scale_im), g_stream);
+    else
+        launch_edge_curl<double, double>(lv->d, (const double*)e, (double*)hfield, lv->h[0], lv->h[1],
+                                         lv->h[2], lv->zeta, scale_re, g_stream);
+    CK_LAUNCH("edge_curl");
+    return 0;
+}
+
+int emg3d_b200_host_edge_curl_factor(int is_cplx, int nx, int ny, int nz, void* mx, void* my, void* mz,
+                                     const void* ex, const void* ey, const void* ez, const double* hx,
+                                     const double* hy, const double* hz, const void* zeta) {
+    NEED_INIT();
+    if (nx < 1 || ny < 1 || nz < 1) return fail_msg("host_edge_curl_factor: need at least 1 cell per axis");
+    Dims d = {};
+    d.n[0] = nx; d.n[1] = ny; d.n[2] = nz;
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    const size_t nc = (size_t)nx * ny * nz;
+    DevBuf e, hf, z, h[3];
+    const double* hh[3] = {hx, hy, hz};
+    int rc;
+    if (e.alloc((size_t)n_edges(d) * el) || hf.alloc((size_t)n_faces(d) * el) || z.alloc(nc * el))
+        return fail_msg("host_edge_curl_factor: out of device memory");
+    for (int a = 0; a < 3; ++a) {
+        if (h[a].alloc(sizeof(double) * d.n[a])) return fail_msg("host_edge_curl_factor: out of device memory");
+        if ((rc = emg3d_b200_h2d(h[a].p, hh[a], sizeof(double) * d.n[a]))) return rc;
+    }
+    if ((rc = field_io(true, is_cplx, d, e.p, (void*)ex, (void*)ey, (void*)ez))) return rc;
+    if ((rc = emg3d_b200_h2d(z.p, zeta, nc * el))) return rc;
+    if (is_cplx)
+        launch_edge_curl<cplx, cplx>(d, (const cplx*)e.p, (cplx*)hf.p, (const double*)h[0].p,
+                                     (const double*)h[1].p, (const double*)h[2].p, (const cplx*)z.p,
+                                     make_c(1.0, 0.0), g_stream);
+    else
+        launch_edge_curl<double, double>(d, (const double*)e.p, (double*)hf.p, (const double*)h[0].p,
+                                         (const double*)h[1].p, (const double*)h[2].p, (const double*)z.p,
+                                         1.0, g_stream);
+    CK_LAUNCH("edge_curl");
+    // faces: hx (nx+1, ny, nz), hy (nx, ny+1, nz), hz (nx, ny, nz+1)
+    const size_t nf[3] = {(size_t)(nx + 1) * ny * nz, (size_t)nx * (ny + 1) * nz, (size_t)nx * ny * (nz + 1)};
+    void* out[3] = {mx, my, mz};
+    size_t off = 0;
+    for (int c = 0; c < 3; ++c) {
+        if ((rc = emg3d_b200_d2h(out[c], (char*)hf.p + off * el, nf[c] * el))) return rc;
+        off += nf[c];
+    }
+    return 0;
+}
+
 int emg3d_b200_host_solve(int is_cplx, int n, void* amat, void* bvec) {
     NEED_INIT();
     if (n < 1) return fail_msg("host_solve: n must be positive");

@@ -61,6 +61,14 @@ void launch_volume_model(const Dims& d, const double* hx, const double* hy, cons
                          const double* px, const double* py, const double* pz, const double* mu,
                          const double* eps, T* ex, T* ey, T* ez, double* zeta, cudaStream_t st);
 
+// H on the faces from E on the edges: curl E times the two-cell average of a per-cell
+// factor (Z = double: zeta of the level, or Z = T: the caller's array) times `scale`,
+// divided by the dual-cell measure (fields._edge_curl_factor); hf is zeroed first
+int64_t n_faces(const Dims& d);
+template <typename T, typename Z>
+void launch_edge_curl(const Dims& d, const T* e, T* hf, const double* hx, const double* hy,
+                      const double* hz, const Z* zeta, T scale, cudaStream_t st);
+
 // vector helpers
 template <typename T>
 void launch_pec_zero(const Dims& d, T* e, cudaStream_t st);

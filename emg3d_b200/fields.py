@@ -30,12 +30,10 @@ class Field:
             dtype = np.asarray(data).dtype
         elif dtype is None:
             dtype = np.complex128
-        if not electric:
-            raise NotImplementedError("only electric (edge) fields are in scope")
         self.grid = grid
         self._frequency = frequency
-        self.electric = True
-        n = grid.n_edges
+        self.electric = bool(electric)     # False: magnetic field, living on the faces
+        n = grid.n_edges if self.electric else grid.n_faces
         if data is None:
             self._field = np.zeros(n, dtype=dtype)
         else:
@@ -45,17 +43,19 @@ class Field:
 
     def __repr__(self):
         g = self.grid
-        return (f"Field: electric; {g.shape_cells[0]} x {g.shape_cells[1]} x "
+        return (f"Field: {['magnetic', 'electric'][self.electric]}; "
+                f"{g.shape_cells[0]} x {g.shape_cells[1]} x "
                 f"{g.shape_cells[2]}; {self.field.size:,}")
 
     def __eq__(self, other):
         return (type(self).__name__ == type(other).__name__ and
                 self.grid == other.grid and
                 self._frequency == other._frequency and
+                self.electric == getattr(other, 'electric', True) and
                 np.allclose(self._field, other._field, atol=0, rtol=1e-10))
 
     def copy(self):
-        return Field(self.grid, self._field.copy(), self._frequency)
+        return Field(self.grid, self._field.copy(), self._frequency, electric=self.electric)
 
     @property
     def field(self):
@@ -67,8 +67,12 @@ class Field:
 
     def _view(self, comp):
         g = self.grid
-        n = (g.n_edges_x, g.n_edges_y, g.n_edges_z)
-        shp = (g.shape_edges_x, g.shape_edges_y, g.shape_edges_z)[comp]
+        if self.electric:
+            n = (g.n_edges_x, g.n_edges_y, g.n_edges_z)
+            shp = (g.shape_edges_x, g.shape_edges_y, g.shape_edges_z)[comp]
+        else:
+            n = (g.n_faces_x, g.n_faces_y, g.n_faces_z)
+            shp = (g.shape_faces_x, g.shape_faces_y, g.shape_faces_z)[comp]
         i0 = sum(n[:comp])
         return self._field[i0:i0 + n[comp]].reshape(shp, order='F')
 
@@ -204,3 +208,24 @@ def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
     if frequency is not None:
         sfield.field *= -sfield.smu0
     return sfield
+
+
+def get_magnetic_field(model, efield):
+    r"""Magnetic field on the faces from the electric field on the edges, by Faraday's
+    law :math:`\nabla \times \mathbf{E} = \rm{i}\omega\mu\mathbf{H}`
+    (emg3d.fields.get_magnetic_field, fields.py:617-659).
+
+    ``zeta = V / mu_r`` is built on the device from the model (models.VolumeModel),
+    the curl runs in one streaming kernel (csrc/hfield.cu); only the electric field
+    goes up and the magnetic field comes down.
+    """
+    from emg3d_b200 import _lib, solver
+    lv = solver._Level.from_model(model, efield)
+    d_e = _lib.DeviceArray.from_host(np.asarray(efield.field))
+    hfield = Field(efield.grid, frequency=efield._frequency, electric=False)
+    d_h = _lib.DeviceArray(hfield.field.size, hfield.field.dtype)
+    scale = 1.0 / complex(efield.smu0)
+    _lib.check(_lib.load().emg3d_b200_magnetic_field(lv.handle.ptr, d_e.ptr, d_h.ptr,
+                                                     scale.real, scale.imag))
+    d_h.download(out=hfield.field)
+    return hfield

@@ -213,6 +213,18 @@ int emg3d_b200_host_gauss_seidel(int cplx, int ldir, int order, int nx, int ny, 
                                  const double* hy, const double* hz, int nu);
 
 /* core.solve (core.py:1481-1482): amat has 6 n entries, bvec n; both in place. */
+/* Magnetic field on the faces from the electric field on the edges (Faraday's law):
+ * emg3d/fields.py:617-659 `get_magnetic_field` (device pointers; the level's model must
+ * be set; hfield holds (nx+1) ny nz + nx (ny+1) nz + nx ny (nz+1) values, laid out
+ * [hx | hy | hz], x fastest; scale = 1 / (s mu_0)) and the kernel it calls,
+ * fields.py:941-1009 `_edge_curl_factor(mx, my, mz, ex, ey, ez, hx, hy, hz, zeta)`,
+ * with that argument list on host arrays (`zeta` has the dtype of the fields). */
+int emg3d_b200_magnetic_field(emg3d_b200_level* lv, const void* e, void* hfield, double scale_re,
+                              double scale_im);
+int emg3d_b200_host_edge_curl_factor(int is_cplx, int nx, int ny, int nz, void* mx, void* my,
+                                     void* mz, const void* ex, const void* ey, const void* ez,
+                                     const double* hx, const double* hy, const double* hz,
+                                     const void* zeta);
 int emg3d_b200_host_solve(int cplx, int n, void* amat, void* bvec);
 
 #ifdef __cplusplus

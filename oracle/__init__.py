@@ -164,6 +164,24 @@ def prolong(ex, ey, ez, cex, cey, cez, nodes, cnodes, sc_dir):
        ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(nz), flags)
 
 
+def edge_curl_factor(mx, my, mz, ex, ey, ez, hx, hy, hz, zeta):
+    """NumPy restatement of emg3d/fields.py:941-1009 `_edge_curl_factor`: curl of the
+    edge field through every face that is not on the low boundary, times the sum of
+    ``zeta`` over the two cells sharing the face, over (sum of the two widths across
+    the face) x (face area); results into mx (nx+1, ny, nz), my, mz (other faces stay)."""
+    hx, hy, hz = _h(hx), _h(hy), _h(hz)
+    nx, ny, nz = hx.size, hy.size, hz.size
+    X, Y, Z = hx[:, None, None], hy[None, :, None], hz[None, None, :]
+    fx = (ez[:nx, 1:, :] - ez[:nx, :ny, :]) / Y - (ey[:nx, :, 1:] - ey[:nx, :, :nz]) / Z
+    fy = (ex[:, :ny, 1:] - ex[:, :ny, :nz]) / Z - (ez[1:, :ny, :] - ez[:nx, :ny, :]) / X
+    fz = (ey[1:, :, :nz] - ey[:nx, :, :nz]) / X - (ex[:, 1:, :nz] - ex[:, :ny, :nz]) / Y
+    z = np.asarray(zeta)
+    mx[1:nx] = (fx[1:] * (z[:-1] + z[1:]) / ((hx[:-1] + hx[1:])[:, None, None] * Y * Z))
+    my[:, 1:ny] = (fy[:, 1:] * (z[:, :-1] + z[:, 1:]) / (X * (hy[:-1] + hy[1:])[None, :, None] * Z))
+    mz[:, :, 1:nz] = (fz[:, :, 1:] * (z[:, :, :-1] + z[:, :, 1:])
+                      / (X * Y * (hz[:-1] + hz[1:])[None, None, :]))
+
+
 def gs_sequence(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy, hz, seq):
     """Relax the blocks listed in ``seq`` one after the other (test helper).
 

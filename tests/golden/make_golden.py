@@ -15,6 +15,8 @@ not on the hot path); ``_refstubs/`` provides two-line stand-ins.  Outputs:
                   (tests/data/regression.npz: res, reg_2, lap) re-exported as bare
                   arrays, plus small siblings of the five BASELINE.json configs
     host.npz      VolumeModel and source-field vectors (host-side inputs)
+    hfield.npz    get_magnetic_field / _edge_curl_factor (the first "next" row of
+                  SURVEY.md 8f that shares the stencil family of amat_x)
 
 The fixtures travel to the GPU box; the reference does not.
 """
@@ -267,11 +269,50 @@ def make_host():
     np.savez_compressed(os.path.join(HERE, 'host.npz'), **out)
 
 
+def make_hfield():
+    """get_magnetic_field / _edge_curl_factor (emg3d/fields.py:617-659, 941-1009)."""
+    from emg3d import fields
+    rng = np.random.default_rng(4)
+    out = {}
+    cases = [((6, 4, 8), True), ((5, 3, 2), False), ((2, 2, 2), True), ((9, 7, 5), True)]
+    for k, (shape, cplx) in enumerate(cases):
+        nx, ny, nz = shape
+        hx = 50 * 1.1 ** rng.uniform(-3, 3, nx)
+        hy = 60 * 1.2 ** rng.uniform(-3, 3, ny)
+        hz = 40 * 1.15 ** rng.uniform(-3, 3, nz)
+        g = emg3d.TensorMesh([hx, hy, hz], (-hx.sum() / 2, -hy.sum() / 2, -hz.sum() / 2))
+        rx = 10 ** rng.uniform(-0.5, 1.5, g.shape_cells)
+        m = emg3d.Model(g, rx, 1.5 * rx, 3 * rx, mu_r=rng.uniform(1, 2, g.shape_cells))
+        freq = 1.3 if cplx else -1.3
+        ef = emg3d.Field(g, frequency=freq)
+        n = ef.field.size
+        ef.field[:] = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+        hf = fields.get_magnetic_field(m, ef)
+        p = f"h{k}_"
+        out[p + 'hx'], out[p + 'hy'], out[p + 'hz'] = g.h
+        out[p + 'origin'] = np.asarray(g.origin, dtype=float)
+        out[p + 'property_x'], out[p + 'property_y'], out[p + 'property_z'] = (
+            m.property_x, m.property_y, m.property_z)
+        out[p + 'mu_r'] = m.mu_r
+        out[p + 'frequency'] = freq
+        out[p + 'e'] = np.asarray(ef.field)
+        out[p + 'h'] = np.asarray(hf.field)
+        # the kernel alone, with an arbitrary (complex / real) factor array
+        zeta = rng.uniform(1, 2, g.shape_cells) * ((1 + 0.5j) if cplx else 1.0)
+        zeta = np.asfortranarray(zeta)
+        hk = emg3d.Field(g, frequency=freq, electric=False)
+        fields._edge_curl_factor(hk.fx, hk.fy, hk.fz, ef.fx, ef.fy, ef.fz, *g.h, zeta)
+        out[p + 'zeta_k'] = zeta
+        out[p + 'h_k'] = np.asarray(hk.field)
+    out['n_cases'] = len(cases)
+    np.savez_compressed(os.path.join(HERE, 'hfield.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host']
+    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield']
     for w in which:
         globals()['make_' + w]()
-    for f in ('kernels', 'transfer', 'solves', 'host'):
+    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield'):
         fn = os.path.join(HERE, f + '.npz')
         if os.path.exists(fn):
             print(f, os.path.getsize(fn) // 1024, 'KiB')

@@ -46,3 +46,25 @@ def solve_case(gs, prefix):
     d['stdout'] = str(gs[prefix + 'stdout'])
     d['source'] = gs[prefix + 'source'] if prefix + 'source' in gs.files else None
     return d
+
+
+def split_faces(shape, f):
+    """Views (hx, hy, hz) of a 1-D magnetic (face) field for cell shape (nx, ny, nz)."""
+    nx, ny, nz = shape
+    shp = ((nx + 1, ny, nz), (nx, ny + 1, nz), (nx, ny, nz + 1))
+    out, i0 = [], 0
+    for s in shp:
+        n = int(np.prod(s))
+        out.append(f[i0:i0 + n].reshape(s, order='F'))
+        i0 += n
+    return out
+
+
+def hfield_case(gh, k):
+    """Inputs / outputs of magnetic-field golden case k."""
+    p = f"h{k}_"
+    d = {n: gh[p + n] for n in ('hx', 'hy', 'hz', 'origin', 'property_x', 'property_y',
+                                'property_z', 'mu_r', 'e', 'h', 'zeta_k', 'h_k')}
+    d['frequency'] = float(gh[p + 'frequency'])
+    d['shape'] = (d['hx'].size, d['hy'].size, d['hz'].size)
+    return d

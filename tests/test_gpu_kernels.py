@@ -18,7 +18,7 @@ import pytest
 import oracle
 from oracle import mg
 from conftest import rel_err
-from helpers import kernel_case, split_field
+from helpers import hfield_case, kernel_case, split_faces, split_field
 
 pytestmark = pytest.mark.gpu
 
@@ -487,3 +487,35 @@ def test_peer_memory_api_needs_a_communicator():
     st = ctypes.c_int(5)
     _lib.check(lib.emg3d_b200_p2p_status(ctypes.byref(st)))
     assert st.value == 0
+
+
+def test_magnetic_field_golden(core, golden):
+    """core.edge_curl_factor (host-array twin of fields._edge_curl_factor) and
+    get_magnetic_field (device VolumeModel + curl kernel) against the reference's
+    outputs, <= 1e-13; and against the oracle on a larger random grid."""
+    import emg3d_b200 as eb
+    gh = golden('hfield')
+    for k in range(int(gh['n_cases'])):
+        c = hfield_case(gh, k)
+        shape = c['shape']
+        h = np.full_like(c['h_k'], 7.0)                     # boundary faces must come back zero
+        core.edge_curl_factor(*split_faces(shape, h), *split_field(shape, c['e']),
+                              c['hx'], c['hy'], c['hz'], c['zeta_k'])
+        assert rel_err(h, c['h_k']) < 1e-13
+        grid = eb.TensorMesh([c['hx'], c['hy'], c['hz']], c['origin'])
+        model = eb.Model(grid, c['property_x'], c['property_y'], c['property_z'], mu_r=c['mu_r'])
+        ef = eb.Field(grid, c['e'], frequency=c['frequency'])
+        hf = eb.get_magnetic_field(model, ef)
+        assert not hf.electric and hf.fx.shape == (shape[0] + 1, shape[1], shape[2])
+        assert rel_err(hf.field, c['h']) < 1e-13
+    rng = np.random.default_rng(11)
+    shape = (37, 20, 45)
+    c = random_case(rng, shape, True)
+    zeta = np.asfortranarray(c['zeta'] * (0.3 - 2j))
+    n_faces = sum(int(np.prod(s)) for s in ((38, 20, 45), (37, 21, 45), (37, 20, 46)))
+    h_gpu, h_cpu = np.zeros(n_faces, complex), np.zeros(n_faces, complex)
+    core.edge_curl_factor(*split_faces(shape, h_gpu), *split_field(shape, c['e']),
+                          c['hx'], c['hy'], c['hz'], zeta)
+    oracle.edge_curl_factor(*split_faces(shape, h_cpu), *split_field(shape, c['e']),
+                            c['hx'], c['hy'], c['hz'], zeta)
+    assert rel_err(h_gpu, h_cpu) < 1e-13

@@ -139,6 +139,10 @@ def test_field_container():
     assert abs(f.sval - 2j * np.pi * 2.0) == 0 and eb.Field(grid, frequency=-2.0).sval == 2.0
     with pytest.raises(ValueError, match='`frequency` must be'):
         eb.Field(grid, frequency=0.0)
+    h = eb.Field(grid, frequency=2.0, electric=False)              # magnetic: on the faces
+    assert h.field.size == grid.n_faces == 4 * 4 * 5 + 3 * 5 * 5 + 3 * 4 * 6
+    assert h.fx.shape == (4, 4, 5) and h.fy.shape == (3, 5, 5) and h.fz.shape == (3, 4, 6)
+    assert 'magnetic' in repr(h) and not h.copy().electric and h != f
     g = f.copy()
     assert g == f
     g.field[0] = 1

@@ -11,7 +11,7 @@ import pytest
 import oracle
 from oracle import mg
 from conftest import rel_err
-from helpers import kernel_case, solve_case, split_field
+from helpers import hfield_case, kernel_case, solve_case, split_faces, split_field
 
 KTOL = 1e-12
 
@@ -150,3 +150,25 @@ def test_solves(golden, prefix):
         # the reference's own regression data (tests/data/regression.npz)
         np.testing.assert_allclose(e, golden('solves')[prefix + 'regression'],
                                    rtol=1e-6, atol=1e-14 * np.abs(c['efield']).max() + 1e-30)
+
+
+def test_edge_curl_factor_and_magnetic_field(golden):
+    """fields._edge_curl_factor and get_magnetic_field (fields.py:617-659, 941-1009)."""
+    gh = golden('hfield')
+    for k in range(int(gh['n_cases'])):
+        c = hfield_case(gh, k)
+        shape = c['shape']
+        h = np.zeros_like(c['h_k'])
+        oracle.edge_curl_factor(*split_faces(shape, h), *split_field(shape, c['e']),
+                                c['hx'], c['hy'], c['hz'], c['zeta_k'])
+        assert rel_err(h, c['h_k']) < 1e-14
+        # the caller: zeta = V / mu_r divided by s mu_0
+        g = mg.Grid([c['hx'], c['hy'], c['hz']])
+        vm = mg.VolumeModel(g, c['property_x'], c['property_y'], c['property_z'], c['mu_r'], None,
+                            c['frequency'])
+        f = c['frequency']
+        smu0 = (-f if f < 0 else 2j * np.pi * f) * mg.MU_0
+        h = np.zeros_like(c['h'])
+        oracle.edge_curl_factor(*split_faces(shape, h), *split_field(shape, c['e']),
+                                c['hx'], c['hy'], c['hz'], vm.zeta / smu0)
+        assert rel_err(h, c['h']) < 1e-14
