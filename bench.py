@@ -114,6 +114,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def recorded_traffic(kernel_prefix):
+    """DRAM bytes per launch (read + write) of a kernel from the committed ncu capture
+    (profiles/r1_ncu_stalls.csv, `ncu --set full`, 256^3 workload); None if absent.
+    bench.py never runs under a profiler, so this is a recorded, not a live, number."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_stalls.csv')
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    try:
+        rows = [ln.rstrip('\n').split(',') for ln in open(path) if not ln.startswith('#')]
+        col = next(i for i, name in enumerate(rows[0]) if name.startswith(kernel_prefix))
+        total = 0.0
+        for want in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            val, u = next(r[col] for r in rows if r[0] == want).split()
+            total += float(val) * unit[u]
+        return total
+    except (OSError, StopIteration, ValueError, KeyError, IndexError):
+        return None
+
+
 def build_inputs(n):
     import emg3d_b200 as eb
     from emg3d_b200 import recipes
@@ -300,9 +318,12 @@ def main():
     peak, peak_src = peaks()
     bytes_per_launch = bytes_per_cell_sweep * cells * 2 * reps / klaunch
     achieved = bytes_per_launch / (kms * 1e-3 / klaunch) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gs_point_color_kernel (finest grid)",
+    roofline = {"bound": "hbm", "kernel": "gs_point_tile_kernel (finest grid, one tile-colour launch)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                "traffic": recorded_traffic('gs_point_tile_kernel') if n == 256 else None,
+                "traffic_source": "profiles/r1_ncu_stalls.csv (ncu --set full, same workload); "
+                                  "algorithmic bytes per launch: %d" % int(bytes_per_launch),
                 "bytes_per_cell_sweep": bytes_per_cell_sweep,
                 "launch_ms": kms / klaunch,
                 "cell_sweeps_per_s": cells * 2 * reps / (kms * 1e-3)}
