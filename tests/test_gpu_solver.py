@@ -225,6 +225,43 @@ def test_full_size_properties(eb):
         assert err[2] < 0.2 * err[1] < 0.2 * err[0]
 
 
+def test_smoothers_keep_the_exact_solution_at_256_cubed(eb):
+    """Size-independent exactness check at the bench size (256^3, 16.8 M cells; the
+    tile-fused point smoother, the colour line kernels with cached factorisations and
+    the plane-streaming residual are the code paths of that size): with s := A e every
+    Gauss-Seidel block solve must return the values it found, so a sweep of any
+    smoother leaves e unchanged, and the residual of (s, e) vanishes."""
+    from emg3d_b200 import _lib, recipes, solver
+    cfg = recipes.config('config2', 256)                   # stretched grid, triaxial
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    probe = eb.Field(grid, frequency=cfg['frequency'])
+    lv = solver._Level.from_model(model, probe)
+    rng = np.random.default_rng(5)
+    n = grid.n_edges
+    probe.field[:] = rng.standard_normal(n)
+    probe.field[:] += 1j * rng.standard_normal(n)
+    f = probe
+    f.fx[:, 0, :] = f.fx[:, -1, :] = f.fx[:, :, 0] = f.fx[:, :, -1] = 0
+    f.fy[0, :, :] = f.fy[-1, :, :] = f.fy[:, :, 0] = f.fy[:, :, -1] = 0
+    f.fz[0, :, :] = f.fz[-1, :, :] = f.fz[:, 0, :] = f.fz[:, -1, :] = 0
+    lib = _lib.load()
+    d_e0 = _lib.DeviceArray.from_host(f.field)
+    d_s = lv.new_field()
+    _lib.check(lib.emg3d_b200_apply(lv.handle.ptr, d_e0.ptr, d_s.ptr))          # s = A e
+    vec = solver._Vec(lv.cplx, n)
+    norm_e = vec.norm(d_e0)
+    assert solver._dev_residual(lv, d_s, d_e0, norm=True) < 1e-12 * vec.norm(d_s)
+    for ldir in (0, 1, 2, 3):
+        d_e = d_e0.copy()
+        _lib.check(lib.emg3d_b200_gauss_seidel(lv.handle.ptr, d_e.ptr, d_s.ptr, 2, ldir,
+                                               _lib.ORDER_COLOR))
+        vec.axpby(-1.0, d_e0, 1.0, d_e)                                          # e_new - e
+        assert vec.norm(d_e) < 1e-10 * norm_e, ldir
+        lv.handle.drop_factors()
+        d_e.free()
+
+
 @pytest.mark.parametrize('cycle,kw', [('W', dict(plain=True)), ('F', dict(sslsolver=False)),
                                       ('V', dict())])
 def test_cuda_graph_replay_equals_eager(cycle, kw):
