@@ -29,7 +29,13 @@ class _Map:
         if name not in self._fwd:
             raise ValueError(f"Unknown mapping: {name!r}")
         self.name = name
-        self.forward, self.backward = self._fwd[name]
+
+    # looked up by name, so that a Model can be pickled (batch.solve_many)
+    def forward(self, conductivity):
+        return self._fwd[self.name][0](conductivity)
+
+    def backward(self, mapped):
+        return self._fwd[self.name][1](mapped)
 
 
 class Model:

@@ -285,3 +285,19 @@ def test_cuda_graph_replay_equals_eager(cycle, kw):
     assert np.array_equal(out[False][0], out[True][0])
     assert out[False][1]['it_mg'] == out[True][1]['it_mg']
     assert out[False][1]['abs_error'] == out[True][1]['abs_error']
+
+
+def test_solve_many_equals_single_solves(eb, golden):
+    """batch.solve_many (one worker process per GPU, model resident in the worker's
+    Workspace) returns what solve() returns for each source."""
+    from emg3d_b200 import recipes
+    cfg = recipes.config('config2', 32)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    srcs = [eb.get_source_field(grid, (x, 0., -950., 0., 0.), cfg['frequency']) for x in (0., 150.)]
+    kw = dict(sslsolver=False, cycle='F', tol=1e-8, return_info=True)
+    many = eb.solve_many(model, srcs, devices=[0], **kw)
+    for s, (e_m, info_m) in zip(srcs, many):
+        e_1, info_1 = eb.solve(model, s, **kw)
+        assert info_m['it_mg'] == info_1['it_mg'] and info_m['exit_message'] == 'CONVERGED'
+        assert np.array_equal(e_m.field, e_1.field)

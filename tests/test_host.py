@@ -339,3 +339,14 @@ def test_bench_work_count():
     assert bench.vcycle_work((128, 128, 128)) == 9586952
     assert bench.vcycle_work((32, 32, 32)) == 149768
     assert bench.vcycle_work((512, 512, 512)) == 613566728
+
+
+def test_process_map_binds_one_device_per_worker():
+    """batch.process_map: the reference's process-pool fan-out (_multiprocessing.py:33-65)
+    with every worker bound to one GPU before its first task; order of results kept."""
+    from emg3d_b200 import batch
+    out = batch.process_map(batch._echo_device, list(range(6)), devices=[3, 5], payload='p')
+    assert [x for x, _, _ in out] == list(range(6))
+    assert {d for _, d, _ in out} <= {3, 5} and all(str(d) == env for _, d, env in out)
+    with pytest.raises(ValueError, match='at least one GPU'):
+        batch.process_map(batch._echo_device, [1], devices=[])
