@@ -623,7 +623,8 @@ __device__ __forceinline__ void march_column(const Model<T>& m, const FieldView<
 #ifndef EMG_MARCH_MINB
 #define EMG_MARCH_MINB 8
 #endif
-static_assert((TX / 2) * (TZ / 2) == 32, "the marching kernel maps one tile to one warp");
+static_assert(!EMG_PT_MARCH || (TX / 2) * (TZ / 2) == 32,
+              "the marching kernel maps one tile to one warp");
 
 template <typename T>
 __global__ void __launch_bounds__(32, EMG_MARCH_MINB)
