@@ -528,6 +528,7 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
     # halo-exchange cost on the finest level (one exchange of E), for the record
     for _ in range(2):
         dmg.exchange(dl, dmg.e)
+    barrier()          # ranks arrive here at different times; an exchange waits for the neighbours
     x0, x1 = _lib.Event(), _lib.Event()
     x0.record()
     for _ in range(10):
