@@ -3,23 +3,35 @@
 // all edges touching the interior nodes of one grid line, plus the line's own
 // edges, are solved for simultaneously.
 //
-// Unknown order per line, as in the reference (core.py:775-783, 1060-1068,
-// 1340-1348): block i = [ L_i, T_{i+1} ],  L_i = line edge between nodes i and
-// i+1, T_m = the four transverse edges at interior node m in slot order
-// [p-, p+, q-, q+], (p, q) = (y,z) / (x,z) / (x,y) for x- / y- / z-lines; the
-// last block holds L_{N-1} only.  The matrix is block tridiagonal,
-//     S_0 = M_0,  S_i = M_i - F_i (S_{i-1}^{-1}) F_i^T,
-// with a *real* sparse coupling F_i: row 0 = (0, f_0..f_3), rows 1..4 =
-// diag(d_0..d_3).  Only the trailing 4x4 block of S_{i-1}^{-1} enters.
+// Unknowns of a line of N cells: the line edges L_i (cell i, between nodes i and
+// i+1), i = 0 .. N-1, and the four transverse edges T_m = [p-, p+, q-, q+] at the
+// interior nodes m = 1 .. N-1, (p, q) = (y,z) / (x,z) / (x,y) for x- / y- / z-lines;
+// T_0 and T_N lie on the line's end planes and are fixed data (zero on a PEC
+// boundary, halo values on a multi-GPU z-window).  The reference orders them in
+// 5-unknown blocks [L_i, T_{i+1}] (core.py:775-783) and factorises a banded matrix
+// per line and sweep.  Here the line edges are eliminated first: L_i couples only to
+// T_i and T_{i+1}, with  c_i = -f_i,
+//     L_i = (bL_i - f_i . (T_i - T_{i+1})) / dL_i ,
+// which leaves a block-tridiagonal system of 4x4 blocks for the T_m alone,
+//     E_m T_{m-1} + D_m T_m + E_{m+1} T_{m+1} = r_m ,
+//     D_m = C_m - f_{m-1} f_{m-1}^T / dL_{m-1} - f_m f_m^T / dL_m ,
+//     E_m = diag(d_{m-1}) + f_{m-1} f_{m-1}^T / dL_{m-1}      (symmetric; d, f real),
+//     r_m = bT_m + f_{m-1} bL_{m-1} / dL_{m-1} - f_m bL_m / dL_m ,
+// solved by block elimination:  S_1 = D_1,  S_m = D_m - E_m S_{m-1}^{-1} E_m.
+// Same equations, same solution (to rounding) as the reference's block solve.
 //
 // B200 design: the matrix depends on (grid, model, s) only, not
-// on E, so the block factors L_i D_i L_i^T of S_i (15 numbers per block) are
-// computed ONCE per level and direction (`line_factor`) and streamed from HBM
-// by every sweep; the reference refactors every line in every sweep
-// (core.py:769-772).  A sweep is then one forward and one backward block
-// substitution per line, one thread per line, with the intermediate vector
-// stored in place in E.  Factor layout [block][entry][line] makes the factor
-// stream perfectly coalesced across the threads of a warp.
+// on E, so the LDL^T factors of S_m (10 numbers) and 1/dL (1 number) are computed
+// ONCE per level and direction (`line_factor`) and streamed from HBM by every
+// sweep -- 11 numbers per cell instead of the 15 of a 5x5 block LDL^T, and E_m is
+// rebuilt from zeta and the widths on the fly (the kernels are bound by the bytes
+// they move, with the fp64 pipe below 10 %).  A sweep is one forward pass
+//     g_m = S_m^{-1} (r_m - E_m g_{m-1}),  g_0 = T_0,
+// and one backward pass
+//     T_m = g_m - S_m^{-1} E_{m+1} T_{m+1},   L_m = (bL_m - f_m . (T_m - T_{m+1})) / dL_m,
+// one thread per line, g_m and bL_i stored in place in E between the passes.
+// Factor layout [group of 32 lines][block][entry][lane] makes the factor stream one
+// contiguous chunk per warp and block.
 //
 // Orderings: `lex` runs hyperplanes t = tp + 2 tq of the reference's line
 // order (p fastest, then q; core.py:601-624, 886-917, 1166-1197) and is
@@ -29,8 +41,6 @@
 #include "kernels.h"
 
 namespace emg {
-
-constexpr int LINE_STAGES = 4;   // factor blocks in flight per line (cp.async ring)
 
 template <int D> struct Ax {
     static constexpr int d = D;
@@ -42,11 +52,12 @@ template <int D> struct Ax {
 // classes one after the other, each padded to a multiple of 32 lines, and
 // within a class p fastest.  A warp of the colour kernel therefore owns one
 // aligned group of 32 consecutive slots, and the factors are stored
-//     [group][block i][entry e][lane]          (32 lanes, 15 entries, N blocks)
-// so that a warp reads ONE contiguous 15*32*sizeof(T) chunk per block and walks
-// through HBM sequentially from block to block.
+//     [group][block i][entry e][lane]          (32 lanes, 11 entries, N blocks)
+// block i < N-1: entries 0..9 = LDL^T factors of S_{i+1} (6 entries of L, 4 of 1/D),
+// entry 10 = 1/dL_{i+1}; block N-1: entry 0 = 1/dL_0.
+constexpr int FAC_NE = 11;          // entries per block
 constexpr int FAC_ES = 32;          // stride between entries of one block
-constexpr int FAC_BS = 15 * 32;     // stride between blocks of one line
+constexpr int FAC_BS = FAC_NE * 32; // stride between blocks of one line
 
 struct LineSlots {
     int na[2], nb[2], off[4], cnt[4];
@@ -117,30 +128,130 @@ struct Line {
     __device__ __forceinline__ double al_q(int jp) const { return jp == 0 ? rp[0] : -rp[1]; }
 };
 
-// 5x5 symmetric block stored as s[r][c], r >= c.
-// In-place LDL^T: s[r][c] (r>c) <- L(r,c), dinv[r] <- 1/D(r).
+// ---- small dense helpers (everything unrolled, registers only) -----------------
+// symmetric 4x4 in packed lower-triangular storage: (r, c), r >= c, at r (r+1)/2 + c
+__device__ __forceinline__ constexpr int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+// LDL^T without pivoting of a complex-symmetric (not Hermitian) 4x4 (the pivots are
+// those of the reference's banded LDL^T of the same system).  In: x packed lower
+// triangle.  Out: f[0..5] = strict lower part of L row-wise ((1,0) (2,0) (2,1) (3,0)
+// (3,1) (3,2)), f[6..9] = 1 / D; and x <- x^{-1} (needed by the block recurrence only).
 template <typename T>
-__device__ __forceinline__ void ldlt5(T s[5][5], T dinv[5]) {
+__device__ __forceinline__ void ldlt4_and_inverse(T x[10], T f[10]) {
+    T l[4][4], dinv[4];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        T v[5];
-        T dj = s[j][j];
+    for (int j = 0; j < 4; ++j) {
+        T v[4];
+        T dj = x[tri(j, j)];
 #pragma unroll
-        for (int k = 0; k < j; ++k) {
-            v[k] = s[j][k] * s[k][k];
-            dj -= s[j][k] * v[k];
-        }
-        s[j][j] = dj;
-        const T r = rcp(dj);
-        dinv[j] = r;
+        for (int k = 0; k < 4; ++k)
+            if (k < j) {
+                v[k] = l[j][k] * x[tri(k, k)];      // L(j,k) D(k); x(k,k) holds D(k)
+                dj -= l[j][k] * v[k];
+            }
+        x[tri(j, j)] = dj;
+        dinv[j] = rcp(dj);
 #pragma unroll
-        for (int i = j + 1; i < 5; ++i) {
-            T t = s[i][j];
+        for (int i = 0; i < 4; ++i)
+            if (i > j) {
+                T t = x[tri(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) t -= s[i][k] * v[k];
-            s[i][j] = t * r;
-        }
+                for (int k = 0; k < 4; ++k)
+                    if (k < j) t -= l[i][k] * v[k];
+                l[i][j] = t * dinv[j];
+            }
     }
+    f[0] = l[1][0]; f[1] = l[2][0]; f[2] = l[2][1]; f[3] = l[3][0]; f[4] = l[3][1]; f[5] = l[3][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[6 + j] = dinv[j];
+    // inverse of the unit lower factor (strict lower part)
+    T li[4][4];
+    li[1][0] = -l[1][0];
+    li[2][1] = -l[2][1];
+    li[3][2] = -l[3][2];
+    li[2][0] = -l[2][0] - l[2][1] * li[1][0];
+    li[3][1] = -l[3][1] - l[3][2] * li[2][1];
+    li[3][0] = -l[3][0] - l[3][1] * li[1][0] - l[3][2] * li[2][0];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+            // sum_{k >= r} li[k][r] dinv[k] li[k][c], li[k][k] = 1
+            T t = (r == c) ? dinv[r] : dinv[r] * li[r][c];
+#pragma unroll
+            for (int k = r + 1; k < 4; ++k) t += li[k][r] * dinv[k] * li[k][c];
+            x[tri(r, c)] = t;
+        }
+}
+
+// y <- S^{-1} y with the factors of ldlt4_and_inverse
+template <typename T>
+__device__ __forceinline__ void solve4(const T f[10], T y[4]) {
+    y[1] -= f[0] * y[0];
+    y[2] -= f[1] * y[0] + f[2] * y[1];
+    y[3] -= f[3] * y[0] + f[4] * y[1] + f[5] * y[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = y[j] * f[6 + j];
+    y[2] -= f[5] * y[3];
+    y[1] -= f[2] * y[2] + f[4] * y[3];
+    y[0] -= f[0] * y[1] + f[1] * y[2] + f[3] * y[3];
+}
+
+template <typename T>
+__device__ __forceinline__ void symv4(const T x[10], const T v[4], T out[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        T t = x[tri(r, 0)] * v[0];
+#pragma unroll
+        for (int c = 1; c < 4; ++c) t += x[tri(r, c)] * v[c];
+        out[r] = t;
+    }
+}
+
+// E v with E = diag(d) + rl f f^T  (d, f real; rl = 1/dL complex)
+template <typename T>
+__device__ __forceinline__ void apply_E(const double d[4], const double f[4], T rl, const T v[4], T out[4]) {
+    T fv = f[0] * v[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) fv += f[k] * v[k];
+    const T a = rl * fv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = d[k] * v[k] + f[k] * a;
+}
+
+// geometry of one line cell: couplings of its line edge
+struct CellCoef {
+    double f[4];      // L <-> T at the cell's lower node (upper node: -f)
+    double d[4];      // T(lower node) <-> T(upper node) through the cell's side faces
+    double gaa[4];    // gs * a_side^2: L <-> outer parallel line edges (and part of dL)
+    double gra[4];    // gs * rd * a_side: T <-> outer parallel line edges
+    double grr[4];    // gs * rd^2: contribution to the transverse diagonals
+};
+template <typename T, int D>
+__device__ __forceinline__ void cell_coef(const Line<T, D>& ln, const double gs[4], double rd, CellCoef& c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double as = ln.a_side(k);
+        c.gaa[k] = gs[k] * as * as;
+        c.gra[k] = gs[k] * rd * as;
+        c.grr[k] = gs[k] * rd * rd;
+        c.f[k] = -c.gra[k];
+        c.d[k] = -c.grr[k];
+    }
+}
+
+// diagonal entry of the line edge of line cell i
+template <typename T, int D>
+__device__ __forceinline__ T line_diag(const Line<T, D>& ln, int i, const CellCoef& c) {
+    using A = Ax<D>;
+    T st = zero_<T>();
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+        for (int jq = 0; jq < 2; ++jq) st += ldg(ln.m.eta[A::d] + ln.cbase[jp][jq] + ln.cstr * i);
+    T dl = -0.25 * st;
+    add_real(dl, c.gaa[0] + c.gaa[1] + c.gaa[2] + c.gaa[3]);
+    return dl;
 }
 
 // ---- factorisation: one thread per line ------------------------------------
@@ -152,142 +263,93 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
     const int N = ln.N;
     T* const fbase = fac + ls.base(ls.slot(tp, tq), N);
 
-    double zc[2][2], zn[2][2];
+    double zc[2][2], zn[2][2], gs[4];
     ln.load_zeta(0, zc);
-    T X[4][4];                       // trailing 4x4 of S_{i-1}^{-1} (lower part used)
+    ln.side_g(zc, gs);
+    CellCoef cc, cn;
+    cell_coef<T, D>(ln, gs, ldg(m.rh[A::d]), cc);
+    T rl_c = rcp(line_diag<T, D>(ln, 0, cc));
+    fbase[(int64_t)(N - 1) * FAC_BS] = rl_c;                 // 1 / dL_0
     // eta sums carried from the previous line cell for the transverse diagonals
     T etp_c[2], etq_c[2];            // sum over jq (resp. jp) of eta_p / eta_q at line cell i
-    {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        etp_c[j] = ldg(m.eta[A::p] + ln.cbase[j][0]) + ldg(m.eta[A::p] + ln.cbase[j][1]);
+        etq_c[j] = ldg(m.eta[A::q] + ln.cbase[0][j]) + ldg(m.eta[A::q] + ln.cbase[1][j]);
+    }
+    T X[10];                         // X_{m-1}
+    for (int i = 0; i < N - 1; ++i) {                        // node m = i + 1
+        ln.load_zeta(i + 1, zn);
+        double gn[4];
+        ln.side_g(zn, gn);
+        cell_coef<T, D>(ln, gn, ldg(m.rh[A::d] + i + 1), cn);
+        const T rl_n = rcp(line_diag<T, D>(ln, i + 1, cn));
+        T etp_n[2], etq_n[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            etp_c[j] = ldg(m.eta[A::p] + ln.cbase[j][0]) + ldg(m.eta[A::p] + ln.cbase[j][1]);
-            etq_c[j] = ldg(m.eta[A::q] + ln.cbase[0][j]) + ldg(m.eta[A::q] + ln.cbase[1][j]);
+            const int64_t o = ln.cstr * (i + 1);
+            etp_n[j] = ldg(m.eta[A::p] + ln.cbase[j][0] + o) + ldg(m.eta[A::p] + ln.cbase[j][1] + o);
+            etq_n[j] = ldg(m.eta[A::q] + ln.cbase[0][j] + o) + ldg(m.eta[A::q] + ln.cbase[1][j] + o);
         }
-    }
-    for (int i = 0; i < N; ++i) {
-        const double rd = ldg(m.rh[A::d] + i);
-        double gs[4];
-        ln.side_g(zc, gs);
-        T S[5][5];
-        // line edge diagonal
-        {
-            T st = zero_<T>();
+        // C_m: transverse block at node m (eta, side faces of both cells, end faces)
+        T S[10];
 #pragma unroll
-            for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                for (int jq = 0; jq < 2; ++jq)
-                    st += ldg(m.eta[A::d] + ln.cbase[jp][jq] + ln.cstr * i);
-            S[0][0] = -0.25 * st;
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc += gs[k] * ln.a_side(k) * ln.a_side(k);
-            add_real(S[0][0], acc);
-        }
-        double f[4], dk[4];
+        for (int e = 0; e < 10; ++e) S[e] = zero_<T>();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double c = gs[k] * ln.a_side(k) * rd;
-            f[k] = -c;                   // L_i <-> T_{i,k}
-            dk[k] = -gs[k] * rd * rd;    // T_{i+1,k} <-> T_{i,k}
-            S[1 + k][0] = zero_<T>();
-            add_real(S[1 + k][0], c);    // L_i <-> T_{i+1,k}
+            const T et = k < 2 ? etp_c[k] + etp_n[k] : etq_c[k - 2] + etq_n[k - 2];
+            S[tri(k, k)] = -0.25 * et;
+            add_real(S[tri(k, k)], cc.grr[k] + cn.grr[k]);
         }
-        const bool last = (i == N - 1);
-        if (!last) {
-            ln.load_zeta(i + 1, zn);
-            const double rdn = ldg(m.rh[A::d] + i + 1);
-            double gn[4];
-            ln.side_g(zn, gn);
-            T etp_n[2], etq_n[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t o = ln.cstr * (i + 1);
-                etp_n[j] = ldg(m.eta[A::p] + ln.cbase[j][0] + o) + ldg(m.eta[A::p] + ln.cbase[j][1] + o);
-                etq_n[j] = ldg(m.eta[A::q] + ln.cbase[0][j] + o) + ldg(m.eta[A::q] + ln.cbase[1][j] + o);
+        for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) {
+                const double g = 0.5 * (zc[jp][jq] + zn[jp][jq]);
+                const double ap = ln.al_p(jq), aq = ln.al_q(jp);
+                add_real(S[tri(jp, jp)], g * ap * ap);
+                add_real(S[tri(2 + jq, 2 + jq)], g * aq * aq);
+                add_real(S[tri(2 + jq, jp)], g * ap * aq);
             }
-            // transverse diagonals: eta, side faces of L_i and L_{i+1}
+        // D_m = C_m - f_c f_c^T / dL_c - f_n f_n^T / dL_n
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const T et = k < 2 ? etp_c[k] + etp_n[k] : etq_c[k - 2] + etq_n[k - 2];
-                S[1 + k][1 + k] = -0.25 * et;
-                add_real(S[1 + k][1 + k], gs[k] * rd * rd + gn[k] * rdn * rdn);
-            }
-            S[2][1] = zero_<T>();
-            S[4][3] = zero_<T>();
-            S[3][1] = S[3][2] = S[4][1] = S[4][2] = zero_<T>();
-            // end faces at node i+1
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                for (int jq = 0; jq < 2; ++jq) {
-                    const double g = 0.5 * (zc[jp][jq] + zn[jp][jq]);
-                    const double ap = ln.al_p(jq), aq = ln.al_q(jp);
-                    add_real(S[1 + jp][1 + jp], g * ap * ap);
-                    add_real(S[3 + jq][3 + jq], g * aq * aq);
-                    add_real(S[3 + jq][1 + jp], g * ap * aq);
-                }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) { etp_c[j] = etp_n[j]; etq_c[j] = etq_n[j]; }
-        }
-        // Schur update with the previous block
+            for (int c = 0; c <= r; ++c)
+                S[tri(r, c)] -= (cc.f[r] * cc.f[c]) * rl_c + (cn.f[r] * cn.f[c]) * rl_n;
+        // S_m = D_m - E_m X_{m-1} E_m,  E_m = diag(d_c) + rl_c f_c f_c^T
         if (i > 0) {
-            T xf[4];                     // X f
+            T fr[4], u[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                T t = zero_<T>();
+            for (int k = 0; k < 4; ++k) fr[k] = cc.f[k] * rl_c;          // rl_c f_c  (complex)
+            T fc[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) t += f[c] * (r >= c ? X[r][c] : X[c][r]);
-                xf[r] = t;
-            }
-            T z00 = zero_<T>();
+            for (int k = 0; k < 4; ++k) { fc[k] = zero_<T>(); add_real(fc[k], cc.f[k]); }
+            symv4<T>(X, fc, u);                                          // u = X f_c
+            T beta = cc.f[0] * u[0];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) z00 += f[r] * xf[r];
-            S[0][0] -= z00;
-            if (!last) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    S[1 + r][0] -= dk[r] * xf[r];
-#pragma unroll
-                    for (int c = 0; c <= r; ++c) S[1 + r][1 + c] -= (dk[r] * dk[c]) * X[r][c];
-                }
-            }
-        }
-        T* out = fbase + (int64_t)i * FAC_BS;
-        if (last) {
-            out[0] = rcp(S[0][0]);
-            break;
-        }
-        T dinv[5];
-        ldlt5<T>(S, dinv);
-        {
-            int e = 0;
-#pragma unroll
-            for (int r = 1; r < 5; ++r)
-#pragma unroll
-                for (int c = 0; c < r; ++c) out[(e++) * FAC_ES] = S[r][c];
-#pragma unroll
-            for (int r = 0; r < 5; ++r) out[(10 + r) * FAC_ES] = dinv[r];
-        }
-        // X = (L4 D4 L4^T)^-1 with L4 = L[1:,1:], D4 = D[1:]
-        {
-            T Li[4][4];                  // inverse of unit lower L4 (strict lower part)
-            Li[1][0] = -S[2][1];
-            Li[2][1] = -S[3][2];
-            Li[3][2] = -S[4][3];
-            Li[2][0] = -S[3][1] - S[3][2] * Li[1][0];
-            Li[3][1] = -S[4][2] - S[4][3] * Li[2][1];
-            Li[3][0] = -S[4][1] - S[4][2] * Li[1][0] - S[4][3] * Li[2][0];
+            for (int k = 1; k < 4; ++k) beta += cc.f[k] * u[k];          // f_c^T X f_c
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) {
-                    // sum_{k >= r} Li[k][r] dinv[k+1] Li[k][c], Li[k][k] = 1
-                    T t = (r == c) ? dinv[1 + r] : dinv[1 + r] * Li[r][c];
-#pragma unroll
-                    for (int k = r + 1; k < 4; ++k) t += Li[k][r] * dinv[1 + k] * Li[k][c];
-                    X[r][c] = t;
-                }
+                for (int c = 0; c <= r; ++c)
+                    S[tri(r, c)] -= (cc.d[r] * cc.d[c]) * X[tri(r, c)] + (cc.d[r] * u[r]) * fr[c] +
+                                    fr[r] * (u[c] * cc.d[c]) + (fr[r] * fr[c]) * beta;
         }
+        T fl[10];
+        ldlt4_and_inverse<T>(S, fl);
+        T* out = fbase + (int64_t)i * FAC_BS;
+#pragma unroll
+        for (int e = 0; e < 10; ++e) {
+            out[e * FAC_ES] = fl[e];
+            X[e] = S[e];
+        }
+        out[10 * FAC_ES] = rl_n;
+        // shift: cell i+1 becomes the current cell
+        cc = cn;
+        rl_c = rl_n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { etp_c[j] = etp_n[j]; etq_c[j] = etq_n[j]; }
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp)
 #pragma unroll
@@ -295,22 +357,7 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
     }
 }
 
-// ---- one line sweep: forward and backward block substitution ----------------
-//
-// What one thread streams per block of its line:
-//   forward  : 15 factor entries, 5 sources, 4 parallel line edges of the next
-//              cell, 8 outer transverse edges of the end faces, 4 zeta
-//   backward : 15 factor entries, the 5 intermediate values it stored, 4 zeta
-// One thread per line leaves one warp per scheduler (16 k lines per colour at
-// 256^3), so nothing hides memory latency unless the loads of later blocks are
-// in flight while the current block is being solved.  `Staged` does that with
-// cp.async (LDGSTS) into a shared-memory ring [stage][word][thread], STAGES
-// blocks ahead, without touching the register file; `Direct` loads on demand
-// (used by the small-grid and hyperplane kernels).
-constexpr int FWD_WORDS = 32;   // T-words per forward stage: 15 + 5 + 4 + 8
-constexpr int BWD_WORDS = 20;   // 15 + 5
-
-// addresses of everything a line touches
+// ---- addresses of everything a line touches -----------------------------------
 template <typename T, int D>
 struct LineAddr {
     using A = Ax<D>;
@@ -345,424 +392,160 @@ struct LineAddr {
                 oQ[j][o] = E.idx(A::q, pos);     // q-edge in q-cell j at p-node tp-1+o
             }
     }
-    // source pointers of the forward words 15.. of block j (node m = j+1, cell j+1)
-    __device__ __forceinline__ const T* fwd_src(int w, int j) const {
-        const int m = j + 1;
-        switch (w) {
-            case 15: return sdp + oL + sd * j;
-            case 16: return spp + oP[0][1] + sp * m;
-            case 17: return spp + oP[1][1] + sp * m;
-            case 18: return sqp + oQ[0][1] + sq * m;
-            case 19: return sqp + oQ[1][1] + sq * m;
-            case 20: case 21: case 22: case 23: return ed + oLn[w - 20] + sd * m;
-            case 24: return ep + oP[0][0] + sp * m;   // (jp, jq) = (0, 0)
-            case 25: return ep + oP[0][2] + sp * m;   // (0, 1)
-            case 26: return ep + oP[1][0] + sp * m;   // (1, 0)
-            case 27: return ep + oP[1][2] + sp * m;   // (1, 1)
-            case 28: return eq + oQ[0][0] + sq * m;   // (0, 0)
-            case 29: return eq + oQ[1][0] + sq * m;   // (0, 1): q-cell 1, p-node tp-1
-            case 30: return eq + oQ[0][2] + sq * m;   // (1, 0)
-            default: return eq + oQ[1][2] + sq * m;   // (1, 1)
-        }
+    // the four transverse edges [p-, p+, q-, q+] of this line at node m
+    __device__ __forceinline__ T* t_ptr(int k, int m) const {
+        return k == 0 ? ep + oP[0][1] + sp * m : k == 1 ? ep + oP[1][1] + sp * m
+             : k == 2 ? eq + oQ[0][1] + sq * m : eq + oQ[1][1] + sq * m;
     }
-    __device__ __forceinline__ const T* bwd_src(int w, int i) const {
-        const int m = i + 1;
-        switch (w) {
-            case 15: return ed + oL + sd * i;
-            case 16: return ep + oP[0][1] + sp * m;
-            case 17: return ep + oP[1][1] + sp * m;
-            case 18: return eq + oQ[0][1] + sq * m;
-            default: return eq + oQ[1][1] + sq * m;
-        }
+    __device__ __forceinline__ const T* ts_ptr(int k, int m) const {      // their sources
+        return k == 0 ? spp + oP[0][1] + sp * m : k == 1 ? spp + oP[1][1] + sp * m
+             : k == 2 ? sqp + oQ[0][1] + sq * m : sqp + oQ[1][1] + sq * m;
     }
+    // outer transverse edges of the end faces at node m: quadrant (jp, jq)
+    __device__ __forceinline__ T epo(int jp, int jq, int m) const { return ep[oP[jp][2 * jq] + sp * m]; }
+    __device__ __forceinline__ T eqo(int jp, int jq, int m) const { return eq[oQ[jq][2 * jp] + sq * m]; }
 };
 
-// Forward words: f15 = w[0..14]; s5 = w[15..19]; en = w[20..23];
-// epo(jp,jq) = w[24 + 2 jp + jq]; eqo(jp,jq) = w[28 + 2 jp + jq].
-template <typename T, int NW>
-struct RegWords {            // words held in registers
-    T v[NW];
-    __device__ __forceinline__ T operator[](int e) const { return v[e]; }
-};
-template <typename T>
-struct SmemWords {           // words read from the shared-memory ring on use
-    const T* src;
-    int nt;
-    __device__ __forceinline__ T operator[](int e) const { return src[e * nt]; }
-};
-
+// right-hand side of the line edge of cell i: source + outer parallel line edges
 template <typename T, int D>
-struct Direct {
-    using FwdView = RegWords<T, FWD_WORDS>;
-    using BwdView = RegWords<T, BWD_WORDS>;
-    const LineAddr<T, D>& a;
-    const Line<T, D>& ln;
-    int N;
-    __device__ Direct(const LineAddr<T, D>& a_, const Line<T, D>& ln_) : a(a_), ln(ln_), N(ln_.N) {}
-    __device__ __forceinline__ void fwd_start() {}
-    __device__ __forceinline__ void bwd_start() {}
-    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
-        FwdView w;
-        const T* fp = a.fac + (int64_t)j * FAC_BS;
+__device__ __forceinline__ T line_rhs(const LineAddr<T, D>& a, int i, const CellCoef& c, const T eo[4]) {
+    T acc = ldg(a.sdp + a.oL + a.sd * i);
 #pragma unroll
-        for (int e = 0; e < 15; ++e) w.v[e] = ldg(fp + e * FAC_ES);
-        w.v[15] = ldg(a.fwd_src(15, j));
-        if (j < N - 1) {
-#pragma unroll
-            for (int e = 16; e < 20; ++e) w.v[e] = ldg(a.fwd_src(e, j));
-#pragma unroll
-            for (int e = 20; e < FWD_WORDS; ++e) w.v[e] = *a.fwd_src(e, j);
-            ln.load_zeta(j + 1, zn);
-        }
-        return w;
-    }
-    __device__ __forceinline__ BwdView bwd_get(int, int i, double zc[2][2]) {
-        BwdView w;
-        const T* fp = a.fac + (int64_t)i * FAC_BS;
-#pragma unroll
-        for (int e = 0; e < 15; ++e) w.v[e] = ldg(fp + e * FAC_ES);
-#pragma unroll
-        for (int e = 15; e < BWD_WORDS; ++e) w.v[e] = *a.bwd_src(e, i);
-        if (i > 0) ln.load_zeta(i, zc);
-        return w;
-    }
-};
-
-template <typename T, int D, int STAGES>
-struct Staged {
-    using FwdView = SmemWords<T>;
-    using BwdView = SmemWords<T>;
-    const LineAddr<T, D>& a;
-    const Line<T, D>& ln;
-    int N, nt;
-    T* smT;          // this thread's column: word w of stage s at smT[(s * FWD_WORDS + w) * nt]
-    double* smZ;     // zeta ring: smZ[(s * 4 + c) * nt]
-    __device__ Staged(const LineAddr<T, D>& a_, const Line<T, D>& ln_, T* smT_, double* smZ_, int nt_)
-        : a(a_), ln(ln_), N(ln_.N), nt(nt_), smT(smT_), smZ(smZ_) {}
-
-    __device__ __forceinline__ void fwd_issue(int j) {
-        if (j < N) {
-            T* dst = smT + (int64_t)(j % STAGES) * FWD_WORDS * nt;
-            const T* fp = a.fac + (int64_t)j * FAC_BS;
-#pragma unroll
-            for (int e = 0; e < 15; ++e) cp_async(dst + e * nt, fp + e * FAC_ES);
-            cp_async(dst + 15 * nt, a.fwd_src(15, j));
-            if (j < N - 1) {
-#pragma unroll
-                for (int e = 16; e < FWD_WORDS; ++e) cp_async(dst + e * nt, a.fwd_src(e, j));
-                double* dz = smZ + (int64_t)(j % STAGES) * 4 * nt;
-#pragma unroll
-                for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                    for (int jq = 0; jq < 2; ++jq)
-                        cp_async(dz + (2 * jp + jq) * nt,
-                                 ln.m.zeta + ln.cbase[jp][jq] + ln.cstr * (j + 1));
-            }
-        }
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void fwd_start() {
-#pragma unroll
-        for (int k = 0; k < STAGES - 1; ++k) fwd_issue(k);
-    }
-    // The stage overwritten by the new copies is the one consumed in the previous
-    // step; its words were all read (into registers) before this call.
-    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
-        fwd_issue(j + STAGES - 1);
-        cp_async_wait<STAGES - 1>();
-        const double* sz = smZ + (int64_t)(j % STAGES) * 4 * nt;
-#pragma unroll
-        for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-            for (int jq = 0; jq < 2; ++jq) zn[jp][jq] = sz[(2 * jp + jq) * nt];
-        return FwdView{smT + (int64_t)(j % STAGES) * FWD_WORDS * nt, nt};
-    }
-    // backward sequence: k-th step handles block i = N - 2 - k
-    __device__ __forceinline__ void bwd_issue(int k) {
-        const int i = N - 2 - k;
-        if (i >= 0) {
-            T* dst = smT + (int64_t)(k % STAGES) * FWD_WORDS * nt;
-            const T* fp = a.fac + (int64_t)i * FAC_BS;
-#pragma unroll
-            for (int e = 0; e < 15; ++e) cp_async(dst + e * nt, fp + e * FAC_ES);
-#pragma unroll
-            for (int e = 15; e < BWD_WORDS; ++e) cp_async(dst + e * nt, a.bwd_src(e, i));
-            if (i > 0) {
-                double* dz = smZ + (int64_t)(k % STAGES) * 4 * nt;
-#pragma unroll
-                for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                    for (int jq = 0; jq < 2; ++jq)
-                        cp_async(dz + (2 * jp + jq) * nt, ln.m.zeta + ln.cbase[jp][jq] + ln.cstr * i);
-            }
-        }
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void bwd_start() {
-        // our own stores of the forward pass must be visible to the async copies
-        __threadfence_block();
-#pragma unroll
-        for (int k = 0; k < STAGES - 1; ++k) bwd_issue(k);
-    }
-    __device__ __forceinline__ BwdView bwd_get(int k, int, double zc[2][2]) {
-        bwd_issue(k + STAGES - 1);
-        cp_async_wait<STAGES - 1>();
-        const double* sz = smZ + (int64_t)(k % STAGES) * 4 * nt;
-#pragma unroll
-        for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-            for (int jq = 0; jq < 2; ++jq) zc[jp][jq] = sz[(2 * jp + jq) * nt];
-        return BwdView{smT + (int64_t)(k % STAGES) * FWD_WORDS * nt, nt};
-    }
-};
-
-// Factor stream through TMA: the factors of one block of the 32 lines of a warp are
-// ONE contiguous chunk of 15 * 32 words (layout above), so a single elected lane
-// fetches it with one cp.async.bulk (UBLKCP) into a per-warp shared-memory ring,
-// BULK_STAGES blocks ahead of the block being solved, completion on an mbarrier.
-// The fetch sequence runs through the forward pass (blocks 0 .. N-1) and straight on
-// into the backward pass (blocks N-2 .. 0), so the ring never drains between the
-// passes.  No registers and no LSU instructions are spent on the factor stream; the
-// strided E / S / zeta accesses stay ordinary loads through the L1.
-#ifndef EMG_LINE_BULK
-#define EMG_LINE_BULK 0
-#endif
-#ifndef EMG_LINE_BULK_STAGES
-#define EMG_LINE_BULK_STAGES 4
-#endif
-constexpr int BULK_STAGES = EMG_LINE_BULK_STAGES;
-
-template <typename T, int D>
-struct BulkFac {
-    using FwdView = RegWords<T, FWD_WORDS>;
-    using BwdView = RegWords<T, BWD_WORDS>;
-    static constexpr unsigned BYTES = FAC_BS * sizeof(T);
-    const LineAddr<T, D>& a;
-    const Line<T, D>& ln;
-    int N, lane, q;
-    unsigned mask;
-    T* ring;              // this warp's ring: [stage][entry][lane]
-    uint64_t* bars;       // this warp's mbarriers: [stage]
-    const T* gsrc;        // (block 0, entry 0, lane 0) of the warp's 32-line group
-    __device__ BulkFac(const LineAddr<T, D>& a_, const Line<T, D>& ln_, T* ring_, uint64_t* bars_,
-                       unsigned mask_)
-        : a(a_), ln(ln_), N(ln_.N), lane(threadIdx.x & 31), q(0), mask(mask_), ring(ring_), bars(bars_),
-          gsrc(a_.fac - (threadIdx.x & 31)) {}
-
-    // fetch number qq of the sequence: forward blocks 0 .. N-1, then backward N-2 .. 0
-    __device__ __forceinline__ void issue(int qq) {
-        if (qq > 2 * N - 2) return;
-        const int blk = qq < N ? qq : 2 * N - 2 - qq;
-        const int st = qq % BULK_STAGES;
-        mbar_expect_tx(bars + st, BYTES);
-        bulk_g2s(ring + st * FAC_BS, gsrc + (int64_t)blk * FAC_BS, BYTES, bars + st);
-    }
-    __device__ __forceinline__ void fwd_start() {
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < BULK_STAGES; ++k) issue(k);
-        }
-    }
-    __device__ __forceinline__ void bwd_start() {}
-    template <class V>
-    __device__ __forceinline__ void factors(V& w) {
-        const int st = q % BULK_STAGES;
-        mbar_wait(bars + st, (q / BULK_STAGES) & 1);
-        const T* p = ring + st * FAC_BS + lane;
-#pragma unroll
-        for (int e = 0; e < 15; ++e) w.v[e] = p[e * FAC_ES];
-        __syncwarp(mask);                       // every lane has read the stage
-        if (lane == 0) {
-            fence_proxy_async_smem();
-            issue(q + BULK_STAGES);
-        }
-        ++q;
-    }
-    __device__ __forceinline__ FwdView fwd_get(int j, double zn[2][2]) {
-        FwdView w;
-        factors(w);
-        w.v[15] = ldg(a.fwd_src(15, j));
-        if (j < N - 1) {
-#pragma unroll
-            for (int e = 16; e < 20; ++e) w.v[e] = ldg(a.fwd_src(e, j));
-#pragma unroll
-            for (int e = 20; e < FWD_WORDS; ++e) w.v[e] = *a.fwd_src(e, j);
-            ln.load_zeta(j + 1, zn);
-        }
-        return w;
-    }
-    __device__ __forceinline__ BwdView bwd_get(int, int i, double zc[2][2]) {
-        BwdView w;
-        factors(w);
-#pragma unroll
-        for (int e = 15; e < BWD_WORDS; ++e) w.v[e] = *a.bwd_src(e, i);
-        if (i > 0) ln.load_zeta(i, zc);
-        return w;
-    }
-};
-
-template <typename T, class W>
-__device__ __forceinline__ void solve5(const W& f, T y[5], bool first_zero) {
-    T L[10], dinv[5];
-#pragma unroll
-    for (int e = 0; e < 10; ++e) L[e] = f[e];
-#pragma unroll
-    for (int e = 0; e < 5; ++e) dinv[e] = f[10 + e];
-    // L index: (1,0)=0 (2,0)=1 (2,1)=2 (3,0)=3 (3,1)=4 (3,2)=5 (4,0)=6 (4,1)=7 (4,2)=8 (4,3)=9
-    if (!first_zero) {
-        y[1] -= L[0] * y[0];
-        y[2] -= L[1] * y[0];
-        y[3] -= L[3] * y[0];
-        y[4] -= L[6] * y[0];
-    }
-    y[2] -= L[2] * y[1];
-    y[3] -= L[4] * y[1];
-    y[4] -= L[7] * y[1];
-    y[3] -= L[5] * y[2];
-    y[4] -= L[8] * y[2];
-    y[4] -= L[9] * y[3];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) y[r] = y[r] * dinv[r];
-    y[3] -= L[9] * y[4];
-    y[2] -= L[8] * y[4] + L[5] * y[3];
-    y[1] -= L[7] * y[4] + L[4] * y[3] + L[2] * y[2];
-    y[0] -= L[6] * y[4] + L[3] * y[3] + L[1] * y[2] + L[0] * y[1];
+    for (int k = 0; k < 4; ++k) acc += c.gaa[k] * eo[k];
+    return acc;
 }
 
-template <typename T, int D, class Loader>
-__device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a, Loader& ld) {
+// ---- one line sweep: forward and backward block substitution ----------------
+//
+// What one thread streams per cell of its line:
+//   forward  : 11 factor entries, 5 sources, 4 parallel line edges of the next
+//              cell, 8 outer transverse edges of the end faces, 4 zeta;
+//              writes g_m (4) and bL (1)
+//   backward : 11 factor entries, g_m (4), bL (1), 4 zeta; writes T_m (4), L (1)
+template <typename T, int D>
+__device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
     using A = Ax<D>;
     const Model<T>& m = ln.m;
     const int N = ln.N;
 
     // ---------------- forward ----------------
-    ld.fwd_start();
-    double zc[2][2], zn[2][2], gs[4], gn[4];
+    double zc[2][2], zn[2][2], gs[4];
     ln.load_zeta(0, zc);
     ln.side_g(zc, gs);
-    double rd = ldg(m.rh[A::d]);
-    T eo[4];                             // parallel neighbours of L_i
+    CellCoef cc, cn;
+    cell_coef<T, D>(ln, gs, ldg(m.rh[A::d]), cc);
+    T eo_c[4], eo_n[4];                  // outer parallel neighbours of L in the current / next cell
 #pragma unroll
-    for (int k = 0; k < 4; ++k) eo[k] = a.ed[a.oLn[k]];
-    // transverse part of the previous block's solution; for the first block the
-    // (fixed) transverse edges on the line's start plane: zero on a PEC boundary,
-    // halo data of the neighbouring slab on a multi-GPU z-window
-    T wT[4];
-    wT[0] = a.ep[a.oP[0][1]];
-    wT[1] = a.ep[a.oP[1][1]];
-    wT[2] = a.eq[a.oQ[0][1]];
-    wT[3] = a.eq[a.oQ[1][1]];
+    for (int k = 0; k < 4; ++k) eo_c[k] = a.ed[a.oLn[k]];
+    T rl_c = ldg(a.fac + (int64_t)(N - 1) * FAC_BS);         // 1 / dL_0
+    T bl_c = line_rhs<T, D>(a, 0, cc, eo_c);
+    a.ed[a.oL] = bl_c;
+    // g_0 = T_0: the (fixed) transverse edges on the line's start plane: zero on a PEC
+    // boundary, halo data of the neighbouring slab on a multi-GPU z-window
+    T g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = *a.t_ptr(k, 0);
 
-    for (int i = 0; i < N; ++i) {
-        const bool last = (i == N - 1);
-        const typename Loader::FwdView w = ld.fwd_get(i, zn);
-        T y[5];
-        // line edge
-        {
-            T acc = w[15];
+    for (int i = 0; i < N - 1; ++i) {                        // node mn = i + 1
+        const int mn = i + 1;
+        const T* fp = a.fac + (int64_t)i * FAC_BS;
+        T X[10];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double as = ln.a_side(k);
-                acc += (gs[k] * as * as) * eo[k];
-            }
-            y[0] = acc;
-        }
-        double f[4], dk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            f[k] = -gs[k] * ln.a_side(k) * rd;
-            dk[k] = -gs[k] * rd * rd;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) y[0] -= f[k] * wT[k];
-        if (last) {
-            // coupling to the fixed transverse edges on the line's end plane
-            const T tN[4] = {a.ep[a.oP[0][1] + a.sp * N], a.ep[a.oP[1][1] + a.sp * N],
-                             a.eq[a.oQ[0][1] + a.sq * N], a.eq[a.oQ[1][1] + a.sq * N]};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) y[0] += f[k] * tN[k];
-            a.ed[a.oL + a.sd * i] = y[0] * w[0];
-            break;
-        }
-        // transverse edges at node m = i+1
-        const int mnode = i + 1;
+        for (int e = 0; e < 10; ++e) X[e] = ldg(fp + e * FAC_ES);
+        const T rl_n = ldg(fp + 10 * FAC_ES);
+        ln.load_zeta(mn, zn);
+        double gn[4];
         ln.side_g(zn, gn);
-        const double rdn = ldg(m.rh[A::d] + i + 1);
+        cell_coef<T, D>(ln, gn, ldg(m.rh[A::d] + mn), cn);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y[1 + k] = w[16 + k];
-        // side faces of L_i (+) and L_{i+1} (-)
+        for (int k = 0; k < 4; ++k) eo_n[k] = a.ed[a.oLn[k] + a.sd * mn];
+        const T bl_n = line_rhs<T, D>(a, mn, cn, eo_n);
+        // bT_m: sources, side faces of cell i (+) and cell i+1 (-), end faces at node m
+        T r[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double as = ln.a_side(k);
-            y[1 + k] += (gs[k] * rd * as) * eo[k] - (gn[k] * rdn * as) * w[20 + k];
-        }
-        // end faces at node m
+        for (int k = 0; k < 4; ++k) r[k] = ldg(a.ts_ptr(k, mn)) + cc.gra[k] * eo_c[k] - cn.gra[k] * eo_n[k];
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp)
 #pragma unroll
             for (int jq = 0; jq < 2; ++jq) {
-                const double g = 0.5 * (zc[jp][jq] + zn[jp][jq]);
+                const double gf = 0.5 * (zc[jp][jq] + zn[jp][jq]);
                 const double ap = ln.al_p(jq), aq = ln.al_q(jp);
-                const T out = ap * w[24 + 2 * jp + jq] + aq * w[28 + 2 * jp + jq];
-                y[1 + jp] += (g * ap) * out;
-                y[3 + jq] += (g * aq) * out;
+                const T out = ap * a.epo(jp, jq, mn) + aq * a.eqo(jp, jq, mn);
+                r[jp] += (gf * ap) * out;
+                r[2 + jq] += (gf * aq) * out;
             }
+        // r_m = bT_m + f_c bL_c / dL_c - f_n bL_n / dL_n;   v = r_m - E_m g_{m-1}
+        const T sc = bl_c * rl_c, sn = bl_n * rl_n;
+        T eg[4], v[4];
+        apply_E<T>(cc.d, cc.f, rl_c, g, eg);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) y[1 + k] -= dk[k] * wT[k];
-        if (i == N - 2) {
-            // last interior node: its neighbours on the end plane are fixed data
-            const T tN[4] = {a.ep[a.oP[0][1] + a.sp * N], a.ep[a.oP[1][1] + a.sp * N],
-                             a.eq[a.oQ[0][1] + a.sq * N], a.eq[a.oQ[1][1] + a.sq * N]};
+        for (int k = 0; k < 4; ++k) v[k] = r[k] + cc.f[k] * sc - cn.f[k] * sn - eg[k];
+        solve4<T>(X, v);                                     // g_m = S_m^{-1} v
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[1 + k] += (gn[k] * rdn * rdn) * tN[k];
-        }
-        solve5<T>(w, y, false);
-        a.ed[a.oL + a.sd * i] = y[0];
-        a.ep[a.oP[0][1] + a.sp * mnode] = y[1];
-        a.ep[a.oP[1][1] + a.sp * mnode] = y[2];
-        a.eq[a.oQ[0][1] + a.sq * mnode] = y[3];
-        a.eq[a.oQ[1][1] + a.sq * mnode] = y[4];
+        for (int k = 0; k < 4; ++k) g[k] = v[k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { wT[k] = y[1 + k]; eo[k] = w[20 + k]; gs[k] = gn[k]; }
+        for (int k = 0; k < 4; ++k) *a.t_ptr(k, mn) = g[k];
+        a.ed[a.oL + a.sd * mn] = bl_n;
+        // shift
+        cc = cn;
+        rl_c = rl_n;
+        bl_c = bl_n;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eo_c[k] = eo_n[k];
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp)
 #pragma unroll
             for (int jq = 0; jq < 2; ++jq) zc[jp][jq] = zn[jp][jq];
-        rd = rdn;
     }
 
     // ---------------- backward ----------------
-    // x_i = w_i - S_i^{-1} F_{i+1}^T x_{i+1};  gs / rd now belong to line cell N-1
-    T xL = a.ed[a.oL + a.sd * (N - 1)];
-    ld.bwd_start();
-    T xT[4];
+    // cc / rl_c / bl_c now belong to the last cell N-1; T_N is fixed data
+    T tn[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xT[k] = zero_<T>();
-    for (int i = N - 2; i >= 0; --i) {
-        T v[5];
-        v[0] = zero_<T>();
+    for (int k = 0; k < 4; ++k) tn[k] = *a.t_ptr(k, N);
+    for (int i = N - 2; i >= 0; --i) {                       // node mn = i + 1, cell mn
+        const int mn = i + 1;
+        const T* fp = a.fac + (int64_t)i * FAC_BS;
+        T X[10];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) X[e] = ldg(fp + e * FAC_ES);
+        if (i < N - 2) {                                     // (the last cell's data are at hand)
+            rl_c = ldg(fp + 10 * FAC_ES);
+            bl_c = a.ed[a.oL + a.sd * mn];
+            ln.load_zeta(mn, zc);
+            ln.side_g(zc, gs);
+            cell_coef<T, D>(ln, gs, ldg(m.rh[A::d] + mn), cc);
+        }
+        T gm[4], w[4], tm[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gm[k] = *a.t_ptr(k, mn);
+        apply_E<T>(cc.d, cc.f, rl_c, tn, w);                 // E_{m+1} T_{m+1}
+        solve4<T>(X, w);
+        T fd = zero_<T>();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double fk = -gs[k] * ln.a_side(k) * rd;
-            const double dkk = -gs[k] * rd * rd;
-            v[1 + k] = fk * xL + dkk * xT[k];
+            tm[k] = gm[k] - w[k];
+            fd += cc.f[k] * (tm[k] - tn[k]);
         }
-        const typename Loader::BwdView w = ld.bwd_get(N - 2 - i, i, zc);
-        solve5<T>(w, v, true);
-        const int mnode = i + 1;
-        xL = w[15] - v[0];
+        a.ed[a.oL + a.sd * mn] = rl_c * (bl_c - fd);         // L_m
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xT[k] = w[16 + k] - v[1 + k];
-        a.ed[a.oL + a.sd * i] = xL;
-        a.ep[a.oP[0][1] + a.sp * mnode] = xT[0];
-        a.ep[a.oP[1][1] + a.sp * mnode] = xT[1];
-        a.eq[a.oQ[0][1] + a.sq * mnode] = xT[2];
-        a.eq[a.oQ[1][1] + a.sq * mnode] = xT[3];
-        if (i > 0) {
-            ln.side_g(zc, gs);
-            rd = ldg(m.rh[A::d] + i);
+        for (int k = 0; k < 4; ++k) {
+            *a.t_ptr(k, mn) = tm[k];
+            tn[k] = tm[k];
         }
     }
+    // L_0 = (bL_0 - f_0 . (T_0 - T_1)) / dL_0
+    if (N > 1) {
+        rl_c = ldg(a.fac + (int64_t)(N - 1) * FAC_BS);
+        bl_c = a.ed[a.oL];
+        ln.load_zeta(0, zc);
+        ln.side_g(zc, gs);
+        cell_coef<T, D>(ln, gs, ldg(m.rh[A::d]), cc);
+    }
+    T fd = zero_<T>();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) fd += cc.f[k] * (*a.t_ptr(k, 0) - tn[k]);
+    a.ed[a.oL] = rl_c * (bl_c - fd);
 }
 
 template <typename T, int D>
@@ -771,8 +554,7 @@ __device__ __forceinline__ void sweep_line_direct(const Model<T>& m, int tp, int
                                                   const FieldView<const T>& S) {
     Line<T, D> ln(m, tp, tq);
     LineAddr<T, D> a(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
-    Direct<T, D> ld(a, ln);
-    sweep_line<T, D>(ln, a, ld);
+    sweep_line<T, D>(ln, a);
 }
 
 
@@ -794,47 +576,14 @@ line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c) {
     factor_line<T, D>(m, tp, tq, fac, ls);
 }
 
-#ifndef EMG_LINE_STAGED
-#define EMG_LINE_STAGED 0
-#endif
-
 template <typename T, int D>
 __global__ void __launch_bounds__(64)
 gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c) {
     int tp, tq;
-    const bool valid = class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq);
-#if EMG_LINE_BULK && !EMG_LINE_STAGED
-    const unsigned mask = __ballot_sync(0xffffffffu, valid);
-#endif
-    if (!valid) return;
+    if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
-    Line<T, D> ln(m, tp, tq);
-    LineAddr<T, D> ad(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
-#if EMG_LINE_BULK && !EMG_LINE_STAGED
-    extern __shared__ __align__(128) unsigned char ring_raw[];
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    T* ring = reinterpret_cast<T*>(ring_raw) + (size_t)warp * BULK_STAGES * FAC_BS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<T*>(ring_raw) +
-                                                 (size_t)nwarps * BULK_STAGES * FAC_BS) + warp * BULK_STAGES;
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < BULK_STAGES; ++k) mbar_init(bars + k, 1);
-        mbar_init_fence();
-    }
-    __syncwarp(mask);
-    BulkFac<T, D> ld(ad, ln, ring, bars, mask);
-#elif EMG_LINE_STAGED
-    extern __shared__ __align__(16) unsigned char ring_raw[];
-    const int nt = blockDim.x;
-    T* smT = reinterpret_cast<T*>(ring_raw) + threadIdx.x;
-    double* smZ = reinterpret_cast<double*>(reinterpret_cast<T*>(ring_raw) +
-                                            (size_t)LINE_STAGES * FWD_WORDS * nt) + threadIdx.x;
-    Staged<T, D, LINE_STAGES> ld(ad, ln, smT, smZ, nt);
-#else
-    Direct<T, D> ld(ad, ln);
-#endif
-    sweep_line<T, D>(ln, ad, ld);
+    sweep_line_direct<T, D>(m, tp, tq, fac, ls, E, S);
 }
 
 template <typename T, int D>
@@ -948,27 +697,8 @@ static void gs_dir(const Model<T>& m, const T* fac, T* e, const T* s, int nu, in
                 // again reproduces the same values (block relaxation is idempotent), so
                 // that launch is skipped -- 7 instead of 8 colour launches for nu = 2.
                 if (sw > 0 && cc == 0) continue;
-                const int threads = EMG_LINE_STAGED ? 32 : 64;
-                size_t smem = 0;
-#if EMG_LINE_BULK && !EMG_LINE_STAGED
-                smem = (size_t)(threads / 32) * BULK_STAGES * (FAC_BS * sizeof(T) + sizeof(uint64_t));
-                static bool bulk_attr_set = false;  // per template instance
-                if (!bulk_attr_set) {
-                    cudaFuncSetAttribute(gs_line_color_kernel<T, D>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    bulk_attr_set = true;
-                }
-#endif
-#if EMG_LINE_STAGED
-                smem = (size_t)LINE_STAGES * threads * (FWD_WORDS * sizeof(T) + 4 * sizeof(double));
-                static bool attr_set = false;       // per template instance
-                if (!attr_set) {
-                    cudaFuncSetAttribute(gs_line_color_kernel<T, D>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    attr_set = true;
-                }
-#endif
-                ++g_launch_count; gs_line_color_kernel<T, D><<<(ls.cnt[c] + threads - 1) / threads, threads, smem, st>>>(m, fac, ls, e, s, c);
+                const int threads = 64;
+                ++g_launch_count; gs_line_color_kernel<T, D><<<(ls.cnt[c] + threads - 1) / threads, threads, 0, st>>>(m, fac, ls, e, s, c);
             }
         }
     }

@@ -6,11 +6,17 @@ Bars (fp64 throughout):
 * ``amat_x`` / residual, restriction, prolongation, cell sums: <= 1e-13
   (pure stencils, no solves);
 * smoothers in ``order='lex'`` against the reference's own outputs (golden) and
-  against the oracle on larger grids: <= 1e-11 after a call (every update is a
-  6x6 or banded solve; the reference itself is only defined to ~1e-13 because
-  numba runs with fastmath);
+  against the oracle on larger grids, after a call: point smoother <= 1e-11 (every
+  update is a 6x6 solve; the reference itself is only defined to ~1e-13 because
+  numba runs with fastmath); line smoothers <= 2e-10: the CUDA kernels eliminate
+  the line edges before the transverse edges (4x4 blocks, csrc/gs_line.cu) while
+  the reference and the oracle factorise 5x5 blocks in natural order, and the line
+  systems are ill-conditioned (the curl-curl part is singular on gradients and only
+  the small eta term regularises it), so the two elimination orders differ by
+  cond x eps: measured 5e-14 .. 7e-11 on these cases, worst in the Laplace domain;
+  the reference's own ``Field.__eq__`` uses rtol = 1e-10 (fields.py:135);
 * smoothers in ``order='color'`` against the oracle run in the same colour
-  sequence: <= 1e-11.
+  sequence: same bars.
 """
 import numpy as np
 import pytest
@@ -23,6 +29,7 @@ from helpers import hfield_case, kernel_case, split_faces, split_field
 pytestmark = pytest.mark.gpu
 
 GS = ['gauss_seidel', 'gauss_seidel_x', 'gauss_seidel_y', 'gauss_seidel_z']
+TOL_GS = [1e-11, 2e-10, 2e-10, 2e-10]          # point, x-, y-, z-lines (see above)
 
 
 @pytest.fixture(scope='module')
@@ -93,7 +100,7 @@ def test_gauss_seidel_lex_golden(core, golden, ldir):
             e = c['e'].copy()
             fn(*split_field(c['shape'], e), *split_field(c['shape'], c['s']), *_margs(c), nu,
                order='lex')
-            assert rel_err(e, gk[c['prefix'] + f'gs{ldir}_nu{nu}']) < 1e-11, (k, nu)
+            assert rel_err(e, gk[c['prefix'] + f'gs{ldir}_nu{nu}']) < TOL_GS[ldir], (k, nu)
 
 
 # shapes chosen so that both the single-block path (small grids) and the
@@ -127,7 +134,7 @@ def test_gauss_seidel_vs_oracle(core, ldir, order):
                 seq = oracle.color_sequence(ldir, shape, nu, tile_variant=_tile_variant())
                 oracle.gs_sequence(ldir, *split_field(shape, e_cpu), *split_field(shape, c['s']),
                                    *_margs(c), seq)
-            assert rel_err(e_gpu, e_cpu) < 1e-11, (shape, nu)
+            assert rel_err(e_gpu, e_cpu) < TOL_GS[ldir], (shape, nu)
 
 
 @pytest.mark.parametrize('order', ['lex', 'color'])
@@ -300,7 +307,7 @@ def test_residual_and_smoothing_wrappers(golden):
             g = mg.Grid([c['hx'], c['hy'], c['hz']])
             ovm = mg.VolumeModel.from_arrays(g, c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'])
             mg.smoothing(ovm, c['s'], e2, 2, lr_dir)
-            assert rel_err(e1.field, e2) < 1e-11, (k, lr_dir)
+            assert rel_err(e1.field, e2) < (1e-11 if lr_dir == 0 else 2e-10), (k, lr_dir)
 
 
 def test_volume_model_on_device(golden):
