@@ -199,8 +199,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "plain V(2,2) multigrid cycle, marine CSEM model "
-                               "(BASELINE.json configs[2]); CPU arm sampled at 64^3"},
+        "config": {"workload": "plain V(2,2) multigrid cycle (nu_coarse=1) on the 256^3 marine CSEM "
+                               "model of BASELINE.json configs[2], complex128, VTI",
+                   "order": "lex (the reference's order)", "parallelism": f"{cores} host cores",
+                   "sample": f"the same cycle on the {n}^3 sibling of the workload (bounded CPU "
+                             "sample; throughput in cell-sweeps/s is size-independent to ~20 %)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,6 +226,9 @@ def main():
     ap.add_argument('--order', default='color', choices=['color', 'lex'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cycles-only', action='store_true',
+                    help='run the warm-up and timed cycles and stop (for ncu launch lists: the '
+                         'launches are then those of the step, plus the one-off setup kernels)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -295,6 +301,13 @@ def main():
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     value = world * work * args.steps / (ms * 1e-3)
+
+    if args.cycles_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches), "note": "--cycles-only"}))
+        return
 
     # --- dominant kernel: the point smoother on the finest grid -------------------
     # nu = 2 sweeps = 16 colour launches; algorithmic bytes per cell-sweep: E read +

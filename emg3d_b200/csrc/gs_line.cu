@@ -21,14 +21,18 @@
 // Same equations, same solution (to rounding) as the reference's block solve.
 //
 // B200 design: the matrix depends on (grid, model, s) only, not
-// on E, so the LDL^T factors of S_m (10 numbers) and 1/dL (1 number) are computed
+// on E, so X_m = S_m^{-1} (10 numbers, symmetric) and 1/dL (1 number) are computed
 // ONCE per level and direction (`line_factor`) and streamed from HBM by every
 // sweep -- 11 numbers per cell instead of the 15 of a 5x5 block LDL^T, and E_m is
 // rebuilt from zeta and the widths on the fly (the kernels are bound by the bytes
-// they move, with the fp64 pipe below 10 %).  A sweep is one forward pass
-//     g_m = S_m^{-1} (r_m - E_m g_{m-1}),  g_0 = T_0,
+// they move, with the fp64 pipe below 10 %).  The explicit inverse is stored rather
+// than LDL^T factors: applying it is a matrix-vector product without a dependent
+// chain (measured 8-17 % faster with one warp per scheduler) and as accurate on the
+// golden cases (the inverse is needed by the block recurrence anyway).  A sweep is
+// one forward pass
+//     g_m = X_m (r_m - E_m g_{m-1}),  g_0 = T_0,
 // and one backward pass
-//     T_m = g_m - S_m^{-1} E_{m+1} T_{m+1},   L_m = (bL_m - f_m . (T_m - T_{m+1})) / dL_m,
+//     T_m = g_m - X_m E_{m+1} T_{m+1},   L_m = (bL_m - f_m . (T_m - T_{m+1})) / dL_m,
 // one thread per line, g_m and bL_i stored in place in E between the passes.
 // Factor layout [group of 32 lines][block][entry][lane] makes the factor stream one
 // contiguous chunk per warp and block.
@@ -53,8 +57,8 @@ template <int D> struct Ax {
 // within a class p fastest.  A warp of the colour kernel therefore owns one
 // aligned group of 32 consecutive slots, and the factors are stored
 //     [group][block i][entry e][lane]          (32 lanes, 11 entries, N blocks)
-// block i < N-1: entries 0..9 = LDL^T factors of S_{i+1} (6 entries of L, 4 of 1/D),
-// entry 10 = 1/dL_{i+1}; block N-1: entry 0 = 1/dL_0.
+// block i < N-1: entries 0..9 = X_{i+1} = S_{i+1}^{-1} (symmetric, lower triangle
+// row-wise), entry 10 = 1/dL_{i+1}; block N-1: entry 0 = 1/dL_0.
 constexpr int FAC_NE = 11;          // entries per block
 constexpr int FAC_ES = 32;          // stride between entries of one block
 constexpr int FAC_BS = FAC_NE * 32; // stride between blocks of one line
@@ -132,12 +136,10 @@ struct Line {
 // symmetric 4x4 in packed lower-triangular storage: (r, c), r >= c, at r (r+1)/2 + c
 __device__ __forceinline__ constexpr int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
-// LDL^T without pivoting of a complex-symmetric (not Hermitian) 4x4 (the pivots are
-// those of the reference's banded LDL^T of the same system).  In: x packed lower
-// triangle.  Out: f[0..5] = strict lower part of L row-wise ((1,0) (2,0) (2,1) (3,0)
-// (3,1) (3,2)), f[6..9] = 1 / D; and x <- x^{-1} (needed by the block recurrence only).
+// x <- x^{-1} for a complex-symmetric (not Hermitian) 4x4 in packed lower-triangular
+// storage, through its LDL^T without pivoting.
 template <typename T>
-__device__ __forceinline__ void ldlt4_and_inverse(T x[10], T f[10]) {
+__device__ __forceinline__ void inv4sym(T x[10]) {
     T l[4][4], dinv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -161,9 +163,6 @@ __device__ __forceinline__ void ldlt4_and_inverse(T x[10], T f[10]) {
                 l[i][j] = t * dinv[j];
             }
     }
-    f[0] = l[1][0]; f[1] = l[2][0]; f[2] = l[2][1]; f[3] = l[3][0]; f[4] = l[3][1]; f[5] = l[3][2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) f[6 + j] = dinv[j];
     // inverse of the unit lower factor (strict lower part)
     T li[4][4];
     li[1][0] = -l[1][0];
@@ -182,19 +181,6 @@ __device__ __forceinline__ void ldlt4_and_inverse(T x[10], T f[10]) {
             for (int k = r + 1; k < 4; ++k) t += li[k][r] * dinv[k] * li[k][c];
             x[tri(r, c)] = t;
         }
-}
-
-// y <- S^{-1} y with the factors of ldlt4_and_inverse
-template <typename T>
-__device__ __forceinline__ void solve4(const T f[10], T y[4]) {
-    y[1] -= f[0] * y[0];
-    y[2] -= f[1] * y[0] + f[2] * y[1];
-    y[3] -= f[3] * y[0] + f[4] * y[1] + f[5] * y[2];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = y[j] * f[6 + j];
-    y[2] -= f[5] * y[3];
-    y[1] -= f[2] * y[2] + f[4] * y[3];
-    y[0] -= f[0] * y[1] + f[1] * y[2] + f[3] * y[3];
 }
 
 template <typename T>
@@ -336,12 +322,11 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
                     S[tri(r, c)] -= (cc.d[r] * cc.d[c]) * X[tri(r, c)] + (cc.d[r] * u[r]) * fr[c] +
                                     fr[r] * (u[c] * cc.d[c]) + (fr[r] * fr[c]) * beta;
         }
-        T fl[10];
-        ldlt4_and_inverse<T>(S, fl);
+        inv4sym<T>(S);
         T* out = fbase + (int64_t)i * FAC_BS;
 #pragma unroll
         for (int e = 0; e < 10; ++e) {
-            out[e * FAC_ES] = fl[e];
+            out[e * FAC_ES] = S[e];               // the inverse (see file header)
             X[e] = S[e];
         }
         out[10 * FAC_ES] = rl_n;
@@ -480,9 +465,7 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
         apply_E<T>(cc.d, cc.f, rl_c, g, eg);
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = r[k] + cc.f[k] * sc - cn.f[k] * sn - eg[k];
-        solve4<T>(X, v);                                     // g_m = S_m^{-1} v
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g[k] = v[k];
+        symv4<T>(X, v, g);                                   // g_m = S_m^{-1} v
 #pragma unroll
         for (int k = 0; k < 4; ++k) *a.t_ptr(k, mn) = g[k];
         a.ed[a.oL + a.sd * mn] = bl_n;
@@ -516,15 +499,15 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
             ln.side_g(zc, gs);
             cell_coef<T, D>(ln, gs, ldg(m.rh[A::d] + mn), cc);
         }
-        T gm[4], w[4], tm[4];
+        T gm[4], w[4], xw[4], tm[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) gm[k] = *a.t_ptr(k, mn);
         apply_E<T>(cc.d, cc.f, rl_c, tn, w);                 // E_{m+1} T_{m+1}
-        solve4<T>(X, w);
+        symv4<T>(X, w, xw);
         T fd = zero_<T>();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            tm[k] = gm[k] - w[k];
+            tm[k] = gm[k] - xw[k];
             fd += cc.f[k] * (tm[k] - tn[k]);
         }
         a.ed[a.oL + a.sd * mn] = rl_c * (bl_c - fd);         // L_m
