@@ -77,6 +77,7 @@ _SIGNATURES = {
     'emg3d_b200_amat_x': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_apply': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_point_tile_schedule': (c_int, [POINTER(c_int)]),
+    'emg3d_b200_point_tile_shape': (c_int, [POINTER(c_int)]),
     'emg3d_b200_magnetic_field': (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double]),
     'emg3d_b200_host_edge_curl_factor': (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 10),
     'emg3d_b200_residual': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

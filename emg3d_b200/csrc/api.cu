@@ -679,6 +679,11 @@ int emg3d_b200_point_tile_schedule(int* variant) {
     return 0;
 }
 
+int emg3d_b200_point_tile_shape(int* txyz) {
+    point_tile_shape(txyz);
+    return 0;
+}
+
 int emg3d_b200_restrict(emg3d_b200_level* c, const void* r_fine, void* s_coarse) {
     NEED_INIT();
     if (!c->linked) return fail_msg("restrict: coarse level is not linked to a fine level");

@@ -311,10 +311,13 @@ gs_point_color_kernel(Model<T> m, T* e, const T* s, int fx, int fy, int fz, int 
 // all 8 node colours of its tile back to back, with a block barrier between
 // colours.  The tile's edges, sources and coefficients are then read from HBM
 // once per sweep instead of once per node colour (the re-reads hit L1/L2).
+// Tile shape (nodes).  Measured at 256^3 (tools/tune_tiles128.sh, r1): 64 x 4 x 4 runs a
+// tile-colour launch in 0.159 ms, 32 x 8 x 4 in 0.165, 16 x 8 x 8 in 0.181, 8 x 8 x 8 in 0.246:
+// long x-rows make every warp-wide access one contiguous 1 KB run per row.
 #ifndef EMG_TILE_X
-#define EMG_TILE_X 16
-#define EMG_TILE_Y 8
-#define EMG_TILE_Z 8
+#define EMG_TILE_X 64
+#define EMG_TILE_Y 4
+#define EMG_TILE_Z 4
 #endif
 #ifndef EMG_TILE_MINB
 #define EMG_TILE_MINB 3
@@ -761,6 +764,7 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
 }
 
 int point_tile_schedule() { return EMG_PT_MARCH ? 1 : 0; }
+void point_tile_shape(int* t) { t[0] = TX; t[1] = TY; t[2] = TZ; }
 
 template void launch_gs_point<double>(const Model<double>&, double*, const double*, int, int, cudaStream_t);
 template void launch_gs_point<cplx>(const Model<cplx>&, cplx*, const cplx*, int, int, cudaStream_t);

@@ -28,6 +28,7 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
 // order inside a tile of the tile-fused schedule: 0 = 8 node colours, 1 = 4 column
 // colours with a sequential march along y (tests build the oracle's sequence from it)
 int point_tile_schedule();
+void point_tile_shape(int* txyz);      // tile shape in nodes
 // diagonal of A per edge (field layout), read by the point smoother through m.diag
 template <typename T>
 void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st);

@@ -132,6 +132,8 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
  * colours (parity of ix, iz), every column relaxed sequentially along y
  * (csrc/gs_point.cu).  Tests use it to run the oracle in the same order. */
 int emg3d_b200_point_tile_schedule(int* variant);
+/* tile shape (nodes along x, y, z) of that schedule */
+int emg3d_b200_point_tile_shape(int* txyz);
 /* coarse_s = R r_fine.  Replaces core.restrict (core.py:1620-1621).            */
 int emg3d_b200_restrict(emg3d_b200_level* coarse, const void* r_fine, void* s_coarse);
 /* e_fine += P e_coarse on interior edges.  Replaces solver.prolongation

@@ -203,17 +203,18 @@ def gs_sequence(ldir, ex, ey, ez, sx, sy, sz, eta_x, eta_y, eta_z, zeta, hx, hy,
 
 
 # schedule constants of the CUDA point smoother (csrc/kernels.h, csrc/gs_point.cu)
-TILE = (16, 8, 8)
+TILE = (64, 4, 4)            # default; tests pass the library's emg3d_b200_point_tile_shape
 TILE_MIN_NODES = 300000
 
 
-def color_sequence(ldir, shape, nu, tile_variant=0):
+def color_sequence(ldir, shape, nu, tile_variant=0, tile=None):
     """Block sequence of ``nu`` multicolour sweeps as the CUDA kernels run them.
 
     Point smoother: 8 parity classes of (ix-1, iy-1, iz-1), class index
     ``px + 2 py + 4 pz``; line smoothers: 4 classes ``pp + 2 pq`` of the
-    transverse node indices (``tile_variant``: node order inside a tile of the
-    tile-fused point smoother, see emg3d_b200_point_tile_schedule in the C header).
+    transverse node indices (``tile_variant`` / ``tile``: node order inside a tile and
+    tile shape of the tile-fused point smoother, see emg3d_b200_point_tile_schedule /
+    _shape in the C header).
     Odd sweeps run the classes in descending order,
     even sweeps ascending (the first sweep of the reference is the descending
     one, core.py:301, 311).
@@ -228,8 +229,8 @@ def color_sequence(ldir, shape, nu, tile_variant=0):
             # TILE nodes coloured by tile-index parity; per tile colour every
             # tile runs its 8 node colours; both orders reverse on odd sweeps
             nx, ny, nz = shape
-            tx, ty, tz = TILE
-            ntile = [-(-(n - 1) // t) for n, t in zip(shape, TILE)]
+            tx, ty, tz = tile or TILE
+            ntile = [-(-(n - 1) // t) for n, t in zip(shape, (tx, ty, tz))]
             classes = list(range(7, -1, -1) if back else range(8))
             if tile_variant == 1:
                 # y-marching tiles: per tile colour, 4 column colours (parity of ix,

@@ -117,6 +117,14 @@ def _tile_variant():
     return v.value
 
 
+def _tile_shape():
+    import ctypes
+    from emg3d_b200 import _lib
+    t = (ctypes.c_int * 3)()
+    _lib.check(_lib.load().emg3d_b200_point_tile_shape(t))
+    return tuple(t)
+
+
 @pytest.mark.parametrize('ldir', [0, 1, 2, 3])
 @pytest.mark.parametrize('order', ['lex', 'color'])
 def test_gauss_seidel_vs_oracle(core, ldir, order):
@@ -131,7 +139,8 @@ def test_gauss_seidel_vs_oracle(core, ldir, order):
             if order == 'lex':
                 ofn(*split_field(shape, e_cpu), *split_field(shape, c['s']), *_margs(c), nu)
             else:
-                seq = oracle.color_sequence(ldir, shape, nu, tile_variant=_tile_variant())
+                seq = oracle.color_sequence(ldir, shape, nu, tile_variant=_tile_variant(),
+                                            tile=_tile_shape())
                 oracle.gs_sequence(ldir, *split_field(shape, e_cpu), *split_field(shape, c['s']),
                                    *_margs(c), seq)
             assert rel_err(e_gpu, e_cpu) < TOL_GS[ldir], (shape, nu)
