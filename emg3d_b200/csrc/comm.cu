@@ -422,6 +422,15 @@ int emg3d_b200_p2p_status(int* status) {
 }
 
 int emg3d_b200_p2p_shutdown(void) {
+    if (g_p2p.flags && emg3d_b200_internal_stream()) {
+        // back to the initial state (all flags 0, sequence number 1), so that a later
+        // communicator in this process starts in step with its new neighbours
+        cudaStream_t st = (cudaStream_t)emg3d_b200_internal_stream();
+        u64 init[8] = {0, 0, 0, 0, 1, 0, 0, 0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyAsync(g_p2p.flags, init, sizeof init, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+    }
     for (auto& o : g_p2p.opened) cudaIpcCloseMemHandle(o.second);
     g_p2p.opened.clear();
     g_p2p.slots.clear();
