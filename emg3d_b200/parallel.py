@@ -355,7 +355,7 @@ class DistributedMultigrid:
     """
 
     def __init__(self, model, sfield, comm, n_dist=None, order=None):
-        from emg3d_b200 import _lib, core, fields, meshes, models, solver
+        from emg3d_b200 import _lib, core, meshes, models, solver
         self._lib, self._solver = _lib, solver
         self.comm, self.rank, self.nranks = comm, comm.rank, comm.nranks
         self._slots = {}                             # device pointer -> peer-memory slot

@@ -3,7 +3,6 @@ Used under ncu (see profiles/README.md); prints nothing that is a bench value.""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import emg3d_b200 as eb
 from emg3d_b200 import _lib, solver, recipes
 
