@@ -172,3 +172,131 @@ def test_edge_curl_factor_and_magnetic_field(golden):
         oracle.edge_curl_factor(*split_faces(shape, h), *split_field(shape, c['e']),
                                 c['hx'], c['hy'], c['hz'], vm.zeta / smu0)
         assert rel_err(h, c['h']) < 1e-14
+
+
+@pytest.mark.parametrize('d', [0, 1, 2])
+def test_line_system_structure_and_reduced_elimination(golden, d):
+    """The algebra the CUDA line smoothers rely on (csrc/gs_line.cu),
+    checked on the operator itself: in the system of one grid line a line edge L_i
+    couples only to the transverse edges at its two end nodes, with opposite signs
+    (c_i = -f_i); transverse edges of neighbouring nodes couple diagonally; and
+    eliminating the L_i first leaves a block-tridiagonal system of 4x4 blocks with
+    E_m = diag(d) + f f^T / dL whose forward / backward recurrences reproduce the dense
+    solve of the line system (= what the reference's banded LDL^T computes)."""
+    gk = golden('kernels')
+    c = kernel_case(gk, 0)                                 # (6, 4, 8), complex, triaxial
+    shape = c['shape']
+    args = (c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'], c['hx'], c['hy'], c['hz'])
+    p, q = (1 if d == 0 else 0), (1 if d == 2 else 2)
+    N = shape[d]
+    tp, tq = 2, 3                                          # an interior line
+    offs, shp = [], []
+    for comp in range(3):
+        sh = tuple(shape[a] + (a != comp) for a in range(3))
+        offs.append(sum(int(np.prod(x)) for x in shp))
+        shp.append(sh)
+
+    def eidx(comp, idx):
+        sh = shp[comp]
+        return offs[comp] + idx[0] + sh[0] * (idx[1] + sh[1] * idx[2])
+
+    def pos(**kw):
+        i = [0, 0, 0]
+        for a, v in kw.items():
+            i[int(a[1])] = v
+        return i
+
+    L = [eidx(d, pos(**{f'a{d}': i, f'a{p}': tp, f'a{q}': tq})) for i in range(N)]
+    T = [[eidx(p, pos(**{f'a{d}': m, f'a{p}': tp - 1, f'a{q}': tq})),
+          eidx(p, pos(**{f'a{d}': m, f'a{p}': tp, f'a{q}': tq})),
+          eidx(q, pos(**{f'a{d}': m, f'a{p}': tp, f'a{q}': tq - 1})),
+          eidx(q, pos(**{f'a{d}': m, f'a{p}': tp, f'a{q}': tq}))] for m in range(N + 1)]
+    n_all = c['e'].size
+
+    def apply_A(e):
+        r = np.zeros(n_all, dtype=complex)
+        oracle.amat_x(*split_field(shape, r), *split_field(shape, e), *args)
+        return -r                                           # amat_x: r -= A e
+
+    unknowns = L + [j for m in range(1, N) for j in T[m]]
+    cols = {}
+    for j in unknowns:
+        e = np.zeros(n_all, dtype=complex)
+        e[j] = 1.0
+        cols[j] = apply_A(e)
+    A = lambda i, j: cols[j][i]
+    scale = max(abs(A(j, j)) for j in unknowns)
+    # structure
+    for i in range(N):
+        for j in range(N):
+            if i != j:
+                assert abs(A(L[i], L[j])) == 0
+        for m in range(1, N):
+            for k in range(4):
+                v = A(L[i], T[m][k])
+                if m not in (i, i + 1):
+                    assert abs(v) == 0
+        if 1 <= i and i + 1 <= N - 1:
+            f = np.array([A(L[i], T[i][k]) for k in range(4)])
+            cc = np.array([A(L[i], T[i + 1][k]) for k in range(4)])
+            assert np.all(np.abs(f.imag) < 1e-15 * scale) and np.allclose(cc, -f, rtol=1e-13, atol=0)
+    for m in range(2, N):
+        B = np.array([[A(T[m][r], T[m - 1][k]) for k in range(4)] for r in range(4)])
+        assert np.all(np.abs(B - np.diag(np.diag(B))) == 0) and np.all(np.abs(B.imag) < 1e-15 * scale)
+
+    # right-hand side of the line system for the golden field: b = s - A e with the
+    # line's unknowns removed from e
+    e0 = c['e'].copy()
+    e0[unknowns] = 0
+    b_all = c['s'] - apply_A(e0)
+    M = np.array([[A(i, j) for j in unknowns] for i in unknowns])
+    x_dense = np.linalg.solve(M, b_all[unknowns])
+
+    # reduced elimination (fixed end-plane values are already inside b here)
+    dL = np.array([A(L[i], L[i]) for i in range(N)])
+    bL = np.array([b_all[L[i]] for i in range(N)])
+    # couplings of L_i to the transverse edges at its lower (f) and upper (cu) node
+    f = [np.array([A(L[i], T[i][k]) for k in range(4)]).real if i >= 1 else None for i in range(N)]
+    cu = [np.array([A(L[i], T[i + 1][k]) for k in range(4)]).real if i + 1 <= N - 1 else None
+          for i in range(N)]
+    Tsol = {}
+    X, g = {}, {}
+    for m in range(1, N):
+        C = np.array([[A(T[m][r], T[m][k]) for k in range(4)] for r in range(4)])
+        D = C - np.outer(cu[m - 1], cu[m - 1]) / dL[m - 1]
+        r = np.array([b_all[j] for j in T[m]]) - cu[m - 1] * bL[m - 1] / dL[m - 1]
+        if m <= N - 1 and f[m] is not None:
+            D = D - np.outer(f[m], f[m]) / dL[m]
+            r = r - f[m] * bL[m] / dL[m]
+        if m >= 2:
+            dk = np.array([A(T[m][k], T[m - 1][k]) for k in range(4)]).real
+            E = np.diag(dk) + np.outer(f[m - 1], f[m - 1]) / dL[m - 1]
+            np.testing.assert_allclose(E, np.diag(dk) - np.outer(cu[m - 1], f[m - 1]) / dL[m - 1],
+                                       rtol=1e-13)
+            D = D - E @ X[m - 1] @ E
+            r = r - E @ g[m - 1]
+        X[m] = np.linalg.inv(D)
+        g[m] = X[m] @ r
+    for m in range(N - 1, 0, -1):
+        if m == N - 1:
+            Tsol[m] = g[m]
+        else:
+            dk = np.array([A(T[m + 1][k], T[m][k]) for k in range(4)]).real
+            E = np.diag(dk) + np.outer(f[m], f[m]) / dL[m]
+            Tsol[m] = g[m] - X[m] @ (E @ Tsol[m + 1])
+    Lsol = np.zeros(N, dtype=complex)
+    for i in range(N):
+        acc = bL[i]
+        if i >= 1:
+            acc = acc - f[i] @ Tsol[i]
+        if i + 1 <= N - 1:
+            acc = acc - cu[i] @ Tsol[i + 1]
+        Lsol[i] = acc / dL[i]
+    x_red = np.r_[Lsol, np.concatenate([Tsol[m] for m in range(1, N)])]
+    assert rel_err(x_red, x_dense) < 1e-10
+
+    # and the dense solve is what one line relaxation of the oracle does
+    e1 = c['e'].copy()
+    oracle.gs_sequence(d + 1, *split_field(shape, e1), *split_field(shape, c['s']), *args,
+                       np.array([[tp, tq]], dtype=np.int32))
+    assert rel_err(e1[unknowns], x_dense) < 1e-10
