@@ -300,3 +300,110 @@ def test_line_system_structure_and_reduced_elimination(golden, d):
     oracle.gs_sequence(d + 1, *split_field(shape, e1), *split_field(shape, c['s']), *args,
                        np.array([[tp, tq]], dtype=np.int32))
     assert rel_err(e1[unknowns], x_dense) < 1e-10
+
+
+def test_orderings_respect_the_block_interactions():
+    """What the parallel orderings of the CUDA smoothers assume,
+    checked on the operator: two point blocks (nodes) interact -- share an edge or are
+    coupled by A -- only if they are face or face-diagonal neighbours; then the
+    hyperplane index t = ix + 2 iy + 3 iz differs with the sign of the lexicographic
+    order (so hyperplane-by-hyperplane == the reference's sequential sweep) and their
+    parity classes differ (8 colours are conflict-free).  Same for lines with
+    t = tp + 2 tq and 4 colours; 2 colours would not be enough."""
+    rng = np.random.default_rng(0)
+    shape = (5, 4, 6)
+    g = mg.Grid([rng.uniform(1, 2, n) for n in shape])
+    vm = mg.VolumeModel(g, rng.uniform(1, 10, shape), rng.uniform(1, 10, shape),
+                        rng.uniform(1, 10, shape), rng.uniform(1, 2, shape), None, 1.0)
+    args = (vm.eta_x, vm.eta_y, vm.eta_z, vm.zeta, *g.h)
+    n_all = g.n_edges
+    shp = [tuple(shape[a] + (a != comp) for a in range(3)) for comp in range(3)]
+    offs = [0, int(np.prod(shp[0])), int(np.prod(shp[0])) + int(np.prod(shp[1]))]
+
+    def eidx(comp, i, j, k):
+        return offs[comp] + i + shp[comp][0] * (j + shp[comp][1] * k)
+
+    nz = np.zeros((n_all, n_all), dtype=bool)
+    for j in range(n_all):
+        e = np.zeros(n_all, dtype=complex)
+        e[j] = 1.0
+        r = np.zeros(n_all, dtype=complex)
+        oracle.amat_x(*split_field(shape, r), *split_field(shape, e), *args)
+        nz[:, j] = r != 0
+    nx, ny, nzc = shape
+
+    def node_block(ix, iy, iz):
+        return {eidx(0, ix - 1, iy, iz), eidx(0, ix, iy, iz), eidx(1, ix, iy - 1, iz),
+                eidx(1, ix, iy, iz), eidx(2, ix, iy, iz - 1), eidx(2, ix, iy, iz)}
+
+    def interact(a, b):
+        return bool(a & b) or bool(nz[np.ix_(sorted(a), sorted(b))].any())
+
+    nodes = [(ix, iy, iz) for iz in range(1, nzc) for iy in range(1, ny) for ix in range(1, nx)]
+    blocks = {n: node_block(*n) for n in nodes}
+    for ia, a in enumerate(nodes):
+        for b in nodes[ia + 1:]:                               # a before b lexicographically
+            if not interact(blocks[a], blocks[b]):
+                continue
+            dx, dy, dz = (b[0] - a[0], b[1] - a[1], b[2] - a[2])
+            assert max(abs(dx), abs(dy), abs(dz)) == 1 and (dx, dy, dz).count(0) >= 1
+            assert (b[0] + 2 * b[1] + 3 * b[2]) > (a[0] + 2 * a[1] + 3 * a[2])
+            assert (dx % 2, dy % 2, dz % 2) != (0, 0, 0)
+    # x-lines: blocks = all edges touching the interior nodes of the line (+ its own edges)
+    lines = [(iy, iz) for iz in range(1, nzc) for iy in range(1, ny)]
+    lblocks = {}
+    for iy, iz in lines:
+        bl = {eidx(0, i, iy, iz) for i in range(nx)}
+        for m in range(1, nx):
+            bl |= {eidx(1, m, iy - 1, iz), eidx(1, m, iy, iz), eidx(2, m, iy, iz - 1), eidx(2, m, iy, iz)}
+        lblocks[(iy, iz)] = bl
+    diagonal_pairs = 0
+    for ia, a in enumerate(lines):
+        for b in lines[ia + 1:]:
+            if not interact(lblocks[a], lblocks[b]):
+                continue
+            dp, dq = b[0] - a[0], b[1] - a[1]
+            assert max(abs(dp), abs(dq)) == 1
+            assert b[0] + 2 * b[1] > a[0] + 2 * a[1]
+            assert (dp % 2, dq % 2) != (0, 0)
+            diagonal_pairs += abs(dp) == 1 and abs(dq) == 1
+    assert diagonal_pairs > 0          # diagonal neighbours interact: red-black is not enough
+
+
+def test_point_block_structure():
+    """Structure of the 6x6 node system the CUDA point smoother exploits
+    (csrc/gs_point.cu NodeSys): the two x-edges do not couple, neither do the two y-
+    nor the two z-edges, all off-diagonal entries are real, and eliminating the x-edges
+    first (a 4x4 Schur complement) reproduces the dense solve."""
+    rng = np.random.default_rng(1)
+    shape = (4, 5, 3)
+    g = mg.Grid([rng.uniform(1, 2, n) for n in shape])
+    vm = mg.VolumeModel(g, rng.uniform(1, 10, shape), rng.uniform(1, 10, shape),
+                        rng.uniform(1, 10, shape), rng.uniform(1, 2, shape),
+                        rng.uniform(1, 5, shape), 2.0)
+    args = (vm.eta_x, vm.eta_y, vm.eta_z, vm.zeta, *g.h)
+    n_all = g.n_edges
+    shp = [tuple(shape[a] + (a != comp) for a in range(3)) for comp in range(3)]
+    offs = [0, int(np.prod(shp[0])), int(np.prod(shp[0])) + int(np.prod(shp[1]))]
+    eidx = lambda comp, i, j, k: offs[comp] + i + shp[comp][0] * (j + shp[comp][1] * k)
+    ix, iy, iz = 2, 3, 1
+    blk = [eidx(0, ix - 1, iy, iz), eidx(0, ix, iy, iz), eidx(1, ix, iy - 1, iz),
+           eidx(1, ix, iy, iz), eidx(2, ix, iy, iz - 1), eidx(2, ix, iy, iz)]
+    M = np.zeros((6, 6), dtype=complex)
+    for c, j in enumerate(blk):
+        e = np.zeros(n_all, dtype=complex)
+        e[j] = 1.0
+        r = np.zeros(n_all, dtype=complex)
+        oracle.amat_x(*split_field(shape, r), *split_field(shape, e), *args)
+        M[:, c] = -r[blk]
+    assert np.allclose(M, M.T, rtol=1e-14, atol=0)                       # complex symmetric
+    assert M[0, 1] == 0 and M[2, 3] == 0 and M[4, 5] == 0
+    off = M - np.diag(np.diag(M))
+    assert np.all(off.imag == 0)
+    b = rng.standard_normal(6) + 1j * rng.standard_normal(6)
+    x = np.linalg.solve(M, b)
+    dX, B, C = np.diag(M)[:2], M[:2, 2:].real, M[2:, 2:]
+    S = C - B.T @ np.diag(1 / dX) @ B
+    xT = np.linalg.solve(S, b[2:] - B.T @ (b[:2] / dX))
+    xX = (b[:2] - B @ xT) / dX
+    assert rel_err(np.r_[xX, xT], x) < 1e-12
