@@ -406,4 +406,8 @@ def test_point_block_structure():
     S = C - B.T @ np.diag(1 / dX) @ B
     xT = np.linalg.solve(S, b[2:] - B.T @ (b[:2] / dX))
     xX = (b[:2] - B @ xT) / dX
-    assert rel_err(np.r_[xX, xT], x) < 1e-12
+    # the node system is ill-conditioned (curl-curl is singular on the gradient of the
+    # node's potential; only the eta term regularises it), so two elimination orders
+    # agree to cond x eps only -- the reason for the 1e-11 / 2e-10 bars of the GPU tests
+    assert np.linalg.cond(M) > 1e3
+    assert rel_err(np.r_[xX, xT], x) < 1e-16 * np.linalg.cond(M) * 10
