@@ -350,3 +350,21 @@ def test_process_map_binds_one_device_per_worker():
     assert {d for _, d, _ in out} <= {3, 5} and all(str(d) == env for _, d, env in out)
     with pytest.raises(ValueError, match='at least one GPU'):
         batch.process_map(batch._echo_device, [1], devices=[])
+
+
+def test_bench_work_accounting_and_recorded_traffic():
+    """bench.py: W = sum over levels of cells x sweeps for the plain V(2,2) cycle
+    (76 695 816 at 256^3, 9 586 952 at 128^3, 149 768 at 32^3) and the
+    DRAM traffic of the roofline kernel parsed from the committed ncu summary."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        'bench', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.vcycle_work((256, 256, 256)) == 76695816
+    assert bench.vcycle_work((128, 128, 128)) == 9586952
+    assert bench.vcycle_work((32, 32, 32)) == 149768
+    t = bench.recorded_traffic('gs_point_tile_kernel')
+    assert t is not None and 3.0e8 < t < 1.5e9            # algorithmic: 3.86e8 bytes per launch
+    assert bench.recorded_traffic('no_such_kernel') is None
