@@ -104,7 +104,7 @@ def test_gauss_seidel_lex_golden(core, golden, ldir):
 
 
 # shapes chosen so that both the single-block path (small grids) and the
-# multi-launch path (> 4096 interior nodes / > 1024 lines) are exercised
+# multi-launch path (> 512 interior nodes / > 1024 lines) are exercised
 BIG = [((24, 20, 18), True), ((6, 40, 36), True), ((38, 5, 37), False), ((36, 35, 4), True),
        ((12, 11, 9), False)]
 
