@@ -156,6 +156,43 @@ def test_pull_plan_equals_send_recv_pairs(nz, nranks, n_dist):
             np.testing.assert_array_equal(a[r], b[r])
 
 
+@pytest.mark.parametrize('nz,nranks,n_dist', [(64, 2, 3), (64, 4, 2), (96, 3, 2)])
+def test_owned_plane_window_equals_owned_ranges(nz, nranks, n_dist):
+    """The residual kernel sums |r|^2 over the planes [own0, own1) of the rank's z-window
+    (emg3d_b200_level_set_owned: x/y-edges on those node planes, z-edges of the layers whose
+    upper plane is among them).  That set must be exactly the element ranges of
+    `owned_ranges`, which the unfused norm (sum_owned) uses, and the ranks' sets must
+    partition the global field."""
+    nx, ny = 5, 3
+    part = parallel.SlabPartition(nz, nranks, n_dist)
+    for level in range(n_dist):
+        nzl = part.nz_level(level)
+        total = 0
+        for rank in range(nranks):
+            lo, hi = part.local(level, rank)
+            p0, p1 = part.owned(level, rank)
+            z0 = 0 if rank == 0 else p0 - 1 - lo           # window start (parallel._DLevel)
+            own0, own1 = p0 - lo - z0, p1 - lo - z0
+            nzw = hi - lo - z0                              # cells of the window
+            assert 0 <= own0 < own1 <= nzw + 1
+            nloc = hi - lo
+            px, py, pz = nx * (ny + 1), (nx + 1) * ny, (nx + 1) * (ny + 1)
+            mask = np.zeros(px * (nloc + 1) + py * (nloc + 1) + pz * nloc, dtype=bool)
+            ox, oy, oz = 0, px * (nloc + 1), px * (nloc + 1) + py * (nloc + 1)
+            for k in range(nzw + 1):                        # window-local plane k = local plane z0 + k
+                if own0 <= k < own1:
+                    mask[ox + px * (z0 + k):ox + px * (z0 + k + 1)] = True
+                    mask[oy + py * (z0 + k):oy + py * (z0 + k + 1)] = True
+                if k < nzw and own0 <= k + 1 < own1:
+                    mask[oz + pz * (z0 + k):oz + pz * (z0 + k + 1)] = True
+            want = np.zeros_like(mask)
+            for off, n in parallel.owned_ranges(part, level, rank, nx, ny):
+                want[off:off + n] = True
+            np.testing.assert_array_equal(mask, want)
+            total += int(mask.sum())
+        assert total == px * (nzl + 1) + py * (nzl + 1) + pz * nzl
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
