@@ -78,6 +78,7 @@ _SIGNATURES = {
     'emg3d_b200_apply': (c_int, [c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_point_tile_schedule': (c_int, [POINTER(c_int)]),
     'emg3d_b200_point_tile_shape': (c_int, [POINTER(c_int)]),
+    'emg3d_b200_line_seg_mask': (c_int, [c_int, POINTER(c_int)]),
     'emg3d_b200_magnetic_field': (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double]),
     'emg3d_b200_host_edge_curl_factor': (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 10),
     'emg3d_b200_residual': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -178,6 +179,14 @@ def launch_count():
     n = c_longlong(0)
     check(load().emg3d_b200_launch_count(byref(n)))
     return n.value
+
+
+def line_seg_mask(mask=-1):
+    """Set (mask >= 0) / query which line directions use the segment-parallel kernels
+    (bit a = axis a; see emg3d_b200_line_seg_mask in the C header).  Returns the previous mask."""
+    prev = ctypes.c_int(0)
+    check(load().emg3d_b200_line_seg_mask(int(mask), byref(prev)))
+    return prev.value
 
 
 def _hptr(a):

@@ -61,6 +61,7 @@ struct emg3d_b200_level {
     const void* eta[3];
     const double* zeta;
     void* fac[3];        // cached line factorisations (device), per direction
+    void* fac2[3];       // cached data of the segment-parallel line kernels (gs_line_seg.cu)
     void* diag;          // cached diagonal of A per edge (device), point smoother
     double* scratch;     // residual-norm partials
     double* norm2;       // device scalar
@@ -94,15 +95,22 @@ static cudaError_t malloc_evicting(void** p, size_t nbytes, const emg3d_b200_lev
             if (n_cells(lv->d) < EVICT_MIN_CELLS) continue;
             const size_t el = lv->cplx == 0 ? sizeof(double) : sizeof(cplx);
             for (int a = 0; a < 3; ++a) {
-                if (!lv->fac[a] || (lv == keep && a == keep_dir)) continue;
-                const size_t b = (size_t)line_factor_elems(lv->d, a) * el;
-                if (b > best_bytes) { best = lv; best_dir = a; best_bytes = b; }
+                if (lv == keep && a == keep_dir) continue;
+                if (lv->fac[a]) {
+                    const size_t b = (size_t)line_factor_elems(lv->d, a) * el;
+                    if (b > best_bytes) { best = lv; best_dir = a; best_bytes = b; }
+                }
+                if (lv->fac2[a]) {
+                    const size_t b = (size_t)line_seg_elems(lv->d, a) * el;
+                    if (b > best_bytes) { best = lv; best_dir = a + 3; best_bytes = b; }
+                }
             }
         }
         if (!best) return cudaErrorMemoryAllocation;
         cudaStreamSynchronize(g_stream);
-        cudaFree(best->fac[best_dir]);
-        best->fac[best_dir] = nullptr;
+        void** victim = best_dir < 3 ? &best->fac[best_dir] : &best->fac2[best_dir - 3];
+        cudaFree(*victim);
+        *victim = nullptr;
         e = cudaMalloc(p, nbytes);
     }
     return e;
@@ -472,6 +480,8 @@ int emg3d_b200_level_drop_factors(emg3d_b200_level* lv) {
     for (int a = 0; a < 3; ++a) {
         if (lv->fac[a]) cudaFree(lv->fac[a]);
         lv->fac[a] = nullptr;
+        if (lv->fac2[a]) cudaFree(lv->fac2[a]);
+        lv->fac2[a] = nullptr;
     }
     return 0;
 }
@@ -649,7 +659,20 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
         return 0;
     }
     const int dir = ldir - 1;
-    if (!lv->fac[dir]) {
+    const size_t el = lv->cplx ? sizeof(cplx) : sizeof(double);
+    // long lines in multicolour order: segment-parallel kernels with their own cached data
+    const bool seg = (order & 0xff) == ORDER_COLOR && line_seg_elems(lv->d, dir) > 0;
+    if (seg && !lv->fac2[dir]) {
+        const size_t nbytes = (size_t)line_seg_elems(lv->d, dir) * el;
+        cudaError_t me = malloc_evicting(&lv->fac2[dir], nbytes, lv, dir);
+        if (me != cudaSuccess) { lv->fac2[dir] = nullptr; return fail("cudaMalloc (line factorisation)", me); }
+        if (lv->cplx)
+            launch_line_seg_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac2[dir], g_stream);
+        else
+            launch_line_seg_factor<double>(model_of<double>(lv), dir, (double*)lv->fac2[dir], g_stream);
+        CK_LAUNCH("line_seg_factor");
+    }
+    if (!seg && !lv->fac[dir]) {
         size_t nbytes;
         emg3d_b200_level_factor_bytes(lv, ldir, &nbytes);
         if (nbytes == 0) return 0;
@@ -664,18 +687,25 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
             launch_line_factor<double>(model_of<double>(lv), dir, (double*)lv->fac[dir], g_stream);
         CK_LAUNCH("line_factor");
     }
+    const void* f2 = seg ? lv->fac2[dir] : nullptr;
     if (lv->cplx)
-        launch_gs_line<cplx>(model_of<cplx>(lv), dir, (const cplx*)lv->fac[dir], (cplx*)e, (const cplx*)s,
-                             nu, order, g_stream);
+        launch_gs_line<cplx>(model_of<cplx>(lv), dir, (const cplx*)lv->fac[dir], (const cplx*)f2, (cplx*)e,
+                             (const cplx*)s, nu, order, g_stream);
     else
-        launch_gs_line<double>(model_of<double>(lv), dir, (const double*)lv->fac[dir], (double*)e,
-                               (const double*)s, nu, order, g_stream);
+        launch_gs_line<double>(model_of<double>(lv), dir, (const double*)lv->fac[dir], (const double*)f2,
+                               (double*)e, (const double*)s, nu, order, g_stream);
     CK_LAUNCH("gauss_seidel_line");
     return 0;
 }
 
 int emg3d_b200_point_tile_schedule(int* variant) {
     *variant = point_tile_schedule();
+    return 0;
+}
+
+int emg3d_b200_line_seg_mask(int mask, int* previous) {
+    const int prev = line_seg_mask(mask);
+    if (previous) *previous = prev;
     return 0;
 }
 

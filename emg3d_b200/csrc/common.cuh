@@ -74,19 +74,6 @@ __device__ __forceinline__ cplx ldg(const cplx* p) {
     return make_c(v.x, v.y);
 }
 
-// ---- cp.async (LDGSTS): global -> shared without a register round trip --------
-__device__ __forceinline__ void cp_async(cplx* dst, const cplx* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async(double* dst, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ---------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -118,8 +105,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned nb
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+// nbytes (multiple of 16) from global memory into the L2, no destination
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned nbytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(nbytes) : "memory");
 }
 
 // ---- grid / model description passed by value to kernels -------------------

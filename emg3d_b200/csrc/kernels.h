@@ -37,9 +37,21 @@ void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st);
 int64_t line_factor_elems(const Dims& d, int dir);     // number of T elements
 template <typename T>
 void launch_line_factor(const Model<T>& m, int dir, T* fac, cudaStream_t st);
+// `fac`: factors in the one-thread-per-line layout (lexicographic order, small grids, and the
+// multicolour order wherever `fac2` is null); `fac2`: cached data of the segment-parallel
+// kernels (gs_line_seg.cu; multicolour order on long lines) or null
 template <typename T>
-void launch_gs_line(const Model<T>& m, int dir, const T* fac, T* e, const T* s, int nu, int order,
-                    cudaStream_t st);
+void launch_gs_line(const Model<T>& m, int dir, const T* fac, const T* fac2, T* e, const T* s, int nu,
+                    int order, cudaStream_t st);
+// segment-parallel line smoother (one warp per line, factors staged on chip by TMA)
+int line_seg_mask(int mask);                           // set (mask >= 0) / query the direction mask
+int line_seg_qp(const Dims& d, int dir);               // lanes per line; 0 = kernel not used for this shape
+int64_t line_seg_elems(const Dims& d, int dir);        // number of T elements of its cached data
+template <typename T>
+void launch_line_seg_factor(const Model<T>& m, int dir, T* fac2, cudaStream_t st);
+template <typename T>
+void launch_gs_line_seg_color(const Model<T>& m, int dir, const T* fac2, T* e, const T* s, int c,
+                              cudaStream_t st);
 
 // transfer operators; cflag[a] = 1 if axis a is coarsened
 template <typename T>

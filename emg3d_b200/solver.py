@@ -232,14 +232,26 @@ class _Level:
         return child
 
 
+_DIGEST_POOL = None
+
+
+def _digest_pool():
+    global _DIGEST_POOL
+    if _DIGEST_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _DIGEST_POOL = ThreadPoolExecutor(max_workers=8)
+    return _DIGEST_POOL
+
+
 class Workspace:
     """Device-resident state that can be reused by consecutive :func:`solve` calls.
 
     ``solve(model, sfield, workspace=ws)`` keeps the coefficient arrays, the
     coarse-grid hierarchy and the cached line factorisations of ``model`` on the
     GPU, keyed by the model object, the Laplace parameter of ``sfield`` and the
-    dtype.  A cheap fingerprint of the property arrays (buffer address, shape and
-    a strided checksum) guards against models that were modified in place.
+    dtype.  A checksum over every element of the property arrays and the cell widths
+    guards against models that were modified in place (``model.property_x[a:b] = v``
+    between two solves rebuilds the hierarchy).
     """
 
     def __init__(self, max_models=2, pinned_result=False):
@@ -254,16 +266,37 @@ class Workspace:
         self._buffers = {}
 
     @staticmethod
-    def _fingerprint(model):
-        fp = [tuple(float(h.sum()) for h in model.grid.h)]
+    def _digest(a):
+        """Checksum over EVERY element of a property array (an in-place edit anywhere changes it):
+        wrapping sum and xor of the 64-bit patterns, evaluated in parallel chunks (NumPy
+        reductions release the GIL).  ~10 ms for a 256^3 array."""
+        a = np.asarray(a)
+        flat = a.reshape(-1, order='A')
+        if flat.dtype.itemsize % 8 or not (flat.flags.c_contiguous or flat.flags.f_contiguous):
+            flat = np.ascontiguousarray(flat, dtype=np.float64)
+        bits = flat.view(np.uint64)
+        nchunk = max(1, min(8, bits.size // (1 << 20)))
+
+        def part(k):
+            c = bits[k * bits.size // nchunk:(k + 1) * bits.size // nchunk]
+            return int(c.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(c))
+
+        if nchunk == 1:
+            parts = [part(0)]
+        else:
+            parts = list(_digest_pool().map(part, range(nchunk)))
+        total, mixed = 0, 0
+        for k, (sm, xr) in enumerate(parts):
+            total = (total + sm * (2 * k + 1)) & 0xFFFFFFFFFFFFFFFF
+            mixed ^= xr
+        return a.shape, total, mixed
+
+    @classmethod
+    def _fingerprint(cls, model):
+        fp = [tuple(np.asarray(h, dtype=np.float64).tobytes() for h in model.grid.h)]
         for name in ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r'):
             a = getattr(model, name, None)
-            if a is None:
-                fp.append(None)
-            else:
-                a = np.asarray(a)
-                flat = a.reshape(-1, order='A')
-                fp.append((a.ctypes.data, a.shape, float(flat[::4099].sum()), float(flat[-1])))
+            fp.append(None if a is None else cls._digest(a))
         fp.append(getattr(model.map, 'name', None))
         return tuple(fp)
 
@@ -435,6 +468,7 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
         d_e = _lib.DeviceArray.from_host(np.asarray(efield.field))
         _lib.check(_lib.load().emg3d_b200_pec_zero(level.handle.ptr, d_e.ptr))
         var.do_return = always_return
+        var.user_start = True       # the caller's field is the start vector (see _krylov)
         var.l2 = _dev_residual(level, d_s, d_e, norm=True)
         if var.l2 < var.tol * var.l2_refe:
             var.sslsolver = None
@@ -525,12 +559,17 @@ def _as_level(model, dtype):
     """Device level of a (Volume)model-like object; cached on the object."""
     if isinstance(model, _Level):
         return model
+    if isinstance(model, _CoarseModel):          # device-born (restriction): nothing to guard
+        return model._b200_level
+    # cached on the object, guarded by a checksum over every coefficient (a VolumeModel whose
+    # eta / zeta were edited in place gets a new device level)
+    stamp = tuple(Workspace._digest(getattr(model, n)) for n in ('eta_x', 'eta_y', 'eta_z', 'zeta'))
     cached = getattr(model, '_b200_level', None)
-    if cached is not None and cached.dtype == np.dtype(dtype):
-        return cached
+    if cached is not None and cached[0] == stamp and cached[1].dtype == np.dtype(dtype):
+        return cached[1]
     lv = _Level.from_volume_model(model, dtype)
     try:
-        model._b200_level = lv
+        model._b200_level = (stamp, lv)
     except AttributeError:
         pass
     return lv
@@ -818,6 +857,11 @@ def _krylov(lv, s, e, var):
         elif var.verb in [2, 3]:
             _print_one_liner(var, var.l2)
 
+    # When the preconditioner diverges the reference never assigns the solver's iterate
+    # (solver.py:763-768): a start field supplied by the caller keeps its (PEC-cleaned) input
+    # and only the default zero start "returns zero".  The device iterate is updated in place,
+    # so a supplied start field is kept aside.
+    x0 = e.copy() if getattr(var, 'user_start', False) else None
     try:
         if var.sslsolver == 'bicgstab':
             i = _bicgstab(lv, s, e, var, record)
@@ -825,8 +869,12 @@ def _krylov(lv, s, e, var):
             i = _scipy_krylov(lv, s, e, var, record)
     except _ConvergenceError:
         i = -1
-        e.zero()
+        if x0 is None:
+            e.zero()
+        else:
+            e.copy_from(x0)
         var.exit_message += " (returned field is zero)"
+    del x0
 
     if var.verb == 3:
         pre = 50 * " " + "\r"
@@ -1092,34 +1140,37 @@ class MGParameters:
         self._repr_lr_dir = f"{self.linerelaxation} {seq}"
         self.raw_lr_cycle = seq
 
+    # Accepted Krylov wrappers / cycle types (solver.py:1341-1381).  The messages are pinned by
+    # the reference's tests (tests/test_solver.py); the checks are table-driven here.
+    _SSLSOLVERS = ('bicgstab', 'cgs', 'gcrotmk')
+    _CYCMAX = {'V': 1, 'W': 2, 'F': 2, None: 1}
+
     def _solver_and_cycle(self):
-        solvers = ['bicgstab', 'cgs', 'gcrotmk']
-        if self.sslsolver is True:
-            self.sslsolver = 'bicgstab'
-        elif self.sslsolver is not False and self.sslsolver not in solvers:
-            raise ValueError(
-                f"`sslsolver` must be True, False, or one of {solvers}. "
-                f"Provided: {self.sslsolver!r}."
-            )
-        if self.cycle not in ['F', 'V', 'W', None]:
-            raise ValueError(
-                "`cycle` must be one of {'F';'V';'W';None}. "
-                f"Provided: {self.cycle}."
-            )
-        self.cycmax = 2 if self.cycle in ['F', 'W'] else 1
-        if not self.sslsolver and not self.cycle:
-            raise ValueError(
-                "At least `cycle` or `sslsolver` is required. Provided"
-                f"input: cycle={self.cycle}; sslsolver={self.sslsolver}."
-            )
-        self.ssl_maxit = 0
-        self._repr_maxit = f"{self.maxit}"
+        ssl = {True: 'bicgstab', False: False}.get(self.sslsolver, self.sslsolver) \
+            if isinstance(self.sslsolver, bool) else self.sslsolver
+        problems = (
+            (ssl is not False and ssl not in self._SSLSOLVERS,
+             f"`sslsolver` must be True, False, or one of {list(self._SSLSOLVERS)}. "
+             f"Provided: {self.sslsolver!r}."),
+            (self.cycle not in self._CYCMAX,
+             "`cycle` must be one of {'F';'V';'W';None}. " f"Provided: {self.cycle}."),
+            (not ssl and not self.cycle,
+             "At least `cycle` or `sslsolver` is required. Provided"
+             f"input: cycle={self.cycle}; sslsolver={ssl}."),
+        )
+        for bad, message in problems:
+            if bad:
+                raise ValueError(message)
+        self.sslsolver = ssl
+        self.cycmax = self._CYCMAX[self.cycle]
+        # With a Krylov wrapper `maxit` bounds the Krylov iterations and each preconditioner
+        # call runs one round of the sc / lr cycling patterns (solver.py:1370-1381).
         self.maxcycle = max(len(self.raw_sc_cycle), len(self.raw_lr_cycle))
-        if self.sslsolver:
-            self.ssl_maxit = self.maxit
-            if self.cycle is not None:
-                self.maxit = self.maxcycle
-                self._repr_maxit += f" ({self.maxit})"
+        self._repr_maxit = f"{self.maxit}"
+        self.ssl_maxit = self.maxit if ssl else 0
+        if ssl and self.cycle is not None:
+            self.maxit = self.maxcycle
+            self._repr_maxit += f" ({self.maxit})"
 
 
 class RegularGridProlongator:
@@ -1173,34 +1224,33 @@ class _ConvergenceError(Exception):
 
 
 def _terminate(var, l2_last, l2_stag, it):
-    """Termination criteria of the multigrid iteration (solver.py:1591-1664)."""
-    finished = sslabort = False
-    if l2_last < var.tol * var.l2_refe:
-        var.exit_message = "CONVERGED"
-        finished = True
-    elif l2_last > 10 * var.l2_refe or not np.isfinite(l2_last):
-        var.exit_message = "DIVERGED"
-        finished = sslabort = True
-    elif it > 2 and l2_last >= l2_stag:
-        var.exit_message = "STAGNATED"
-        finished = sslabort = True
-    elif it == var.maxit:
-        if not var.sslsolver:
-            var.exit_message = "MAX. ITERATION REACHED, NOT CONVERGED"
-        finished = True
+    """Termination criteria of the multigrid iteration (solver.py:1591-1664).
 
-    if finished:
-        if var.sslsolver and sslabort:
+    One ordered rule table: (condition, message, fatal).  The first rule that holds ends the
+    iteration; a *fatal* outcome inside a Krylov run (multigrid as preconditioner) aborts the
+    Krylov solver through `_ConvergenceError`; reaching `maxit` as preconditioner is the normal
+    end of a preconditioner call and sets no message.  ``l2_refe`` is the global ||b||, also
+    inside the preconditioner (solver.py:1622 with 714-719).
+    """
+    rules = (
+        (l2_last < var.tol * var.l2_refe, "CONVERGED", False),
+        (l2_last > 10 * var.l2_refe or not np.isfinite(l2_last), "DIVERGED", True),
+        (it > 2 and l2_last >= l2_stag, "STAGNATED", True),
+        (it == var.maxit, None if var.sslsolver else "MAX. ITERATION REACHED, NOT CONVERGED", False),
+    )
+    hit = next((rule for rule in rules if rule[0]), None)
+    if hit is None:
+        return False
+    _, message, fatal = hit
+    if message is not None:
+        var.exit_message = message
+    if var.sslsolver:
+        if fatal:
             raise _ConvergenceError
-        elif not var.sslsolver:
-            if var.verb == 3:
-                add = 50 * " " + "\r"
-            elif var.verb < 5:
-                add = "\n"
-            else:
-                add = ""
-            var.cprint(add + "   > " + var.exit_message, 2)
-    return finished
+        return True
+    lead = {3: 50 * " " + "\r"}.get(var.verb, "\n" if var.verb < 5 else "")
+    var.cprint(lead + "   > " + var.exit_message, 2)
+    return True
 
 
 def _restrict_model_parameters(param, sc_dir):

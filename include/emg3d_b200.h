@@ -134,6 +134,15 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
 int emg3d_b200_point_tile_schedule(int* variant);
 /* tile shape (nodes along x, y, z) of that schedule */
 int emg3d_b200_point_tile_shape(int* txyz);
+/* Line smoothers in multicolour order: bit a of the mask selects, for lines along axis a
+ * (0 = x, 1 = y, 2 = z), the segment-parallel kernel (one warp per line, factors staged on
+ * chip by TMA bulk copies, csrc/gs_line_seg.cu) on lines of 66 .. 257 cells instead of the
+ * one-thread-per-line kernel (csrc/gs_line.cu).  Same colour sequence, same results to
+ * rounding.  mask < 0 only queries.  Default 1 (x-lines), or the environment variable
+ * EMG3D_B200_LINE_SEG.  Cached factorisations of existing levels are not converted: set the
+ * mask before the first smoothing call or drop the factors.  *previous (may be NULL)
+ * receives the mask in force before the call. */
+int emg3d_b200_line_seg_mask(int mask, int* previous);
 /* coarse_s = R r_fine.  Replaces core.restrict (core.py:1620-1621).            */
 int emg3d_b200_restrict(emg3d_b200_level* coarse, const void* r_fine, void* s_coarse);
 /* e_fine += P e_coarse on interior edges.  Replaces solver.prolongation

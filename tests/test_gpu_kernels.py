@@ -146,6 +146,52 @@ def test_gauss_seidel_vs_oracle(core, ldir, order):
             assert rel_err(e_gpu, e_cpu) < TOL_GS[ldir], (shape, nu)
 
 
+# long lines: the segment-parallel kernels (csrc/gs_line_seg.cu: one warp per line, 8 blocks per
+# lane, jump-matrix scans) take over for 66 .. 257 cells along the line.  Shapes are given for
+# x-lines and permuted for y / z; they cover 16 and 32 lanes per line, full and partial last
+# segments, one block in the last segment, odd line counts (padding line of a two-line warp).
+LONG = [((130, 7, 6), True), ((257, 4, 5), True), ((100, 6, 5), False), ((66, 5, 4), True),
+        ((129, 3, 4), False), ((200, 4, 3), True)]
+
+
+def _perm(shape, ldir):
+    n, a, b = shape
+    return {1: (n, a, b), 2: (a, n, b), 3: (a, b, n)}[ldir]
+
+
+@pytest.mark.parametrize('ldir', [1, 2, 3])
+def test_long_lines_segment_kernel_vs_oracle(core, ldir):
+    """Multicolour order on long lines: segment-parallel kernel == oracle in the same colour
+    sequence == the one-thread-per-line kernel, with PEC and with non-zero boundary data."""
+    from emg3d_b200 import _lib
+    rng = np.random.default_rng(300 + ldir)
+    fn = getattr(core, GS[ldir])
+    prev = _lib.line_seg_mask(7)
+    try:
+        for shape0, cplx in LONG:
+            shape = _perm(shape0, ldir)
+            c = random_case(rng, shape, cplx)
+            for nonzero_bc in (False, True):
+                e0 = c['e'].copy()
+                if nonzero_bc:
+                    e0 = rng.standard_normal(e0.size) + (1j * rng.standard_normal(e0.size) if cplx else 0)
+                for nu in (1, 2):
+                    e_seg, e_thr, e_cpu = e0.copy(), e0.copy(), e0.copy()
+                    _lib.line_seg_mask(7)
+                    fn(*split_field(shape, e_seg), *split_field(shape, c['s']), *_margs(c), nu, order='color')
+                    _lib.line_seg_mask(0)
+                    fn(*split_field(shape, e_thr), *split_field(shape, c['s']), *_margs(c), nu, order='color')
+                    assert rel_err(e_seg, e_thr) < 1e-11, (shape, nonzero_bc, nu, 'seg vs thread kernel')
+                    if nonzero_bc:      # the oracle sweeps assume PEC data on the side faces
+                        continue
+                    seq = oracle.color_sequence(ldir, shape, nu)
+                    oracle.gs_sequence(ldir, *split_field(shape, e_cpu), *split_field(shape, c['s']),
+                                       *_margs(c), seq)
+                    assert rel_err(e_seg, e_cpu) < TOL_GS[ldir], (shape, nonzero_bc, nu, 'seg vs oracle')
+    finally:
+        _lib.line_seg_mask(prev)
+
+
 @pytest.mark.parametrize('order', ['lex', 'color'])
 def test_single_block_exactness(core, order):
     """On a grid with one block a sweep solves the system exactly (residual ~ 0)."""
