@@ -226,6 +226,8 @@ def main():
     ap.add_argument('--order', default='color', choices=['color', 'lex'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true',
+                    help='N > 1: skip the N-GPU against 1-GPU correctness leg')
     ap.add_argument('--cycles-only', action='store_true',
                     help='run the warm-up and timed cycles and stop (for ncu launch lists: the '
                          'launches are then those of the step, plus the one-off setup kernels)')
@@ -436,6 +438,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(128 if n >= 128 else n)
 
+    n_dist = dmg.n_dist
+    dmg.close()
+    del dmg
+    barrier()
+    parity = None if args.no_parity else distributed_parity(comm, rank, world, dist, args.order)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -457,6 +465,55 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def distributed_parity(comm, rank, world, dist, order, n=128, cycle='F', tol=1e-10):
+    """Cheap correctness leg of the N > 1 arm: the stretched triaxial model of BASELINE.json
+    configs[4] on n^3 cells, solved by the SAME distributed driver on N GPUs and by the single-GPU
+    solver on rank 0 (plain multigrid, multicolour order).  Reports the field difference and the
+    number of cycles both need to reach 1e-6; the run fails if the distributed solve does not
+    converge, differs by more than 1e-8 or needs more than one cycle more."""
+    import torch
+    import emg3d_b200 as eb
+    from emg3d_b200 import parallel, recipes
+    cfg = recipes.config('config5', n)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    sfield = eb.get_source_field(grid, cfg['source'], cfg['frequency'])
+    out = {}
+    for name, exact in (('exact', True), ('relaxed', False)):
+        dmg = parallel.DistributedMultigrid(model, sfield, comm, order=order, exact=exact)
+        info = dmg.solve(cycle=cycle, tol=tol, maxit=40)
+        field = np.zeros(grid.n_edges, dtype=complex)
+        dmg.download_owned(field)
+        t = torch.from_numpy(field.view(np.float64))
+        dist.all_reduce(t)                               # disjoint owned parts: sum = gather (gloo)
+        rel = info['error_at_cycle'] / info['ref_error']
+        out[name] = dict(field=field, it=int(info['it_mg']), exit=info['exit_message'],
+                         to_1e6=int(np.argmax(rel < 1e-6)) if (rel < 1e-6).any() else None,
+                         err_cycle1=float(rel[1]))
+        dmg.close()
+        del dmg
+        dist.barrier()
+    res = None
+    if rank == 0:
+        e1, i1 = eb.solve(model, sfield, plain=True, cycle=cycle, tol=tol, maxit=40, order=order,
+                          return_info=True)
+        rel1 = i1['error_at_cycle'] / i1['ref_error']
+        single_to = int(np.argmax(rel1 < 1e-6))
+        res = {"workload": f"BASELINE.json configs[4] model on {n}^3 cells, plain {cycle}-cycles, tol {tol:g}",
+               "single_gpu": {"cycles": int(i1['it_mg']), "cycles_to_1e-6": single_to,
+                              "rel_error_after_cycle_1": float(rel1[1])}}
+        for name in ('exact', 'relaxed'):
+            o = out[name]
+            res[name] = {"cycles": o['it'], "cycles_to_1e-6": o['to_1e6'], "exit": o['exit'],
+                         "rel_error_after_cycle_1": o['err_cycle1'],
+                         "efield_rel_diff_vs_single_gpu": float(
+                             np.linalg.norm(o['field'] - e1.field) / np.linalg.norm(e1.field))}
+        ex = res['exact']
+        res["ok"] = bool(ex['exit'] == 'CONVERGED' and ex['efield_rel_diff_vs_single_gpu'] < 1e-8
+                         and ex['cycles_to_1e-6'] is not None and ex['cycles_to_1e-6'] <= single_to + 1)
+    return res
 
 
 def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks):
@@ -585,6 +642,12 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
                        "from and the field slab downloaded to pinned host memory on every rank",
                "note": "model coefficients, slab hierarchy and NCCL communicator stay alive between steps"}
 
+    n_dist = dmg.n_dist
+    dmg.close()
+    del dmg
+    barrier()
+    parity = None if args.no_parity else distributed_parity(comm, rank, world, dist, args.order)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -598,8 +661,10 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
                        "cell_sweeps_per_step": int(work),
                        "l2": "working set 3.2 GB per GPU and step, far larger than the 126 MB L2",
                        "parallelism": f"one solve on {world} GPUs: z-slabs of {shape[2] // world} cell layers, "
-                                      f"{dmg.n_dist} distributed levels, coarser levels replicated; halo "
-                                      "exchange of E after every sweep, residual and prolongation by "
+                                      f"{n_dist} distributed levels, coarser levels replicated; halo "
+                                      "exchange of E after every half sweep (the colour classes of even "
+                                      "/ odd z-parity: a true Gauss-Seidel sweep across slabs), residual "
+                                      "and prolongation by "
                                       + ("one peer-memory kernel per exchange (CUDA IPC mapping of the "
                                          "neighbours' slabs, remote loads over NVLink, flag handshake)"
                                          if comm.p2p else "ncclSend/ncclRecv over NVLink")
@@ -608,11 +673,14 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
             "halo_exchange": {"transport": "peer-memory kernel" if comm.p2p else "nccl", "ms": halo_ms,
                               "bytes_sent_per_rank": int(halo_bytes),
                               "GBs_per_direction": halo_bytes / 2 / (halo_ms * 1e-3) / 1e9 if halo_ms else None},
+            "distributed_parity": parity,
             "gpu_launches": int(launches), "clocks": clocks, "device": _lib.device_name(),
         }
         print(json.dumps(line))
     comm.destroy()
     dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit("distributed parity leg failed: " + json.dumps(parity))
 
 
 if __name__ == '__main__':

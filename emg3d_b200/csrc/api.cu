@@ -552,6 +552,17 @@ int emg3d_b200_level_set_owned(emg3d_b200_level* lv, int plane0, int plane1) {
     return 0;
 }
 
+int emg3d_b200_level_set_zflip(emg3d_b200_level* lv, int flip) {
+    lv->d.zflip = flip ? 1 : 0;
+    return 0;
+}
+
+int emg3d_b200_point_schedule_kind(const emg3d_b200_level* lv, int* kind) {
+    const int64_t nint = (int64_t)(lv->d.n[0] - 1) * (lv->d.n[1] - 1) * (lv->d.n[2] - 1);
+    *kind = nint <= SMALL_GRID_NODES ? 0 : nint > TILE_MIN_NODES ? 2 : 1;
+    return 0;
+}
+
 int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes) {
     if (ldir < 1 || ldir > 3) return fail_msg("level_factor_bytes: ldir must be 1, 2 or 3");
     const size_t el = lv->cplx == 0 ? sizeof(double) : sizeof(cplx);

@@ -268,6 +268,7 @@ struct P2p {
     u64* peer_flags[2] = {nullptr, nullptr};
     std::vector<P2pSlot> slots;
     std::vector<std::pair<IpcBlob, char*>> opened;   // (handle, mapped base)
+    size_t n_keep = 0;                               // the first n_keep mappings: the flag blocks
     IpcBlob* stage_dev = nullptr;                    // nranks blobs (device, for ncclAllGather)
 } g_p2p;
 
@@ -355,8 +356,21 @@ int emg3d_b200_p2p_init(int* enabled) {
     if (publish(g_p2p.flags, peers)) { cudaGetLastError(); return 0; }
     g_p2p.peer_flags[0] = (u64*)peers[0];
     g_p2p.peer_flags[1] = (u64*)peers[1];
+    g_p2p.n_keep = g_p2p.opened.size();
     g_p2p.on = true;
     *enabled = 1;
+    return 0;
+}
+
+// Forget all registered arrays and unmap the neighbours' (everything but the flag blocks).
+// Call on every rank BEFORE the registered arrays are freed, and synchronise the ranks
+// before the next registration.
+int emg3d_b200_p2p_release(void) {
+    if (!g_p2p.on) return 0;
+    cudaStreamSynchronize((cudaStream_t)emg3d_b200_internal_stream());
+    for (size_t i = g_p2p.n_keep; i < g_p2p.opened.size(); ++i) cudaIpcCloseMemHandle(g_p2p.opened[i].second);
+    g_p2p.opened.resize(g_p2p.n_keep);
+    g_p2p.slots.clear();
     return 0;
 }
 

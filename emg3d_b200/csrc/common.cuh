@@ -123,6 +123,11 @@ struct Dims {
     // z-edges of cell layer k iff own0 <= k + 1 < own1 (a layer belongs to the
     // owner of its upper plane).
     int own0, own1;
+    // multi-GPU z-slabs: 1 if local node plane 1 of this view is an EVEN global node plane, so
+    // that the z-parity of the multicolour classes (node colours, x-/y-line colours) is the
+    // global one on every rank: class bit cz relaxes the local planes of parity cz ^ zflip.
+    // (The tile-fused point schedule colours by local tile index and ignores it.)
+    int zflip;
 };
 __host__ __device__ __forceinline__ bool owns_plane(const Dims& d, int k) {
     return d.own1 == 0 || (k >= d.own0 && k < d.own1);

@@ -296,7 +296,10 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
         ++g_launch_count; gs_line_small_kernel<T, D><<<1, threads, 0, st>>>(m, fac, ls, e, s, nu, order);
         return;
     }
-    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    bool back = (order >> 8) & 1;   // bit 8 of `order`: sweeps already done (phase)
+    // bits 16-17: z-half of a multicolour sweep (see gs_point.cu); x- and y-lines are coloured
+    // by (p, z) parity, class index cp + 2 cz
+    const int zsel = D == 2 ? 0 : (order >> 16) & 3;
     order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
@@ -310,7 +313,8 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
             }
         } else {
             for (int cc = 0; cc < 4; ++cc) {
-                const int c = back ? 3 - cc : cc;
+                const int cg = back ? 3 - cc : cc;              // class by global z-parity
+                const int c = D == 2 ? cg : cg ^ ((m.d.zflip & 1) << 1);   // local class
                 if (ls.cnt[c] == 0) continue;
                 // Consecutive sweeps run the colours in opposite order, so the first
                 // colour of a sweep is the last colour of the previous one.  Lines of one
@@ -318,6 +322,7 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
                 // again reproduces the same values (block relaxation is idempotent), so
                 // that launch is skipped -- 7 instead of 8 colour launches for nu = 2.
                 if (sw > 0 && cc == 0) continue;
+                if (zsel && (cg >> 1) != zsel - 1) continue;
                 if (fac2) {          // segment-parallel kernel (gs_line_seg.cu), same colour sequence
                     launch_gs_line_seg_color<T>(m, D, fac2, e, s, c, st);
                     continue;

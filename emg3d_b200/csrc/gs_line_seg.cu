@@ -37,6 +37,12 @@
 namespace emg {
 
 constexpr int SEG_K = 8;                       // blocks per lane
+#ifndef SEG_PF_W
+#define SEG_PF_W 0                             // L2 prefetch of the line's cached data at the start (measured: -8 %)
+#endif
+#ifndef SEG_PF_ROWS
+#define SEG_PF_ROWS 1                          // L2 prefetch of the field rows of an x-line
+#endif
 
 // Layout of one line's chunk of the cached data (elements of T), QP = lanes per line:
 //   [ W: (j, e, q) at (j * FAC_NE + e) * QP + q  | header: 1/dL_0 + 7 pad | Phi: (q, r, c) | Psi: (q, r, c) ]
@@ -64,6 +70,11 @@ __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync
 __device__ __forceinline__ cplx shfl_t(cplx v, int src) {
     return make_c(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src));
 }
+// value of the lane below within groups of `width` lanes (the lowest lane keeps its own)
+__device__ __forceinline__ double shfl_up_t(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
+__device__ __forceinline__ cplx shfl_up_t(cplx v, int width) {
+    return make_c(__shfl_up_sync(0xffffffffu, v.re, 1, width), __shfl_up_sync(0xffffffffu, v.im, 1, width));
+}
 
 // acc += a * b with every product fused into the accumulation (4 DFMA per complex
 // multiply-add instead of 2 DMUL + 2 DFMA + 2 DADD)
@@ -78,23 +89,27 @@ __device__ __forceinline__ void fma_t(cplx& acc, double a, cplx b) {
     acc.re = fma(a, b.re, acc.re);
     acc.im = fma(a, b.im, acc.im);
 }
+// The passes are one dependent chain per lane (one warp per scheduler): sums are evaluated as
+// pairs of independent halves to shorten the chain of dependent DFMAs.
 template <typename T>
 __device__ __forceinline__ void seg_symv4(const T x[10], const T v[4], T out[4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        T t = x[tri(r, 0)] * v[0];
-#pragma unroll
-        for (int c = 1; c < 4; ++c) fma_t(t, x[tri(r, c)], v[c]);
-        out[r] = t;
+        T t0 = x[tri(r, 0)] * v[0];
+        T t1 = x[tri(r, 2)] * v[2];
+        fma_t(t0, x[tri(r, 1)], v[1]);
+        fma_t(t1, x[tri(r, 3)], v[3]);
+        out[r] = t0 + t1;
     }
 }
 // E v with E = diag(d) + rl f f^T
 template <typename T>
 __device__ __forceinline__ void seg_apply_E(const double d[4], const double f[4], T rl, const T v[4], T out[4]) {
-    T fv = f[0] * v[0];
-#pragma unroll
-    for (int k = 1; k < 4; ++k) fma_t(fv, f[k], v[k]);
-    const T a = rl * fv;
+    T f0 = f[0] * v[0];
+    T f1 = f[2] * v[2];
+    fma_t(f0, f[1], v[1]);
+    fma_t(f1, f[3], v[3]);
+    const T a = rl * (f0 + f1);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         out[k] = d[k] * v[k];
@@ -121,6 +136,53 @@ __device__ __forceinline__ void seg_cell(const Line<T, D>& ln, const double* __r
         const double as = ln.a_side(k);
         f[k] = -(gs[k] * rd * as);
         d[k] = -(gs[k] * rd * rd);
+    }
+}
+
+// Sequential scan over the Qn segment ends of a line: sb[qq] <- sb[qq] + J_qq * (previous result),
+// forward (qq = 0 .. Qn-1) or backward (qq = Qn-1 .. 0); G = the value entering the first step.
+// The jump matrices come in batches of QP / 4 by one coalesced load: lane q = 4 u + r holds row r
+// of matrix `batch + u` and the matching entry of sb, and computes that row of step u itself, so
+// a step is 4 fused complex multiply-adds and one broadcast of the new 4-vector (no memory).
+template <typename T, int QP, bool FWD>
+__device__ __forceinline__ void seg_scan(const T* __restrict__ jump, T* __restrict__ sb, T G[4], int Qn,
+                                         int q, int sub) {
+    constexpr int MB = QP / 4;                   // matrices per batch
+    const int nbatch = (Qn + MB - 1) / MB;
+    const int mu = q >> 2;                       // my matrix within a batch
+    auto fetch = [&](int bb, T ph[4], T& v) {
+        const int b = FWD ? bb * MB : (nbatch - 1 - bb) * MB;
+        const T* p = jump + (b + mu) * 16 + (q & 3) * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ph[c] = ldg(p + c);
+        v = sb[(b + mu) * 4 + (q & 3)];
+    };
+    T ph[4], v;
+    fetch(0, ph, v);
+    for (int bb = 0; bb < nbatch; ++bb) {
+        const int b = FWD ? bb * MB : (nbatch - 1 - bb) * MB;
+        T ph2[4], v2;                            // next batch: in flight during this one
+        if (bb + 1 < nbatch) fetch(bb + 1, ph2, v2);
+        T res = v;
+#pragma unroll
+        for (int uu = 0; uu < MB; ++uu) {
+            const int u = FWD ? uu : MB - 1 - uu;
+            if (b + u < Qn) {                    // uniform over the warp
+                T s0 = ph[0] * G[0], s1 = ph[2] * G[2];
+                fma_t(s0, ph[1], G[1]);
+                fma_t(s1, ph[3], G[3]);
+                const T s_ = v + (s0 + s1);
+                if (mu == u) res = s_;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) G[k] = shfl_t(s_, sub * QP + 4 * u + k);
+            }
+        }
+        if (b + mu < Qn) sb[(b + mu) * 4 + (q & 3)] = res;
+        if (bb + 1 < nbatch) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ph[c] = ph2[c];
+            v = v2;
+        }
     }
 }
 
@@ -154,67 +216,141 @@ __device__ void seg_line_sweep(const Model<T>& m, const T* __restrict__ fac2, co
     const int Qn = (NB + SEG_K - 1) / SEG_K;     // segments in use
     const T* const chunk = fac2 + ls.slot(tp, tq) * (int64_t)SL::LINE;
     // the factors are needed after the right-hand sides: start their way towards the L2 now
-    if (q == 0) bulk_prefetch_l2(chunk, (unsigned)(SL::LINE * sizeof(T)));
+    if (SEG_PF_W && q == 0) bulk_prefetch_l2(chunk, (unsigned)(SL::LINE * sizeof(T)));
 
     // ---- right-hand sides, cell-parallel (coalesced): block i = q + QP t ----------------
     {
+    double cz[4];                                // carry: zeta of the cell below lane 0's block
+    T cu[4];                                     //        and its gra * (outer line edges)
+    {
     const LineAddr<T, D> a(E, S, nullptr, tp, tq);
-    if (q < 4) {
-        se[q] = *a.t_ptr(q, 0);
-        se[4 + q] = *a.t_ptr(q, N);
-    }
-#pragma unroll 1
-    for (int t = 0; t < SEG_K; ++t) {
-        const int i = q + QP * t;
-        T r[4], bln;
-        if (i < NB) {
-            const int mn = i + 1;
-            double zc[2][2], zn[2][2], gc[4], gn[4];
-            ln.load_zeta(i, zc);
-            ln.load_zeta(mn, zn);
-            ln.side_g(zc, gc);
-            ln.side_g(zn, gn);
-            CellCoef cc, cn;
-            cell_coef<T, D>(ln, gc, ldg(m.rh[A::d] + i), cc);
-            cell_coef<T, D>(ln, gn, ldg(m.rh[A::d] + mn), cn);
-            T eo_c[4], eo_n[4];
+    if (SEG_PF_ROWS && D == 0 && sizeof(T) == 16) {
+        // x-lines: every array row the line touches is one contiguous run; 21 bulk prefetches,
+        // one per lane, bring them into the L2 while the first loads are in flight
+        const void* row = nullptr;
+        int cnt = N + 1;
+        if (q == 8) { row = a.sdp + a.oL; cnt = N; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                eo_c[k] = a.ed[a.oLn[k] + a.sd * i];
-                eo_n[k] = a.ed[a.oLn[k] + a.sd * mn];
-            }
-            bln = line_rhs<T, D>(a, mn, cn, eo_n);
-            if (i == 0) se[8] = line_rhs<T, D>(a, 0, cc, eo_c);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                r[k] = ldg(a.ts_ptr(k, mn)) + cc.gra[k] * eo_c[k] - cn.gra[k] * eo_n[k];
-#pragma unroll
-            for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                for (int jq = 0; jq < 2; ++jq) {
-                    const double gf = 0.5 * (zc[jp][jq] + zn[jp][jq]);
-                    const double ap = ln.al_p(jq), aq = ln.al_q(jp);
-                    const T out = ap * a.epo(jp, jq, mn) + aq * a.eqo(jp, jq, mn);
-                    r[jp] += (gf * ap) * out;
-                    r[2 + jq] += (gf * aq) * out;
-                }
-#pragma unroll
-            for (int jp = 0; jp < 2; ++jp)
-#pragma unroll
-                for (int jq = 0; jq < 2; ++jq) {
-                    zs[(jp * 2 + jq) * SL::ZR + pad8(mn)] = zn[jp][jq];
-                    if (i == 0) zs[(jp * 2 + jq) * SL::ZR] = zc[jp][jq];
-                }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                r[k] = zero_<T>();
-                zs[k * SL::ZR + pad8(i + 1)] = 0.0;
-            }
-            bln = zero_<T>();
+        for (int k = 0; k < 4; ++k) {            // (static indices: no local-memory arrays)
+            if (q == k) { row = a.ed + a.oLn[k]; cnt = N; }
+            if (q == 4 + k) row = a.ts_ptr(k, 0);
+            if (q == 9 + k) row = a.ep + a.oP[k >> 1][2 * (k & 1)];
+            if (q == 13 + k) row = a.eq + a.oQ[k & 1][2 * (k >> 1)];
         }
+        if (row) bulk_prefetch_l2(row, (unsigned)(cnt * sizeof(T)));
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) wA[k * SL::ST + pad8(i)] = r[k];
+    for (int k = 0; k < 4; ++k)
+        if (q == k) {
+            se[k] = *a.t_ptr(k, 0);
+            se[4 + k] = *a.t_ptr(k, N);
+        }
+    // Every lane loads the data of the cell ABOVE its block (cell i + 1) and of the block's node;
+    // the cell below is the neighbouring lane's cell above (shuffle), lane 0 takes it from lane
+    // QP - 1 of the previous round (carry), the very first one is line cell 0.
+    {
+        double z0[2][2], g0[4];
+        ln.load_zeta(0, z0);
+        ln.side_g(z0, g0);
+        CellCoef c0;
+        cell_coef<T, D>(ln, g0, ldg(m.rh[A::d]), c0);
+        T e0[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            e0[k] = a.ed[a.oLn[k]];
+            cu[k] = c0.gra[k] * e0[k];
+        }
+        cz[0] = z0[0][0]; cz[1] = z0[0][1]; cz[2] = z0[1][0]; cz[3] = z0[1][1];
+        if (q == 0) {
+            se[8] = line_rhs<T, D>(a, 0, c0, e0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) zs[k * SL::ZR] = cz[k];
+        }
+    }
+    }
+#pragma unroll 2
+    for (int t = 0; t < SEG_K; ++t) {
+        // The ~26 row offsets of the line are recomputed every round (a few integer multiply-adds
+        // each): hoisted out of the loop they do not fit the register file next to the 22 loads
+        // in flight, and were spilled and re-read from local memory (= L2) every round.
+        int tpl = tp, tql = tq;
+        asm volatile("" : "+r"(tpl), "+r"(tql));
+        const LineAddr<T, D> a(E, S, nullptr, tpl, tql);
+        const int i = q + QP * t;
+        const bool valid = i < NB;
+        const int mn = valid ? i + 1 : NB;       // (clamped: loads stay inside the line)
+        // ---- loads: cell mn, node mn
+        double zn[4];
+        {
+            double z[2][2];
+            ln.load_zeta(mn, z);
+            zn[0] = z[0][0]; zn[1] = z[0][1]; zn[2] = z[1][0]; zn[3] = z[1][1];
+        }
+        const double rdn = ldg(m.rh[A::d] + mn);
+        T eo_n[4], st[4], op[4], oq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) eo_n[k] = a.ed[a.oLn[k] + a.sd * mn];
+        const T sl = ldg(a.sdp + a.oL + a.sd * mn);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st[k] = ldg(a.ts_ptr(k, mn));
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) {
+                op[jp * 2 + jq] = a.epo(jp, jq, mn);
+                oq[jp * 2 + jq] = a.eqo(jp, jq, mn);
+            }
+        // ---- the cell above
+        T un[4], bln = sl;
+        {
+            double gn[4];
+            gn[0] = 0.5 * (zn[0] + zn[1]);
+            gn[1] = 0.5 * (zn[2] + zn[3]);
+            gn[2] = 0.5 * (zn[0] + zn[2]);
+            gn[3] = 0.5 * (zn[1] + zn[3]);
+            CellCoef cn;
+            cell_coef<T, D>(ln, gn, rdn, cn);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                un[k] = cn.gra[k] * eo_n[k];
+                bln += cn.gaa[k] * eo_n[k];
+            }
+        }
+        if (!valid) {
+            bln = zero_<T>();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { un[k] = zero_<T>(); zn[k] = 0.0; st[k] = zero_<T>(); }
+        }
+        // ---- the cell below: neighbouring lane / carry
+        double zc[4];
+        T uc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            zc[k] = __shfl_up_sync(0xffffffffu, zn[k], 1, QP);
+            uc[k] = shfl_up_t(un[k], QP);
+            if (q == 0) { zc[k] = cz[k]; uc[k] = cu[k]; }
+            cz[k] = __shfl_sync(0xffffffffu, zn[k], sub * QP + QP - 1);
+            cu[k] = shfl_t(un[k], sub * QP + QP - 1);
+        }
+        // ---- right-hand side of the block: sources, side faces of both cells, end faces
+        T r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = valid ? st[k] + uc[k] - un[k] : zero_<T>();
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp)
+#pragma unroll
+            for (int jq = 0; jq < 2; ++jq) {
+                const double gf = valid ? 0.5 * (zc[jp * 2 + jq] + zn[jp * 2 + jq]) : 0.0;
+                const double ap = ln.al_p(jq), aq = ln.al_q(jp);
+                const T out = ap * op[jp * 2 + jq] + aq * oq[jp * 2 + jq];
+                r[jp] += (gf * ap) * out;
+                r[2 + jq] += (gf * aq) * out;
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            zs[k * SL::ZR + pad8(i + 1)] = zn[k];
+            wA[k * SL::ST + pad8(i)] = r[k];
+        }
         wA[4 * SL::ST + pad8(i)] = bln;
     }
     }
@@ -278,24 +414,15 @@ __device__ void seg_line_sweep(const Model<T>& m, const T* __restrict__ fac2, co
     }
     __syncwarp();
 
-    // ---- forward scan over the segment ends (lanes q < 4 = rows of the 4x4 jumps) -------
+    // ---- forward scan over the segment ends ---------------------------------------------
+    // G_q = g~_end(q) + Phi_q G_{q-1}, sequential over the segments.  The jump matrices come in
+    // batches of QP / 4: one coalesced load (lane q holds row q % 4 of matrix batch + q / 4);
+    // lanes q < 4 own one row of the running 4x4 matrix-vector product and fetch their row of
+    // the current matrix by shuffle, so a step never waits for memory.
     T G[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) G[k] = se[k];                    // g_0 = T_0 (fixed data)
-    {
-        const T* ph = chunk + SL::PHI + (q & 3) * 4;
-#pragma unroll 4
-        for (int qq = 0; qq < Qn; ++qq) {
-            T s_ = zero_<T>();
-            if (q < 4) {
-                const T* p = ph + qq * 16;
-                s_ = sb[qq * 4 + q] + ldg(p) * G[0] + ldg(p + 1) * G[1] + ldg(p + 2) * G[2] + ldg(p + 3) * G[3];
-                sb[qq * 4 + q] = s_;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) G[k] = shfl_t(s_, sub * QP + k);
-        }
-    }
+    seg_scan<T, QP, true>(chunk + SL::PHI, sb, G, Qn, q, sub);
     __syncwarp();
 
     // ---- pass 2: propagate the incoming g through the segment ---------------------------
@@ -351,23 +478,10 @@ __device__ void seg_line_sweep(const Model<T>& m, const T* __restrict__ fac2, co
     }
     __syncwarp();
 
-    // ---- backward scan -------------------------------------------------------------------
+    // ---- backward scan: H_q = T~_first(q) + Psi_q H_{q+1} -------------------------------
 #pragma unroll
     for (int k = 0; k < 4; ++k) G[k] = se[4 + k];                // T_N (fixed data)
-    {
-        const T* ps = chunk + SL::PSI + (q & 3) * 4;
-#pragma unroll 4
-        for (int qq = Qn - 1; qq >= 0; --qq) {
-            T s_ = zero_<T>();
-            if (q < 4) {
-                const T* p = ps + qq * 16;
-                s_ = sb[qq * 4 + q] + ldg(p) * G[0] + ldg(p + 1) * G[1] + ldg(p + 2) * G[2] + ldg(p + 3) * G[3];
-                sb[qq * 4 + q] = s_;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) G[k] = shfl_t(s_, sub * QP + k);
-        }
-    }
+    seg_scan<T, QP, false>(chunk + SL::PSI, sb, G, Qn, q, sub);
     __syncwarp();
 
     // ---- pass 4: propagate the incoming T, line edges -----------------------------------

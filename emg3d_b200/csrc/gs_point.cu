@@ -719,7 +719,10 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
         ++g_launch_count; gs_point_small_kernel<T><<<1, threads, 0, st>>>(m, e, s, nu, order);
         return;
     }
-    bool back = (order >> 8) & 1;   // bits 8+ of `order`: sweeps already done (phase)
+    bool back = (order >> 8) & 1;   // bit 8 of `order`: sweeps already done (phase)
+    // bits 16-17: multicolour order, z-half of a sweep (multi-GPU z-slabs): 1 = only the colour
+    // classes of even z-parity, 2 = only those of odd z-parity, 0 = all
+    const int zsel = (order >> 16) & 3;
     order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
@@ -737,6 +740,7 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
             for (int cc = 0; cc < 8; ++cc) {
                 const int c = back ? 7 - cc : cc;
                 const int tcx = c & 1, tcy = (c >> 1) & 1, tcz = (c >> 2) & 1;
+                if (zsel && tcz != zsel - 1) continue;
                 dim3 g((ntx - tcx + 1) / 2, (nty - tcy + 1) / 2, (ntz - tcz + 1) / 2);
                 if (g.x == 0 || g.y == 0 || g.z == 0) continue;
 #if EMG_PT_MARCH
@@ -752,7 +756,8 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
                 // (opposite order); nodes of one colour do not interact and nothing
                 // changed in between, so relaxing them again reproduces the same values
                 if (sw > 0 && cc == 0) continue;
-                const int fx = 1 + (c & 1), fy = 1 + ((c >> 1) & 1), fz = 1 + ((c >> 2) & 1);
+                if (zsel && ((c >> 2) & 1) != zsel - 1) continue;
+                const int fx = 1 + (c & 1), fy = 1 + ((c >> 1) & 1), fz = 1 + (((c >> 2) & 1) ^ (m.d.zflip & 1));
                 const int cx = (nx - fx + 1) / 2, cy = (ny - fy + 1) / 2, cz = (nz - fz + 1) / 2;
                 if (cx <= 0 || cy <= 0 || cz <= 0) continue;
                 dim3 b(32, 4, 1);

@@ -299,6 +299,11 @@ class NcclComm:
         if args[0]:
             self._lib.check(self._lib.load().emg3d_b200_p2p_exchange(slot, *args))
 
+    def p2p_release(self):
+        """Unmap every registered array (before the arrays are freed)."""
+        if getattr(self, 'p2p', False):
+            self._lib.check(self._lib.load().emg3d_b200_p2p_release())
+
     def p2p_status(self):
         import ctypes
         st = ctypes.c_int(0)
@@ -333,8 +338,22 @@ class _DLevel:
         z0 = 0 if rank == 0 else p0 - 1 - lo
         self.win = lv.handle if z0 == 0 else lv.handle.window(z0, hi - lo - z0)
         # norms evaluated by the residual kernel on the window count owned edges only
+        import ctypes
         from emg3d_b200 import _lib
-        _lib.check(_lib.load().emg3d_b200_level_set_owned(self.win.ptr, p0 - lo - z0, p1 - lo - z0))
+        lib = _lib.load()
+        _lib.check(lib.emg3d_b200_level_set_owned(self.win.ptr, p0 - lo - z0, p1 - lo - z0))
+        # Exact (true Gauss-Seidel) sweeps across slabs: the colour classes are run in two
+        # z-halves with a halo exchange after each.  Node / line colours use the GLOBAL z-parity
+        # (local node plane 1 of the window is global plane lo + z0 + 1) ...
+        _lib.check(lib.emg3d_b200_level_set_zflip(self.win.ptr, int((lo + z0 + 1) % 2 == 0)))
+        # ... the tile-fused point schedule colours by local tile index: planes on either side of
+        # an interface fall into different halves iff the top tile of the lower rank is odd
+        kind, tile = ctypes.c_int(0), (ctypes.c_int * 3)()
+        _lib.check(lib.emg3d_b200_point_schedule_kind(self.win.ptr, ctypes.byref(kind)))
+        _lib.check(lib.emg3d_b200_point_tile_shape(tile))
+        nzw = hi - lo - z0                               # cells of the window
+        self.point_halves_ok = (kind.value != 2 or rank == part.nranks - 1
+                                or ((nzw - 2) // tile[2]) % 2 == 1)
         lv.res_buffer().zero()
 
 
@@ -354,8 +373,12 @@ class DistributedMultigrid:
         million cells (the coarser ones are replicated on every GPU).
     """
 
-    def __init__(self, model, sfield, comm, n_dist=None, order=None):
+    def __init__(self, model, sfield, comm, n_dist=None, order=None, exact=None):
+        import os
         from emg3d_b200 import _lib, core, meshes, models, solver
+        if exact is None:
+            exact = os.environ.get('EMG3D_B200_DIST_EXACT', '1') != '0'
+        self.exact = bool(exact)
         self._lib, self._solver = _lib, solver
         self.comm, self.rank, self.nranks = comm, comm.rank, comm.nranks
         self._slots = {}                             # device pointer -> peer-memory slot
@@ -411,6 +434,15 @@ class DistributedMultigrid:
         self.upload_source(sfield)
         self._sums = _lib.DeviceArray(8, np.float64)
         self._sums.zero()
+
+    def close(self):
+        """Release the peer-memory mappings of this solver's arrays.  Call on every rank (and
+        synchronise the ranks) before the instance is dropped and another one is created."""
+        self._lib.sync()
+        if hasattr(self.comm, 'p2p_release'):
+            self.comm.p2p_release()
+        self._slots.clear()
+        self._graphs.clear()
 
     # ---- setup helpers ------------------------------------------------------------
     def _build_global_level(self, model, level):
@@ -495,6 +527,16 @@ class DistributedMultigrid:
                 return
         self.comm.sendrecv(field.ptr, self.dtype.itemsize, dl.plan)
 
+    def check_transport(self):
+        """Raise if a peer-memory halo exchange timed out (csrc/comm.cu sets a status word and
+        lets the kernel finish; the fields are then inconsistent across ranks)."""
+        if getattr(self.comm, 'p2p', False):
+            st = self.comm.p2p_status()
+            if st:
+                raise self._lib.Emg3dB200Error(
+                    f"peer-memory halo exchange timed out (status {st}): a neighbouring rank did "
+                    "not arrive within the spin limit; the fields are inconsistent")
+
     def sum_owned(self, dl, x, y=None):
         """sum over owned edges of conj(x) y (default y = x), all-reduced."""
         lib = self._lib.load()
@@ -521,14 +563,34 @@ class DistributedMultigrid:
         return r
 
     def smoothing(self, dl, s, e, nu, lr_dir):
+        """``nu`` sweeps per line direction on the rank's window.
+
+        Exact variant (default): every multicolour sweep is run as its two z-halves
+        (the classes of even, then odd z-parity, or the reverse in a descending sweep) with a
+        halo exchange after each.  Planes on either side of an interface belong to different
+        halves, so every relaxed node sees current neighbour values: a true multicolour
+        Gauss-Seidel sweep, as on one GPU.  Relaxed variant (``exact=False``, what
+        ``north_star`` words): one exchange per sweep, interface planes see values one sweep
+        old (block-Jacobi across slabs) -- half the messages, weaker smoothing at interfaces.
+        """
         solver, lib = self._solver, self._lib.load()
         c_lr_dir = int(solver._current_lr_dir(lr_dir, dl.lv.grid))
         dirs = solver._LR_DIRS[c_lr_dir] or (0,)
         for ldir in dirs:
+            if ldir == 3:
+                raise NotImplementedError("z-line relaxation across z-slabs is not distributed")
+            halves = self.exact and self.order == 1 and (ldir != 0 or dl.point_halves_ok)
             for sweep in range(int(nu)):
-                self._lib.check(lib.emg3d_b200_gauss_seidel(
-                    dl.win.ptr, e.ptr, s.ptr, 1, ldir, self.order | (sweep << 8)))
-                self.exchange(dl, e)
+                base = self.order | (sweep << 8)
+                if not halves:
+                    self._lib.check(lib.emg3d_b200_gauss_seidel(dl.win.ptr, e.ptr, s.ptr, 1, ldir, base))
+                    self.exchange(dl, e)
+                    continue
+                # sweep 0 is the descending one (classes of odd z-parity first)
+                for half in ((2, 1) if sweep % 2 == 0 else (1, 2)):
+                    self._lib.check(lib.emg3d_b200_gauss_seidel(
+                        dl.win.ptr, e.ptr, s.ptr, 1, ldir, base | (half << 16)))
+                    self.exchange(dl, e)
 
     # ---- the cycle ---------------------------------------------------------------------
     def multigrid(self, var, level=0, new_cycmax=0):
@@ -571,7 +633,10 @@ class DistributedMultigrid:
             else:
                 var.it += 1
                 l2_last = self.residual(dl, s, e, norm=True)
+                self.check_transport()
                 solver._print_cycle_info(var, l2_last, l2_prev)
+                if var.lr_cycle:                         # as solver._multigrid (solver.py:639-642)
+                    var.lr_dir = next(var.lr_cycle)
                 if solver._terminate(var, l2_last, l2_stag[(it - 1) % var.maxcycle], it):
                     break
         var.l2 = l2_last
@@ -638,6 +703,10 @@ class DistributedMultigrid:
               linerelaxation=False, verb=0, zero_start=True):
         """Run multigrid cycles; returns the info dict of solver.solve."""
         solver = self._solver
+        lr_values = np.atleast_1d(linerelaxation)
+        if linerelaxation is True or any(int(v) not in (0, 1, 2, 6) for v in lr_values.ravel()):
+            raise ValueError("distributed line relaxation supports 0 (point), 1 (x), 2 (y) and 6 (x and "
+                             f"y) only: z-lines cross the z-slabs. Provided: {linerelaxation!r}.")
         var = solver.MGParameters(verb=verb, sslsolver=False, semicoarsening=False,
                                   linerelaxation=linerelaxation, shape_cells=self.gshape,
                                   cycle=cycle, tol=tol, maxit=maxit, nu_init=nu_init,
@@ -651,6 +720,7 @@ class DistributedMultigrid:
             self.e.zero()
             var.e_is_zero, var.s_norm = True, var.l2_refe
         self.multigrid(var)
+        self.check_transport()
         return {'exit': int(var.exit_message != 'CONVERGED'), 'exit_message': var.exit_message,
                 'abs_error': var.l2, 'rel_error': var.l2 / var.l2_refe, 'ref_error': var.l2_refe,
                 'it_mg': var.it, 'error_at_cycle': var.error_at_cycle,

@@ -92,6 +92,15 @@ int emg3d_b200_level_window(emg3d_b200_level** out, const emg3d_b200_level* pare
  * plane1 == 0 (default): all edges, i.e. the reference's np.linalg.norm
  * (emg3d/solver.py:1066). */
 int emg3d_b200_level_set_owned(emg3d_b200_level* lv, int plane0, int plane1);
+/* Multi-GPU z-slabs.  flip = 1 declares that local node plane 1 of this (window) level is an
+ * even global node plane: the z-parity of the multicolour classes of the node-colour point
+ * schedule and of the x- / y-line colours is then the global one (class bit cz relaxes local
+ * planes of parity cz ^ flip), so that the "z-half" selection of emg3d_b200_gauss_seidel
+ * (bits 16-17 of `order`) names the same global planes on every rank.                      */
+int emg3d_b200_level_set_zflip(emg3d_b200_level* lv, int flip);
+/* Multicolour point schedule used for this level's shape: 0 = one block (<= 512 interior
+ * nodes), 1 = one launch per node colour, 2 = tile-fused (tiles coloured by LOCAL tile index). */
+int emg3d_b200_point_schedule_kind(const emg3d_b200_level* lv, int* kind);
 /* bytes of the cached factorisation of line direction ldir (1, 2, 3) */
 int emg3d_b200_level_factor_bytes(const emg3d_b200_level* lv, int ldir, size_t* nbytes);
 int emg3d_b200_level_drop_factors(emg3d_b200_level* lv);
@@ -124,7 +133,13 @@ int emg3d_b200_residual_norm(emg3d_b200_level* lv, const void* s, const void* e,
  * (core.gauss_seidel, core.py:210-212), 1/2/3 = x/y/z line relaxation
  * (core.gauss_seidel_x/_y/_z, core.py:506-508, 786-788, 1071-1073).
  * order: LEX = sequentially equivalent to the reference's lexicographic
- * sweeps; COLOR = multicolour ordering (8 colours point, 4 colours lines).     */
+ * sweeps; COLOR = multicolour ordering (8 colours point, 4 colours lines).
+ * Higher bits of `order`: bit 8 = an odd number of sweeps precedes this call (sweeps
+ * alternate direction); bits 16-17 (COLOR, point / x- / y-lines) = z-half of a sweep:
+ * 1 = only the colour classes of even z-parity, 2 = only the odd ones, 0 = all.  A
+ * z-slab solver runs the two halves with a halo exchange after each: planes on either
+ * side of an interface are never relaxed in the same half, which makes the distributed
+ * sweep a true multicolour Gauss-Seidel sweep (exact variant).      */
 int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu, int ldir,
                             int order);
 /* Node order inside a tile of the point smoother's tile-fused multicolour schedule
@@ -204,6 +219,9 @@ int emg3d_b200_comm_allreduce_sum(double* dev, int n);
  * New functionality (the reference has no distributed solve). */
 int emg3d_b200_p2p_init(int* enabled);
 int emg3d_b200_p2p_register(void* dev_ptr, int* slot);
+/* Forget all registered arrays and unmap the neighbours' copies.  Call on every rank before
+ * the registered arrays are freed; synchronise the ranks before registering again.        */
+int emg3d_b200_p2p_release(void);
 int emg3d_b200_p2p_exchange(int slot, int n, const size_t* my_off, const size_t* peer_off,
                             const size_t* nbytes, const int* from_upper);
 int emg3d_b200_p2p_status(int* status);

@@ -12,6 +12,7 @@ from emg3d_b200 import _lib, solver, recipes
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 masks = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else '0,7').split(',')]
 ldirs = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else '1,2,3').split(',')]
+splits = [int(v) for v in (sys.argv[4] if len(sys.argv) > 4 else '100').split(',')]
 cfg = recipes.config('config3', n)
 grid = eb.TensorMesh(cfg['h'], cfg['origin'])
 model = eb.Model(grid, **cfg['model'])
@@ -32,7 +33,7 @@ except Exception:
 out = {}
 fields = {}
 for ldir in ldirs:
-    for mask in masks:
+    for mask, split in [(m, sp) for m in masks for sp in (splits if m else [100])]:
         _lib.line_seg_mask(mask)
         lv.handle.drop_factors()
         d_e = lv.new_field()
@@ -41,7 +42,7 @@ for ldir in ldirs:
         _lib.check(lib.emg3d_b200_gauss_seidel(lv.handle.ptr, d_e.ptr, d_s.ptr, 2, ldir, order))
         b.record()
         t_first = a.elapsed_ms(b)
-        fields[(ldir, mask)] = d_e.download()
+        fields[(ldir, mask, split)] = d_e.download()
         reps = 5
         a, b = _lib.Event(), _lib.Event()
         a.record()
@@ -50,14 +51,15 @@ for ldir in ldirs:
         b.record()
         t = a.elapsed_ms(b) / reps
         gbs = 184 * cells * 2 / (t * 1e-3) / 1e9
-        out[f'ldir{ldir}_mask{mask}'] = dict(ms_nu2=round(t, 4), first_call_ms=round(t_first, 3),
+        out[f'ldir{ldir}_mask{mask}_split{split}'] = dict(ms_nu2=round(t, 4), first_call_ms=round(t_first, 3),
                                              GBs=round(gbs, 1), frac=round(gbs / peak, 4))
-        print(f"n={n} ldir={ldir} mask={mask}: nu=2 call {t:.3f} ms (first call incl. factorisation "
+        print(f"n={n} ldir={ldir} mask={mask} split={split}: nu=2 call {t:.3f} ms (first call incl. factorisation "
               f"{t_first:.2f} ms), {gbs:.0f} GB/s algorithmic = {gbs / peak:.3f} of peak", flush=True)
         del d_e
-    if len(masks) > 1:
-        f0, f1 = fields[(ldir, masks[0])], fields[(ldir, masks[-1])]
-        print(f"   ldir={ldir}: |seg - thread| / |thread| = "
+    keys = [k for k in fields if k[0] == ldir]
+    for k in keys[1:]:
+        f0, f1 = fields[keys[0]], fields[k]
+        print(f"   ldir={ldir}: |{k[1:]} - {keys[0][1:]}| / |.| = "
               f"{np.linalg.norm(f1 - f0) / np.linalg.norm(f0):.2e}", flush=True)
     lv.handle.drop_factors()
 print(json.dumps(out))
