@@ -117,7 +117,7 @@ def owned_ranges(part, level, rank, nx, ny):
             (oz + pz * (l0 - lo), pz * (l1 - l0))]
 
 
-def exchange_plan(part, level, rank, nx, ny):
+def exchange_plan(part, level, rank, nx, ny, shared_from_lower=False):
     """Halo exchange of one field on one level.
 
     Returns a list of ``(is_send, peer, offset, count)`` in elements of the local
@@ -125,6 +125,13 @@ def exchange_plan(part, level, rank, nx, ny):
     below it; downwards fx, fy of its bottom owned plane and the fz layer below
     that plane.  (Two layers of fz are needed below an interface by the
     restriction of fz, one by the smoother.)
+
+    The fz layer between the two planes next to an interface is SHARED: both ranks hold it and
+    the smoothers of both relax it (an interior edge belongs to the blocks of both its end
+    nodes).  By default the upper rank's copy wins (a layer belongs to the owner of its upper
+    plane: residuals, prolongation, norms).  ``shared_from_lower=True`` sends the lower rank's
+    copy up instead: used after the half sweep that relaxed the lower rank's top plane, whose
+    update of the shared layer would otherwise be discarded.
     """
     lo, hi = part.local(level, rank)
     p0, p1 = part.owned(level, rank)
@@ -142,21 +149,27 @@ def exchange_plan(part, level, rank, nx, ny):
     if rank > 0:                                      # interface below: plane p0
         depth_mine = p0 - lo
         plane(1, rank - 1, p0)
-        layer(1, rank - 1, p0 - 1)
+        if not shared_from_lower:
+            layer(1, rank - 1, p0 - 1)
         plane(0, rank - 1, p0 - 1)
+        if shared_from_lower:
+            layer(0, rank - 1, p0 - 1)
         if depth_mine >= 2:                           # the layer exists in my local grid
             layer(0, rank - 1, p0 - 2)
     if rank < part.nranks - 1:                        # interface above: plane p1
         depth_up = 1 << (part.n_dist - level)         # halo depth of the upper neighbour
         plane(1, rank + 1, p1 - 1)
+        if shared_from_lower:
+            layer(1, rank + 1, p1 - 1)
         if depth_up >= 2:
             layer(1, rank + 1, p1 - 2)
         plane(0, rank + 1, p1)
-        layer(0, rank + 1, p1 - 1)
+        if not shared_from_lower:
+            layer(0, rank + 1, p1 - 1)
     return plan
 
 
-def pull_plan(part, level, rank, nx, ny):
+def pull_plan(part, level, rank, nx, ny, shared_from_lower=False):
     """The halo exchange of :func:`exchange_plan` seen from the receiving side.
 
     Returns ``[(from_upper, my_offset, peer_offset, count)]``: the ``count`` elements
@@ -164,13 +177,13 @@ def pull_plan(part, level, rank, nx, ny):
     else ``rank - 1``) belong at ``my_offset`` of this rank's.  A rank's receives
     from a neighbour are matched, in order, with that neighbour's sends to it.
     """
-    mine = exchange_plan(part, level, rank, nx, ny)
+    mine = exchange_plan(part, level, rank, nx, ny, shared_from_lower)
     out = []
     for q in (rank - 1, rank + 1):
         if q < 0 or q >= part.nranks:
             continue
         recvs = [(off, cnt) for s, p, off, cnt in mine if not s and p == q]
-        sends = [(off, cnt) for s, p, off, cnt in exchange_plan(part, level, q, nx, ny)
+        sends = [(off, cnt) for s, p, off, cnt in exchange_plan(part, level, q, nx, ny, shared_from_lower)
                  if s and p == rank]
         if [c for _, c in recvs] != [c for _, c in sends]:
             raise AssertionError("halo plans of neighbouring ranks do not match")
@@ -327,6 +340,10 @@ class _DLevel:
         self.plan = exchange_plan(part, level, rank, nx, ny)
         self.pulls = pull_plan(part, level, rank, nx, ny)
         self.pull_args = None                        # ctypes arrays, built on first use
+        # the same exchange with the shared fz layer of every interface taken from the LOWER rank
+        self.plan_low = exchange_plan(part, level, rank, nx, ny, shared_from_lower=True)
+        self.pulls_low = pull_plan(part, level, rank, nx, ny, shared_from_lower=True)
+        self.pull_args_low = None
         self.owned = owned_ranges(part, level, rank, nx, ny)
         # Smoother and residual run on the z-window [p0 - 1, hi] of the local grid:
         # one halo plane on either side, refreshed by the exchange and fixed during a
@@ -349,6 +366,7 @@ class _DLevel:
         # ... the tile-fused point schedule colours by local tile index: planes on either side of
         # an interface fall into different halves iff the top tile of the lower rank is odd
         kind, tile = ctypes.c_int(0), (ctypes.c_int * 3)()
+        self.point_kind = kind
         _lib.check(lib.emg3d_b200_point_schedule_kind(self.win.ptr, ctypes.byref(kind)))
         _lib.check(lib.emg3d_b200_point_tile_shape(tile))
         nzw = hi - lo - z0                               # cells of the window
@@ -514,18 +532,24 @@ class DistributedMultigrid:
             out_global[goff:goff + n] = loc[loff:loff + n]
 
     # ---- distributed building blocks -------------------------------------------------
-    def exchange(self, dl, field):
-        """Refresh the halo planes of `field` (a local field of level `dl`)."""
+    def exchange(self, dl, field, shared_from_lower=False):
+        """Refresh the halo planes of `field` (a local field of level `dl`); the shared fz layer
+        of an interface comes from the upper rank, or from the lower one (see exchange_plan)."""
         if self.comm.p2p:
             slot = self._slots.get(field.ptr)
             if slot is None:                         # first exchange of this array: collective
                 slot = self._slots[field.ptr] = self.comm.p2p_register(field.ptr)
             if slot >= 0:
+                if shared_from_lower:
+                    if dl.pull_args_low is None:
+                        dl.pull_args_low = self.comm.p2p_args(dl.pulls_low, self.dtype.itemsize)
+                    self.comm.p2p_exchange(slot, dl.pull_args_low)
+                    return
                 if dl.pull_args is None:
                     dl.pull_args = self.comm.p2p_args(dl.pulls, self.dtype.itemsize)
                 self.comm.p2p_exchange(slot, dl.pull_args)
                 return
-        self.comm.sendrecv(field.ptr, self.dtype.itemsize, dl.plan)
+        self.comm.sendrecv(field.ptr, self.dtype.itemsize, dl.plan_low if shared_from_lower else dl.plan)
 
     def check_transport(self):
         """Raise if a peer-memory halo exchange timed out (csrc/comm.cu sets a status word and
@@ -586,11 +610,17 @@ class DistributedMultigrid:
                     self._lib.check(lib.emg3d_b200_gauss_seidel(dl.win.ptr, e.ptr, s.ptr, 1, ldir, base))
                     self.exchange(dl, e)
                     continue
-                # sweep 0 is the descending one (classes of odd z-parity first)
+                # sweep 0 is the descending one (classes of odd z-parity first).  The half that
+                # relaxed the LOWER rank's top plane is followed by an exchange that carries the
+                # lower rank's copy of the shared fz layer upwards (its latest update); the other
+                # half by the default exchange.  Global parity (node colours, lines): ownership
+                # boundaries are even planes, the plane below an interface is odd = class bit 0
+                # = half 1; tile-fused point schedule: the lower rank's top tile is odd = half 2.
+                low_half = 2 if (ldir == 0 and dl.point_kind.value == 2) else 1
                 for half in ((2, 1) if sweep % 2 == 0 else (1, 2)):
                     self._lib.check(lib.emg3d_b200_gauss_seidel(
                         dl.win.ptr, e.ptr, s.ptr, 1, ldir, base | (half << 16)))
-                    self.exchange(dl, e)
+                    self.exchange(dl, e, shared_from_lower=(half == low_half))
 
     # ---- the cycle ---------------------------------------------------------------------
     def multigrid(self, var, level=0, new_cycmax=0):

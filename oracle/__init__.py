@@ -23,23 +23,62 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, 'libemg3d_oracle.so')
 
 
+_FASTPATH = os.path.join(_HERE, 'libemg3d_oracle_fast.so')
+
+
 def build(force=False):
-    """Compile the oracle with gcc (a few seconds)."""
-    if force or not os.path.exists(_LIBPATH) or any(
-            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIBPATH)
-            for f in ('emg3d_oracle.c', 'kernels.inc')):
-        subprocess.run(['make', '-C', _HERE, '-s', '-B'], check=True)
+    """Compile the oracle with gcc (a few seconds): the strict build and the fast-math build
+    used by :func:`noise_floor`."""
+    stale = lambda path: not os.path.exists(path) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(path)
+        for f in ('emg3d_oracle.c', 'kernels.inc', 'Makefile'))
+    if force or stale(_LIBPATH) or stale(_FASTPATH):
+        subprocess.run(['make', '-C', _HERE, '-s', '-B', 'all'], check=True)
 
 
 _lib = None
+_libs = {}
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = ctypes.CDLL(_LIBPATH)
+        _lib = _libs['strict'] = ctypes.CDLL(_LIBPATH)
     return _lib
+
+
+class variant:
+    """Context manager: run the oracle kernels from another build of the same sources.
+
+    ``'fast'`` = value-changing optimisations on (reassociation, FMA contraction), like the
+    reference's ``fastmath=True`` numba kernels; ``'strict'`` = the default build.
+    """
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global _lib
+        lib()
+        if self.name not in _libs:
+            _libs[self.name] = ctypes.CDLL({'fast': _FASTPATH, 'strict': _LIBPATH}[self.name])
+        self._prev, _lib = _lib, _libs[self.name]
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._prev
+
+
+def noise_floor(run):
+    """Rounding-noise floor of an oracle computation: ``run()`` must return an
+    array computed with the oracle; it is evaluated with the strict and with the fast-math
+    build and the relative L2 difference is returned together with the strict result."""
+    strict = np.asarray(run())
+    with variant('fast'):
+        fast = np.asarray(run())
+    return float(np.linalg.norm(fast - strict) / np.linalg.norm(strict)), strict
 
 
 def _p(a):

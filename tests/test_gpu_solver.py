@@ -81,6 +81,94 @@ def test_solve_color_converges_to_reference(eb, golden, prefix):
     print(f"{prefix}: multigrid cycles color {info['it_mg']} vs reference (lex) {c['it_mg']}")
 
 
+# The default ordering (multicolour) changes every iterate; it must reach the same solution.  All
+# five BASELINE.json config siblings at 32^3 and config 2 at 64^3, with the solver settings of
+# the configuration, both solvers run to tol = 1e-11: CUDA (colour) against the oracle (lex).
+# Config 3 (air at 1e8 Ohm.m) is compared where the problem is well conditioned: air lowered to
+# 1e4 Ohm.m, as in the golden 'config3_tight_' case.
+@pytest.mark.parametrize('name,n', [('config1', 32), ('config2', 32), ('config3', 32),
+                                     ('config4', 32), ('config5', 32), ('config2', 64)])
+def test_color_order_converges_to_the_oracle_solution(eb, name, n):
+    from emg3d_b200 import recipes
+    from oracle import mg
+    cfg = recipes.config(name, n)
+    if name in ('config3', 'config4'):           # marine model: air lowered to 1e4 Ohm.m
+        cfg['model'] = recipes.model_marine(cfg['h'], cfg['origin'], rho_air=1e4)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    sfield = eb.get_source_field(grid, cfg['source'], cfg['frequency'])
+    m = cfg['model']
+    vm = mg.VolumeModel(mg.Grid(cfg['h'], cfg['origin']), m['property_x'], m.get('property_y'),
+                        m.get('property_z'), None, None, cfg['frequency'])
+    # the configuration's solver settings on top of solve()'s defaults, spelled out for both
+    kw = dict(sslsolver=True, semicoarsening=True, linerelaxation=True)
+    kw.update(cfg['solver'])
+    if kw.pop('plain', False):
+        kw.update(sslsolver=False, semicoarsening=False, linerelaxation=False)
+    kw.update(tol=1e-11, maxit=60)               # (config 1 itself is a single V-cycle)
+    e_o, i_o = mg.solve(vm, np.asarray(sfield.field).copy(), **kw)
+    e_g, i_g = eb.solve(model, sfield, return_info=True, order='color', **kw)
+    print(f"{name} {n}^3: cycles colour {i_g['it_mg']} (ssl {i_g['it_ssl']}) vs lex oracle "
+          f"{i_o['it_mg']} (ssl {i_o['it_ssl']}); |e_color - e_lex| / |e_lex| = "
+          f"{rel_err(e_g.field, e_o):.2e}")
+    assert i_g['exit_message'] == 'CONVERGED' and i_o['exit_message'] == 'CONVERGED'
+    assert i_g['rel_error'] < 1e-11 and i_o['rel_error'] < 1e-11
+    assert abs(i_g['rel_error'] - i_o['rel_error']) < 1e-10
+    assert rel_err(e_g.field, e_o) < 1e-8
+    assert i_g['it_mg'] <= 2 * i_o['it_mg']
+
+
+def _oracle_case(eb, name, n):
+    from emg3d_b200 import recipes
+    from oracle import mg
+    cfg = recipes.config(name, n)
+    grid = eb.TensorMesh(cfg['h'], cfg['origin'])
+    model = eb.Model(grid, **cfg['model'])
+    sfield = eb.get_source_field(grid, cfg['source'], cfg['frequency'])
+    g = mg.Grid(cfg['h'], cfg['origin'])
+    m = cfg['model']
+    vm = mg.VolumeModel(g, m['property_x'], m.get('property_y'), m.get('property_z'), None, None,
+                        cfg['frequency'])
+    return model, sfield, vm
+
+
+# BASELINE.json configs[1] / configs[2] siblings at 64^3 and at the full 128^3 of configs[1]:
+# one F- resp. V-cycle with semicoarsening and line relaxation at their defaults, lexicographic
+# order, CUDA path against the C oracle run on the box (fields <= 1e-10, per-cycle
+# norms within 1e-10 ||b||; config 3 has air at 1e8 Ohm.m, where the oracle itself is only
+# defined to its fast-math-vs-strict self-difference -- the bound is 10 x that measured floor).
+@pytest.mark.parametrize('name,n,cycle', [('config2', 64, 'F'), ('config3', 64, 'V'),
+                                           ('config2', 128, 'F'), ('config3', 128, 'V')])
+def test_lex_cycle_matches_oracle_at_size(eb, name, n, cycle):
+    import oracle
+    from oracle import mg
+    model, sfield, vm = _oracle_case(eb, name, n)
+    kw = dict(cycle=cycle, maxit=1, semicoarsening=True, linerelaxation=True)
+    out = {}
+
+    def run():
+        e, out['info'] = mg.solve(vm, np.asarray(sfield.field).copy(), sslsolver=False, **kw)
+        return e
+
+    if n <= 64:
+        floor, e_o = oracle.noise_floor(run)
+    else:                       # one oracle run at full size; floor from the 64^3 sibling
+        model64, sfield64, vm64 = _oracle_case(eb, name, 64)
+        floor, _ = oracle.noise_floor(lambda: mg.solve(vm64, np.asarray(sfield64.field).copy(),
+                                                       sslsolver=False, **kw)[0])
+        e_o = run()
+    i_o = out['info']
+    e_g, i_g = eb.solve(model, sfield, sslsolver=False, return_info=True, order='lex', **kw)
+    err = rel_err(e_g.field, e_o)
+    tol = max(1e-10, 10 * floor)
+    print(f"{name} {n}^3 {cycle}-cycle sc+lr lex: |e_gpu - e_oracle| / |e_oracle| = {err:.2e} "
+          f"(oracle noise floor {floor:.1e}, bound {tol:.1e}); error after the cycle "
+          f"gpu {i_g['error_at_cycle'][1]:.9e} oracle {i_o['error_at_cycle'][1]:.9e}")
+    assert err < tol
+    assert abs(i_g['ref_error'] - i_o['ref_error']) <= 1e-13 * i_o['ref_error']
+    assert abs(i_g['error_at_cycle'][1] - i_o['error_at_cycle'][1]) <= max(1e-10, 10 * floor) * i_o['ref_error']
+
+
 def _normalise(log):
     """Drop wall-clock dependent parts of the log."""
     log = re.sub(r'\[\d\d:\d\d:\d\d\]', '[hh:mm:ss]', log)
