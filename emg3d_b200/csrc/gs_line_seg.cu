@@ -89,18 +89,28 @@ __device__ __forceinline__ void fma_t(cplx& acc, double a, cplx b) {
     acc.re = fma(a, b.re, acc.re);
     acc.im = fma(a, b.im, acc.im);
 }
-// The passes are one dependent chain per lane (one warp per scheduler): sums are evaluated as
-// pairs of independent halves to shorten the chain of dependent DFMAs.
 template <typename T>
-__device__ __forceinline__ void seg_symv4(const T x[10], const T v[4], T out[4]) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        T t0 = x[tri(r, 0)] * v[0];
-        T t1 = x[tri(r, 2)] * v[2];
-        fma_t(t0, x[tri(r, 1)], v[1]);
-        fma_t(t1, x[tri(r, 3)], v[3]);
-        out[r] = t0 + t1;
-    }
+__device__ __forceinline__ void seg_symv4(const T f[10], const T v[4], T out[4]) {
+    // out = S^{-1} v by substitution with the LDL^T factors (line_common.cuh: ldl4_factor), every
+    // product fused into its accumulation
+    T y0 = v[0], y1 = v[1], y2 = v[2], y3 = v[3];
+    fma_t(y1, -f[tri(1, 0)], y0);
+    fma_t(y2, -f[tri(2, 0)], y0);
+    fma_t(y3, -f[tri(3, 0)], y0);
+    fma_t(y2, -f[tri(2, 1)], y1);
+    fma_t(y3, -f[tri(3, 1)], y1);
+    fma_t(y3, -f[tri(3, 2)], y2);
+    y0 = f[tri(0, 0)] * y0;
+    y1 = f[tri(1, 1)] * y1;
+    y2 = f[tri(2, 2)] * y2;
+    y3 = f[tri(3, 3)] * y3;
+    fma_t(y2, -f[tri(3, 2)], y3);
+    fma_t(y1, -f[tri(3, 1)], y3);
+    fma_t(y0, -f[tri(3, 0)], y3);
+    fma_t(y1, -f[tri(2, 1)], y2);
+    fma_t(y0, -f[tri(2, 0)], y2);
+    fma_t(y0, -f[tri(1, 0)], y1);
+    out[0] = y0; out[1] = y1; out[2] = y2; out[3] = y3;
 }
 // E v with E = diag(d) + rl f f^T
 template <typename T>

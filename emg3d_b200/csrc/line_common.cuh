@@ -96,10 +96,15 @@ struct Line {
 // symmetric 4x4 in packed lower-triangular storage: (r, c), r >= c, at r (r+1)/2 + c
 __device__ __forceinline__ constexpr int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
-// x <- x^{-1} for a complex-symmetric (not Hermitian) 4x4 in packed lower-triangular
-// storage, through its LDL^T without pivoting.
+// LDL^T (no pivoting) of a complex-symmetric (not Hermitian) 4x4 in packed lower-triangular
+// storage, in place: the diagonal entries become 1 / D(j), the strict lower triangle the unit
+// factor L.  The blocks are applied by SUBSTITUTION with these factors (backward stable).  An
+// explicit inverse assembled from them (r1) is not: where the conductivity is tiny (air, 1e8 Ohm m)
+// the blocks are conditioned ~1e10 (the gradient of the node's hat function is almost in the null
+// space), the Schur recurrence S_m = D_m - E_m S_{m-1}^{-1} E_m then lost all digits after two
+// blocks and line relaxation diverged on the marine model from 64^3 cells on.
 template <typename T>
-__device__ __forceinline__ void inv4sym(T x[10]) {
+__device__ __forceinline__ void ldl4_factor(T x[10]) {
     T l[4][4], dinv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -108,7 +113,7 @@ __device__ __forceinline__ void inv4sym(T x[10]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (k < j) {
-                v[k] = l[j][k] * x[tri(k, k)];      // L(j,k) D(k); x(k,k) holds D(k)
+                v[k] = l[j][k] * x[tri(k, k)];      // L(j,k) D(k); x(k,k) still holds D(k)
                 dj -= l[j][k] * v[k];
             }
         x[tri(j, j)] = dj;
@@ -123,35 +128,30 @@ __device__ __forceinline__ void inv4sym(T x[10]) {
                 l[i][j] = t * dinv[j];
             }
     }
-    // inverse of the unit lower factor (strict lower part)
-    T li[4][4];
-    li[1][0] = -l[1][0];
-    li[2][1] = -l[2][1];
-    li[3][2] = -l[3][2];
-    li[2][0] = -l[2][0] - l[2][1] * li[1][0];
-    li[3][1] = -l[3][1] - l[3][2] * li[2][1];
-    li[3][0] = -l[3][0] - l[3][1] * li[1][0] - l[3][2] * li[2][0];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) {
-            // sum_{k >= r} li[k][r] dinv[k] li[k][c], li[k][k] = 1
-            T t = (r == c) ? dinv[r] : dinv[r] * li[r][c];
-#pragma unroll
-            for (int k = r + 1; k < 4; ++k) t += li[k][r] * dinv[k] * li[k][c];
-            x[tri(r, c)] = t;
-        }
-}
-
-template <typename T>
-__device__ __forceinline__ void symv4(const T x[10], const T v[4], T out[4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        T t = x[tri(r, 0)] * v[0];
+        x[tri(r, r)] = dinv[r];
 #pragma unroll
-        for (int c = 1; c < 4; ++c) t += x[tri(r, c)] * v[c];
-        out[r] = t;
+        for (int c = 0; c < 4; ++c)
+            if (c < r) x[tri(r, c)] = l[r][c];
     }
+}
+
+// out = S^{-1} v with the factors of ldl4_factor: L y = v, z = D^{-1} y, L^T out = z
+template <typename T>
+__device__ __forceinline__ void symv4(const T f[10], const T v[4], T out[4]) {
+    T y0 = v[0];
+    T y1 = v[1] - f[tri(1, 0)] * y0;
+    T y2 = v[2] - f[tri(2, 0)] * y0 - f[tri(2, 1)] * y1;
+    T y3 = v[3] - f[tri(3, 0)] * y0 - f[tri(3, 1)] * y1 - f[tri(3, 2)] * y2;
+    y0 = f[tri(0, 0)] * y0;
+    y1 = f[tri(1, 1)] * y1;
+    y2 = f[tri(2, 2)] * y2;
+    y3 = f[tri(3, 3)] * y3;
+    out[3] = y3;
+    out[2] = y2 - f[tri(3, 2)] * y3;
+    out[1] = y1 - f[tri(2, 1)] * out[2] - f[tri(3, 1)] * y3;
+    out[0] = y0 - f[tri(1, 0)] * out[1] - f[tri(2, 0)] * out[2] - f[tri(3, 0)] * y3;
 }
 
 // E v with E = diag(d) + rl f f^T  (d, f real; rl = 1/dL complex)
@@ -284,7 +284,7 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
         etp_c[j] = ldg(m.eta[A::p] + ln.cbase[j][0]) + ldg(m.eta[A::p] + ln.cbase[j][1]);
         etq_c[j] = ldg(m.eta[A::q] + ln.cbase[0][j]) + ldg(m.eta[A::q] + ln.cbase[1][j]);
     }
-    T X[10];                         // X_{m-1}
+    T X[10];                         // factors of S_{m-1}
     for (int i = 0; i < N - 1; ++i) {                        // node m = i + 1
         ln.load_zeta(i + 1, zn);
         double gn[4];
@@ -324,31 +324,33 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
 #pragma unroll
             for (int c = 0; c <= r; ++c)
                 S[tri(r, c)] -= (cc.f[r] * cc.f[c]) * rl_c + (cn.f[r] * cn.f[c]) * rl_n;
-        // S_m = D_m - E_m X_{m-1} E_m,  E_m = diag(d_c) + rl_c f_c f_c^T
+        // S_m = D_m - E_m S_{m-1}^{-1} E_m,  E_m = diag(d_c) + rl_c f_c f_c^T: column by column,
+        // Z e_c = S_{m-1}^{-1} (E_m e_c) by substitution with the previous block's factors
         if (i > 0) {
-            T fr[4], u[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) fr[k] = cc.f[k] * rl_c;          // rl_c f_c  (complex)
-            T fc[4];
+            for (int c = 0; c < 4; ++c) {
+                T ecol[4], z[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { fc[k] = zero_<T>(); add_real(fc[k], cc.f[k]); }
-            symv4<T>(X, fc, u);                                          // u = X f_c
-            T beta = cc.f[0] * u[0];
+                for (int r = 0; r < 4; ++r) {
+                    ecol[r] = (cc.f[c] * cc.f[r]) * rl_c;
+                    if (r == c) add_real(ecol[r], cc.d[c]);
+                }
+                symv4<T>(X, ecol, z);
+                T fz = cc.f[0] * z[0];
 #pragma unroll
-            for (int k = 1; k < 4; ++k) beta += cc.f[k] * u[k];          // f_c^T X f_c
+                for (int k = 1; k < 4; ++k) fz += cc.f[k] * z[k];
+                fz *= rl_c;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c)
-                    S[tri(r, c)] -= (cc.d[r] * cc.d[c]) * X[tri(r, c)] + (cc.d[r] * u[r]) * fr[c] +
-                                    fr[r] * (u[c] * cc.d[c]) + (fr[r] * fr[c]) * beta;
+                for (int r = 0; r < 4; ++r)
+                    if (r >= c) S[tri(r, c)] -= cc.d[r] * z[r] + cc.f[r] * fz;
+            }
         }
-        inv4sym<T>(S);
+        ldl4_factor<T>(S);
         T* out = QP == 0 ? fbase + (int64_t)i * FAC_BS : fbase + ((i & 7) * FAC_NE) * QP + (i >> 3);
         constexpr int es = QP == 0 ? FAC_ES : QP;
 #pragma unroll
         for (int e = 0; e < 10; ++e) {
-            out[e * es] = S[e];                   // the inverse (see gs_line.cu)
+            out[e * es] = S[e];                   // the LDL^T factors (see ldl4_factor)
             X[e] = S[e];
         }
         out[10 * es] = rl_n;

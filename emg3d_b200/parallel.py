@@ -46,16 +46,28 @@ __all__ = ['SlabPartition', 'exchange_plan', 'pull_plan', 'gather_plan', 'owned_
 class SlabPartition:
     """Ownership of node planes along z for ``nranks`` slabs and ``n_dist`` levels.
 
-    ``nz``: global number of cells along z on the finest grid.  Level ``l`` has
-    ``nz >> l`` cells.  Levels ``0 .. n_dist - 1`` are distributed, level
-    ``n_dist`` is the first replicated one (slabs exist there only to gather).
+    ``nz``: global number of cells along z on the finest grid.  Levels ``0 .. n_dist - 1`` are
+    distributed, level ``n_dist`` is the first replicated one (slabs exist there only to
+    gather).  ``zshifts[l]`` = number of z-coarsenings between level 0 and level ``l`` (default
+    ``l``: standard coarsening; with semicoarsening some transitions leave z alone), so level
+    ``l`` has ``nz >> zshifts[l]`` cells along z.  ``zmax`` (default ``zshifts[n_dist]``):
+    ownership boundaries on the finest grid are multiples of ``2**zmax`` and the local grid of
+    level 0 carries ``2**zmax`` halo planes below -- hierarchies of several semicoarsening
+    patterns share level 0 when they are built with a common ``zmax``.
     """
 
-    def __init__(self, nz, nranks, n_dist):
+    def __init__(self, nz, nranks, n_dist, zshifts=None, zmax=None):
         self.nz, self.nranks, self.n_dist = int(nz), int(nranks), int(n_dist)
-        align = 1 << self.n_dist
+        self.zshifts = list(range(self.n_dist + 1)) if zshifts is None else [int(z) for z in zshifts]
+        if len(self.zshifts) != self.n_dist + 1 or self.zshifts[0] != 0 or any(
+                b - a not in (0, 1) for a, b in zip(self.zshifts[:-1], self.zshifts[1:])):
+            raise ValueError(f"zshifts={zshifts} must start at 0 and grow by 0 or 1 per level")
+        self.zmax = self.zshifts[-1] if zmax is None else int(zmax)
+        if self.zmax < self.zshifts[-1]:
+            raise ValueError("zmax is smaller than the number of z-coarsenings")
+        align = 1 << self.zmax
         if self.nz % align:
-            raise ValueError(f"nz={nz} must be a multiple of 2**n_dist={align}")
+            raise ValueError(f"nz={nz} must be a multiple of 2**{self.zmax}={align}")
         nblocks = self.nz // align
         if nblocks < self.nranks:
             raise ValueError(f"nz={nz} gives {nblocks} aligned blocks for {nranks} ranks; "
@@ -68,11 +80,15 @@ class SlabPartition:
                 raise ValueError("a rank would own no plane on the coarsest distributed level")
 
     def nz_level(self, level):
-        return self.nz >> level
+        return self.nz >> self.zshifts[level]
+
+    def depth(self, level):
+        """Halo planes below the owned planes of a rank's local grid (ranks > 0)."""
+        return 1 << (self.zmax - self.zshifts[level])
 
     def bounds(self, level):
         """Owned plane ranges [B[r], B[r+1]) on ``level`` (plane 0 .. nz_level)."""
-        inner = [b >> level for b in self.bounds0[1:-1]]
+        inner = [b >> self.zshifts[level] for b in self.bounds0[1:-1]]
         return [0] + inner + [self.nz_level(level) + 1]
 
     def owned(self, level, rank):
@@ -82,8 +98,7 @@ class SlabPartition:
     def local(self, level, rank):
         """First and last node plane (inclusive) of the rank's local grid."""
         b = self.bounds(level)
-        depth = 1 << (self.n_dist - level)           # halo planes below
-        lo = 0 if rank == 0 else b[rank] - depth
+        lo = 0 if rank == 0 else b[rank] - self.depth(level)
         hi = self.nz_level(level) if rank == self.nranks - 1 else b[rank + 1]
         return lo, hi
 
@@ -157,7 +172,7 @@ def exchange_plan(part, level, rank, nx, ny, shared_from_lower=False):
         if depth_mine >= 2:                           # the layer exists in my local grid
             layer(0, rank - 1, p0 - 2)
     if rank < part.nranks - 1:                        # interface above: plane p1
-        depth_up = 1 << (part.n_dist - level)         # halo depth of the upper neighbour
+        depth_up = part.depth(level)                  # halo depth of the upper neighbour
         plane(1, rank + 1, p1 - 1)
         if shared_from_lower:
             layer(1, rank + 1, p1 - 1)
@@ -375,8 +390,76 @@ class _DLevel:
         lv.res_buffer().zero()
 
 
+class _Shape:
+    """Stand-in for a grid where only ``shape_cells`` matters (global level shapes)."""
+
+    def __init__(self, shape):
+        self.shape_cells = tuple(int(n) for n in shape)
+
+
+def hierarchy_plan(gshape, pattern, nranks, clevel, min_cells=1_000_000):
+    """Global shapes and transitions of the distributed levels of one semicoarsening pattern.
+
+    ``pattern``: the cycle's ``sc_dir`` (0 = standard coarsening, 1 / 2 / 3 = no coarsening along
+    x / y / z; solver.py:1482-1531).  Returns ``(shapes, trans, zshifts)``: ``shapes[l]`` the
+    GLOBAL cell shape of level ``l`` (``l = 0 .. n_dist``), ``trans[l]`` the effective pattern of
+    the transition ``l -> l + 1`` (which axes are halved), ``zshifts[l]`` the number of
+    z-coarsenings above level ``l``.  Level ``l >= 1`` is distributed while it has more than
+    ``min_cells`` cells (below that a level is launch-latency bound and replicating it is cheaper
+    than exchanging its halos), the level below it leaves every rank two planes, and the
+    hierarchy goes on below it (``clevel``: number of coarsening steps of the pattern).
+    """
+    from emg3d_b200 import core, solver
+    shapes, trans, zshifts = [tuple(int(n) for n in gshape)], [], [0]
+
+    def step(shape):
+        sc = int(solver._current_sc_dir(pattern, _Shape(shape)))
+        flag = core.SC_FLAGS[sc]
+        return sc, tuple(n // 2 if f else n for n, f in zip(shape, flag)), int(bool(flag[2]))
+
+    while True:
+        k = len(trans)                                   # levels 0 .. k exist; decide on k + 1
+        if k + 1 > clevel:
+            break
+        sc, nxt, dz = step(shapes[-1])
+        if nxt == shapes[-1]:
+            break
+        if k >= 1:
+            # level k becomes distributed only if it is big enough and level k + 1 still leaves
+            # two planes per rank
+            if int(np.prod(shapes[-1])) <= min_cells or nxt[2] // nranks < 2 or min(nxt[:2]) < 2:
+                break
+        shapes.append(nxt)
+        trans.append(sc)
+        zshifts.append(zshifts[-1] + dz)
+    if not trans:
+        raise ValueError("grid cannot be coarsened: nothing to distribute")
+    return shapes, trans, zshifts
+
+
+class _Chain:
+    """Distributed levels of one semicoarsening pattern (built on first use)."""
+
+    def __init__(self, dmg, pattern, shapes, trans, zshifts):
+        self.pattern, self.shapes, self.trans = pattern, shapes, trans
+        self.n_dist = len(trans)
+        self.part = SlabPartition(dmg.gshape[2], dmg.nranks, self.n_dist, zshifts, dmg.zmax)
+        self.levels = [dmg.level0]
+        for l in range(1, self.n_dist + 1):              # level n_dist: gather buffer only
+            child = self.levels[-1].lv.coarse(trans[l - 1])
+            self.levels.append(_DLevel(l, child, self.part, dmg.rank))
+        for dl, shp in zip(self.levels, shapes):
+            dl.gshape = shp
+        top = self.levels[self.n_dist]
+        tnx, tny = top.lv.shape[0], top.lv.shape[1]
+        self.glevel = dmg._build_global_level(self)
+        self.g_s, self.g_e = self.glevel.new_field(), self.glevel.new_field()
+        self.gather = gather_plan(self.part, self.n_dist, dmg.rank, tnx, tny)
+        self.scatter = scatter_ranges(self.part, self.n_dist, dmg.rank, tnx, tny)
+
+
 class DistributedMultigrid:
-    """Plain multigrid cycles of one solve on N GPUs (one instance per rank).
+    """One solve on N GPUs (one instance per rank): multigrid cycles and Krylov wrappers.
 
     Parameters
     ----------
@@ -386,12 +469,18 @@ class DistributedMultigrid:
     sfield : Field
         The GLOBAL source field.
     comm : NcclComm
+    semicoarsening, linerelaxation : as in :func:`emg3d_b200.solve`; they select the
+        hierarchies that are planned (one per semicoarsening pattern in the cycle).
     n_dist : int, optional
-        Number of distributed levels; default: the levels with more than about a
-        million cells (the coarser ones are replicated on every GPU).
+        Number of distributed levels (standard coarsening only); default: the levels with more
+        than about a million cells (the coarser ones are replicated on every GPU).
+    exact : bool
+        True (default): two halo exchanges per sweep, a true Gauss-Seidel sweep across slabs;
+        False: one exchange per sweep (see :meth:`smoothing`).
     """
 
-    def __init__(self, model, sfield, comm, n_dist=None, order=None, exact=None):
+    def __init__(self, model, sfield, comm, n_dist=None, order=None, exact=None,
+                 semicoarsening=False, linerelaxation=False):
         import os
         from emg3d_b200 import _lib, core, meshes, models, solver
         if exact is None:
@@ -404,24 +493,31 @@ class DistributedMultigrid:
         if not getattr(comm, 'p2p', False) and hasattr(comm, 'p2p_enable'):
             comm.p2p_enable()
         self.order = core.order_id(order)
-        self.gshape = tuple(model.grid.shape_cells)
+        self.gshape = tuple(int(n) for n in model.grid.shape_cells)
         nx, ny, nz = self.gshape
-        if n_dist is None:
-            # distribute the levels that are worth it (more than ~1 M cells: below that
-            # a level is launch-latency bound and replicating it is cheaper than
-            # exchanging its halos), as long as every rank keeps two owned planes
-            n_dist = 1
-            while (nz % (1 << (n_dist + 1)) == 0 and (nz >> (n_dist + 1)) // self.nranks >= 2
-                   and min(nx, ny) >> (n_dist + 1) >= 2
-                   and (nx * ny * nz) >> (3 * n_dist) > 1_000_000):
-                n_dist += 1
-        self.n_dist = n_dist
-        self.part = part = SlabPartition(nz, self.nranks, n_dist)
+        self.model_grid = model.grid
         self.dtype = np.dtype(np.asarray(sfield.field).dtype)
         self.frequency = sfield._frequency
 
+        # --- plan the hierarchies of every semicoarsening pattern of the cycle -----------
+        probe = solver.MGParameters(verb=-1, sslsolver=False, semicoarsening=semicoarsening,
+                                    linerelaxation=linerelaxation, shape_cells=self.gshape,
+                                    cycle='V')
+        self.patterns = sorted(set(int(v) for v in probe.raw_sc_cycle))
+        self._plans = {}
+        for pat in self.patterns:
+            if n_dist is not None and pat == 0:
+                shapes, trans, zs = hierarchy_plan(self.gshape, 0, self.nranks, int(n_dist), min_cells=0)
+            else:
+                shapes, trans, zs = hierarchy_plan(self.gshape, pat, self.nranks,
+                                                   int(probe.clevel[pat]) - 1)
+            self._plans[pat] = (shapes, trans, zs)
+        self.zmax = max(zs[-1] for _, _, zs in self._plans.values())
+        self.n_dist = len(self._plans[self.patterns[0]][1])       # (of the first pattern)
+
         # --- local finest level: sliced model, device-side VolumeModel -----------------
-        lo, hi = part.local(0, self.rank)
+        part0 = SlabPartition(nz, self.nranks, 0, [0], self.zmax)
+        lo, hi = part0.local(0, self.rank)
         g = model.grid
         nodes_z = np.r_[0., np.asarray(g.h[2]).cumsum()] + g.origin[2]
         lgrid = meshes.TensorMesh([g.h[0], g.h[1], np.asarray(g.h[2])[lo:hi]],
@@ -433,18 +529,12 @@ class DistributedMultigrid:
         lmodel = models.Model(lgrid, mapping=getattr(model.map, 'name', 'Resistivity'), **sl)
         lmodel.case = model.case
         lv0 = solver._Level.from_model(lmodel, sfield)
-        self.levels = [_DLevel(0, lv0, part, self.rank)]
-        for l in range(1, n_dist + 1):               # level n_dist: gather buffer only
-            self.levels.append(_DLevel(l, self.levels[-1].lv.coarse(0), part, self.rank))
-
-        # --- replicated coarse hierarchy: global level `n_dist` ----------------------
-        self.glevel = self._build_global_level(model, n_dist)
-        gl = self.glevel
-        self.g_s, self.g_e = gl.new_field(), gl.new_field()
-        top = self.levels[n_dist]
-        tnx, tny = top.lv.shape[0], top.lv.shape[1]
-        self._gather = gather_plan(part, n_dist, self.rank, tnx, tny)
-        self._scatter = scatter_ranges(part, n_dist, self.rank, tnx, tny)
+        self.part0 = part0
+        self.level0 = _DLevel(0, lv0, part0, self.rank)
+        self.level0.gshape = self.gshape
+        self._chains = {}
+        self.levels = self.chain(self.patterns[0]).levels         # (first pattern; kept for tools)
+        self.part = self.chain(self.patterns[0]).part
 
         # --- local source and field ----------------------------------------------------
         self.s = lv0.new_field()
@@ -452,6 +542,16 @@ class DistributedMultigrid:
         self.upload_source(sfield)
         self._sums = _lib.DeviceArray(8, np.float64)
         self._sums.zero()
+
+    def chain(self, pattern):
+        """Distributed hierarchy of a semicoarsening pattern (device levels built on first use)."""
+        pattern = int(pattern)
+        ch = self._chains.get(pattern)
+        if ch is None:
+            if pattern not in self._plans:
+                raise ValueError(f"semicoarsening pattern {pattern} was not planned for this solver")
+            ch = self._chains[pattern] = _Chain(self, pattern, *self._plans[pattern])
+        return ch
 
     def close(self):
         """Release the peer-memory mappings of this solver's arrays.  Call on every rank (and
@@ -463,25 +563,28 @@ class DistributedMultigrid:
         self._graphs.clear()
 
     # ---- setup helpers ------------------------------------------------------------
-    def _build_global_level(self, model, level):
+    def _build_global_level(self, chain):
         """First replicated level: all-gather the owned cell layers of the local
         coarse coefficient slabs (device to device) into global arrays."""
-        from emg3d_b200 import meshes, solver
+        from emg3d_b200 import core, meshes, solver
         _lib = self._lib
-        top = self.levels[level].lv
+        level = chain.n_dist
+        top = chain.levels[level].lv
         nx, ny = top.shape[0], top.shape[1]
-        nzg = self.part.nz_level(level)
-        f = 1 << level
-        g = model.grid
-        ch = [np.add.reduceat(np.asarray(h, dtype=float), np.arange(0, len(h), f)) for h in g.h]
+        nzg = chain.part.nz_level(level)
+        g = self.model_grid
+        ch = [np.asarray(h, dtype=float) for h in g.h]
+        for sc in chain.trans:                               # coarsen the global widths alike
+            flag = core.SC_FLAGS[sc]
+            ch = [np.add.reduceat(h, np.arange(0, len(h), 2)) if f else h for h, f in zip(ch, flag)]
         cgrid = meshes.BaseMesh(ch, g.origin)
         nxy = nx * ny
 
         def layers(r):                               # owned cell layers [l0, l1) of rank r
-            p0, p1 = self.part.owned(level, r)
+            p0, p1 = chain.part.owned(level, r)
             return max(p0 - 1, 0), p1 - 1
 
-        lo, _ = self.part.local(level, self.rank)
+        lo, _ = chain.part.local(level, self.rank)
 
         def gather(local):
             out = _lib.DeviceArray(nxy * nzg, local.dtype)
@@ -512,22 +615,25 @@ class DistributedMultigrid:
         _lib.sync()
         return solver._Level(cgrid, self.dtype, top.case, eta, zeta)
 
-    def _slab(self, field_1d, level=0):
-        """Local slab (with halos) of a global host field."""
-        nx, ny = self.gshape[0] >> level, self.gshape[1] >> level
-        out = np.empty(self.levels[level].lv.n_edges, dtype=self.dtype)
-        for goff, loff, n in scatter_ranges(self.part, level, self.rank, nx, ny):
+    def _slab(self, field_1d):
+        """Local slab (with halos) of a global host field (finest level)."""
+        nx, ny = self.gshape[0], self.gshape[1]
+        out = np.empty(self.level0.lv.n_edges, dtype=self.dtype)
+        for goff, loff, n in scatter_ranges(self.part0, 0, self.rank, nx, ny):
             out[loff:loff + n] = field_1d[goff:goff + n]
         return out
 
     def upload_source(self, sfield):
         self.s.upload(self._slab(np.asarray(sfield.field)))
 
-    def download_owned(self, out_global):
-        """Write the owned part of the local field into a global host array."""
-        loc = self.e.download()
+    def upload_field(self, efield, dst=None):
+        (self.e if dst is None else dst).upload(self._slab(np.asarray(efield.field)))
+
+    def download_owned(self, out_global, src=None):
+        """Write the owned part of a local field (default: e) into a global host array."""
+        loc = (self.e if src is None else src).download()
         nx, ny = self.gshape[0], self.gshape[1]
-        copies, _, _ = gather_plan(self.part, 0, self.rank, nx, ny)
+        copies, _, _ = gather_plan(self.part0, 0, self.rank, nx, ny)
         for loff, goff, n in copies:
             out_global[goff:goff + n] = loc[loff:loff + n]
 
@@ -586,6 +692,11 @@ class DistributedMultigrid:
         self.exchange(dl, r)
         return r
 
+    def apply(self, dl, src, dst):
+        """dst = A src on the owned planes (halos of src refreshed first)."""
+        self.exchange(dl, src)
+        self._lib.check(self._lib.load().emg3d_b200_apply(dl.win.ptr, src.ptr, dst.ptr))
+
     def smoothing(self, dl, s, e, nu, lr_dir):
         """``nu`` sweeps per line direction on the rank's window.
 
@@ -596,13 +707,15 @@ class DistributedMultigrid:
         Gauss-Seidel sweep, as on one GPU.  Relaxed variant (``exact=False``, what
         ``north_star`` words): one exchange per sweep, interface planes see values one sweep
         old (block-Jacobi across slabs) -- half the messages, weaker smoothing at interfaces.
+        z-lines cross the slabs: :meth:`zline_smoothing`.
         """
         solver, lib = self._solver, self._lib.load()
-        c_lr_dir = int(solver._current_lr_dir(lr_dir, dl.lv.grid))
+        c_lr_dir = int(solver._current_lr_dir(lr_dir, _Shape(dl.gshape)))
         dirs = solver._LR_DIRS[c_lr_dir] or (0,)
         for ldir in dirs:
             if ldir == 3:
-                raise NotImplementedError("z-line relaxation across z-slabs is not distributed")
+                self.zline_smoothing(dl, s, e, nu)
+                continue
             halves = self.exact and self.order == 1 and (ldir != 0 or dl.point_halves_ok)
             for sweep in range(int(nu)):
                 base = self.order | (sweep << 8)
@@ -622,23 +735,31 @@ class DistributedMultigrid:
                         dl.win.ptr, e.ptr, s.ptr, 1, ldir, base | (half << 16)))
                     self.exchange(dl, e, shared_from_lower=(half == low_half))
 
+    def zline_smoothing(self, dl, s, e, nu):
+        raise NotImplementedError("z-line relaxation across z-slabs is not distributed")
+
     # ---- the cycle ---------------------------------------------------------------------
-    def multigrid(self, var, level=0, new_cycmax=0):
+    def multigrid(self, var, level=0, new_cycmax=0, s=None, e=None):
         """Distributed counterpart of solver._multigrid (same control flow)."""
         solver, lib = self._solver, self._lib.load()
-        dl = self.levels[level]
-        s = self.s if level == 0 else dl.lv.s
-        e = self.e if level == 0 else dl.lv.e
+        ch = self.chain(var.sc_dir)
+        dl = ch.levels[level]
+        if level == 0:
+            s = self.s if s is None else s
+            e = self.e if e is None else e
+        else:
+            s, e = dl.lv.s, dl.lv.e
         it = 0
         if new_cycmax == 0 or var.cycle != 'F':
             cycmax = var.cycmax
         else:
             cycmax = new_cycmax
         cyc = 0
-        if level == 0 and getattr(var, 'e_is_zero', False):
+        if level == 0 and getattr(var, 'e_is_zero', False) and var.s_norm is not None:
             l2_last = float(var.s_norm)              # zero start field: ||r|| = ||s||
             var.e_is_zero = False
         else:
+            var.e_is_zero = False
             l2_last = self.residual(dl, s, e, norm=True) if level == 0 else 0.0
         l2_stag = np.ones(var.maxcycle) * l2_last
         if level == 0 and var.nu_init > 0:
@@ -646,13 +767,15 @@ class DistributedMultigrid:
         while level == 0 or it < cycmax:
             l2_prev = l2_last
             l2_stag[(it - 1) % var.maxcycle] = l2_last
+            if level == 0:
+                ch = self.chain(var.sc_dir)          # the pattern may change from cycle to cycle
             if var.nu_pre > 0:
                 self.smoothing(dl, s, e, var.nu_pre, var.lr_dir)
             res = self.residual(dl, s, e)
-            child = self.levels[level + 1]
+            child = ch.levels[level + 1]
             self._lib.check(lib.emg3d_b200_restrict(child.lv.handle.ptr, res.ptr, child.lv.s.ptr))
             child.lv.e.zero()
-            self._descend(var, child, level + 1, cycmax - cyc)
+            self._descend(var, ch, child, level + 1, cycmax - cyc)
             self._lib.check(lib.emg3d_b200_prolong(child.lv.handle.ptr, e.ptr, child.lv.e.ptr))
             self.exchange(dl, e)
             if var.nu_post > 0:
@@ -665,33 +788,31 @@ class DistributedMultigrid:
                 l2_last = self.residual(dl, s, e, norm=True)
                 self.check_transport()
                 solver._print_cycle_info(var, l2_last, l2_prev)
-                if var.lr_cycle:                         # as solver._multigrid (solver.py:639-642)
+                if var.sc_cycle:                         # as solver._multigrid (solver.py:639-642)
+                    var.sc_dir = next(var.sc_cycle)
+                if var.lr_cycle:
                     var.lr_dir = next(var.lr_cycle)
                 if solver._terminate(var, l2_last, l2_stag[(it - 1) % var.maxcycle], it):
                     break
         var.l2 = l2_last
 
-    def _descend(self, var, child, level, new_cycmax):
+    def _descend(self, var, ch, child, level, new_cycmax):
         """Everything between restriction to and prolongation from `child`.
 
         Below the finest level a visit is a fixed sequence of launches (smoothers,
         transfer kernels, halo-exchange kernels, the gather and the replicated coarse
-        sub-cycle; no norms, no host decisions), so the visit of level 1 is captured
-        into ONE CUDA graph per rank and replayed: the first visit runs eagerly (it
-        builds caches and registers the exchanged arrays with the neighbours), the
-        second is captured.  The exchange kernels keep their sequence number in device
-        memory.  OFF by default (EMG3D_B200_DIST_GRAPHS=1 enables it): with the NCCL
-        gather of the replicated levels inside the captured region the replay hung on
-        2 B200s in r1; until the gather runs over peer memory as well, the distributed
-        levels are launched eagerly (the replicated coarse levels still replay the
-        single-GPU graphs of solver._subcycle).
+        sub-cycle; no norms, no host decisions), so the visit of level 1 can be captured
+        into ONE CUDA graph per rank and replayed (EMG3D_B200_DIST_GRAPHS=1; off by default:
+        with the NCCL gather of the replicated levels inside the captured region the replay
+        hung on 2 B200s in r1; the replicated coarse levels still replay the single-GPU graphs
+        of solver._subcycle).
         """
         def run():
-            if level < self.n_dist:
+            if level < ch.n_dist:
                 self.multigrid(var, level, new_cycmax)
                 self.exchange(child, child.lv.e)
             else:
-                self._coarse_replicated(var, child, level, new_cycmax)
+                self._coarse_replicated(var, ch, child, level, new_cycmax)
 
         solver = self._solver
         import os
@@ -699,8 +820,8 @@ class DistributedMultigrid:
                 and var.verb <= 3
                 and not getattr(var, '_capturing', False)):
             return run()
-        key = (int(new_cycmax), var.cycle, int(var.lr_dir), solver._order(var), int(var.nu_pre),
-               int(var.nu_post), int(var.nu_coarse), tuple(var.clevel))
+        key = (int(new_cycmax), var.cycle, int(var.sc_dir), int(var.lr_dir), solver._order(var),
+               int(var.nu_pre), int(var.nu_post), int(var.nu_coarse), tuple(var.clevel))
         g = self._graphs.get(key)
         if g is None:
             self._graphs[key] = False
@@ -715,43 +836,239 @@ class DistributedMultigrid:
             self._graphs[key] = g
         g.launch()
 
-    def _coarse_replicated(self, var, top, level, new_cycmax):
+    def _coarse_replicated(self, var, ch, top, level, new_cycmax):
         """Gather the coarse source, solve the coarse sub-cycle redundantly, keep our slab."""
         isz = self.dtype.itemsize
         lib = self._lib.load()
-        copies, sends, recvs = self._gather
+        copies, sends, recvs = ch.gather
         for loff, goff, n in copies:
-            self._lib.check(lib.emg3d_b200_d2d(self.g_s.ptr + goff * isz, top.lv.s.ptr + loff * isz, n * isz))
-        self.comm.sendrecv_two(top.lv.s.ptr, self.g_s.ptr, isz, sends, recvs)
-        self.g_e.zero()
-        self._solver._multigrid(self.glevel, self.g_s, self.g_e, var, level=level,
+            self._lib.check(lib.emg3d_b200_d2d(ch.g_s.ptr + goff * isz, top.lv.s.ptr + loff * isz, n * isz))
+        self.comm.sendrecv_two(top.lv.s.ptr, ch.g_s.ptr, isz, sends, recvs)
+        ch.g_e.zero()
+        self._solver._multigrid(ch.glevel, ch.g_s, ch.g_e, var, level=level,
                                 new_cycmax=new_cycmax)
-        for goff, loff, n in self._scatter:
-            self._lib.check(lib.emg3d_b200_d2d(top.lv.e.ptr + loff * isz, self.g_e.ptr + goff * isz, n * isz))
+        for goff, loff, n in ch.scatter:
+            self._lib.check(lib.emg3d_b200_d2d(top.lv.e.ptr + loff * isz, ch.g_e.ptr + goff * isz, n * isz))
 
-    def solve(self, cycle='V', tol=1e-6, maxit=50, nu_init=0, nu_pre=2, nu_coarse=1, nu_post=2,
-              linerelaxation=False, verb=0, zero_start=True):
-        """Run multigrid cycles; returns the info dict of solver.solve."""
+    # ---- Krylov backend (solver._DeviceOps interface) ------------------------------------
+    class _Ops:
+        def __init__(self, dmg):
+            self.dmg, self.dl = dmg, dmg.level0
+            self.vec = dmg._solver._Vec(int(dmg.dtype.kind == 'c'), dmg.level0.lv.n_edges)
+
+        def new(self):
+            a = self.dmg.level0.lv.new_field()
+            return a
+
+        def norm(self, x):
+            return float(np.sqrt(self.dmg.sum_owned(self.dl, x).real))
+
+        def dot(self, x, y):
+            v = self.dmg.sum_owned(self.dl, x, y)
+            return v if self.dmg.dtype.kind == 'c' else v.real
+
+        def axpby(self, a, x, b, y):
+            self.vec.axpby(a, x, b, y)                  # (halo planes ride along; never read)
+
+        def matvec(self, src, dst):
+            self.dmg.apply(self.dl, src, dst)
+
+        def psolve(self, src, dst, var):
+            if var.cycle:
+                dst.zero()
+                var.e_is_zero, var.s_norm = True, None
+                self.dmg.exchange(self.dl, src)
+                self.dmg.multigrid(var, s=src, e=dst)
+            else:
+                dst.copy_from(src)
+
+        def residual_norm(self, s, x):
+            self.dmg.exchange(self.dl, x)
+            return self.dmg.residual(self.dl, s, x, norm=True)
+
+    # ---- solve ------------------------------------------------------------------------------
+    def solve(self, sslsolver=False, semicoarsening=False, linerelaxation=False, verb=0,
+              zero_start=True, **kwargs):
+        """Collective.  Arguments and info dict of :func:`emg3d_b200.solve` (``return_info`` is
+        implied); the field stays distributed (``download_owned``).  ``zero_start=False``: start
+        from the current content of ``self.e`` (halos are refreshed)."""
         solver = self._solver
-        lr_values = np.atleast_1d(linerelaxation)
-        if linerelaxation is True or any(int(v) not in (0, 1, 2, 6) for v in lr_values.ravel()):
-            raise ValueError("distributed line relaxation supports 0 (point), 1 (x), 2 (y) and 6 (x and "
-                             f"y) only: z-lines cross the z-slabs. Provided: {linerelaxation!r}.")
-        var = solver.MGParameters(verb=verb, sslsolver=False, semicoarsening=False,
+        if kwargs.pop('plain', False):
+            sslsolver = False if sslsolver is True else sslsolver
+            semicoarsening = False if semicoarsening is True else semicoarsening
+            linerelaxation = False if linerelaxation is True else linerelaxation
+        if sslsolver not in (False, True, 'bicgstab', 'cgs'):
+            raise ValueError("distributed Krylov wrappers: 'bicgstab' (True) and 'cgs'. "
+                             f"Provided: {sslsolver!r}.")
+        kwargs.pop('return_info', None)
+        var = solver.MGParameters(verb=verb, sslsolver=sslsolver, semicoarsening=semicoarsening,
                                   linerelaxation=linerelaxation, shape_cells=self.gshape,
-                                  cycle=cycle, tol=tol, maxit=maxit, nu_init=nu_init,
-                                  nu_pre=nu_pre, nu_coarse=nu_coarse, nu_post=nu_post)
+                                  return_info=True, **kwargs)
         var.order = {0: 'lex', 1: 'color'}[self.order]
-        if var.clevel[0] <= self.n_dist:
-            raise ValueError("grid too small for the requested number of distributed levels")
-        var.l2_refe = float(np.sqrt(self.sum_owned(self.levels[0], self.s).real))
+        if self.rank != 0:                               # one log, from rank 0
+            var.verb, var.log = -1, 0
+        missing = set(int(v) for v in var.raw_sc_cycle) - set(self._plans)
+        if missing:
+            raise ValueError(f"semicoarsening patterns {sorted(missing)} were not planned: pass "
+                             "`semicoarsening` to DistributedMultigrid")
+        for pat in set(int(v) for v in var.raw_sc_cycle):
+            if var.clevel[pat] <= len(self._plans[pat][1]):
+                raise ValueError("grid too small for the number of distributed levels")
+        var.cprint(f"\n:: emg3d START :: {var.time.now} :: v{solver.__version__}\n", 2)
+        var.cprint(var, 2)
+        var.l2_refe = float(np.sqrt(self.sum_owned(self.level0, self.s).real))
         var.error_at_cycle[0] = var.l2_refe
+        info = ""
         if zero_start:
             self.e.zero()
-            var.e_is_zero, var.s_norm = True, var.l2_refe
-        self.multigrid(var)
+            var.e_is_zero, var.s_norm = not var.sslsolver, var.l2_refe
+        else:
+            self.exchange(self.level0, self.e)
+            var.user_start = True
+        if var.l2_refe < 100 * np.finfo(float).tiny:
+            var.l2_refe = np.nan
+            var.sslsolver = var.cycle = None
+            var.exit_message = "CONVERGED"
+            info = "   > RETURN ZERO E-FIELD (provided sfield is zero)\n"
+            self.e.zero()
+        header = f"   [hh:mm:ss]  {'rel. error':<22}"
+        if var.sslsolver:
+            header += f"{'solver':<20}"
+            if var.cycle:
+                header += f"{'MG':<11} l s"
+            var.cprint(header + "\n", 3)
+        elif var.cycle:
+            var.cprint(header + f"{'[abs. error, last/prev]':>29}   l s\n", 3)
+        if var.sslsolver:
+            solver._krylov(None, self.s, self.e, var, ops=self._Ops(self))
+        elif var.cycle:
+            self.multigrid(var)
         self.check_transport()
-        return {'exit': int(var.exit_message != 'CONVERGED'), 'exit_message': var.exit_message,
-                'abs_error': var.l2, 'rel_error': var.l2 / var.l2_refe, 'ref_error': var.l2_refe,
-                'it_mg': var.it, 'error_at_cycle': var.error_at_cycle,
-                'runtime_at_cycle': var.runtime_at_cycle}
+        var.do_return = False
+        return solver._finish(var, None, info)
+
+
+# =========================================================================== #
+# One API for one and many GPUs: emg3d_b200.solve(..., comm= / n_gpus=)
+# =========================================================================== #
+
+def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
+                      linerelaxation=True, verb=0, efield=None, order=None, always_return=False,
+                      return_info=False, exact=None, **kwargs):
+    """What ``emg3d_b200.solve(model, sfield, ..., comm=comm)`` runs: COLLECTIVE over the ranks of
+    ``comm`` (one process per GPU; every rank passes the same global model, source field and
+    options).  Same arguments, log, info dict and return conventions as the single-GPU solve;
+    every rank receives the whole field."""
+    from emg3d_b200 import _lib, fields
+    if kwargs.pop('plain', False):
+        sslsolver = False if sslsolver is True else sslsolver
+        semicoarsening = False if semicoarsening is True else semicoarsening
+        linerelaxation = False if linerelaxation is True else linerelaxation
+    kwargs.pop('workspace', None)
+    if sfield.frequency is None and getattr(sfield, '_frequency', None) is None:
+        raise ValueError("Source field is missing frequency information.")
+    dmg = DistributedMultigrid(model, sfield, comm, order=order, exact=exact,
+                               semicoarsening=semicoarsening, linerelaxation=linerelaxation)
+    try:
+        do_return = efield is None or always_return
+        if efield is not None:
+            if sfield.field.dtype != efield.field.dtype:
+                raise ValueError(
+                    "Source field and electric field must have the same "
+                    "dtype; complex (f-domain) or real (s-domain). Provided:"
+                    f"sfield: {sfield.field.dtype}; efield: {efield.field.dtype}.")
+            dmg.upload_field(efield)
+            # PEC: tangential edges on the six GLOBAL boundary faces are zero (solver.py:350-355);
+            # the local z-boundaries of inner ranks are halo planes, refreshed by the solve
+            _lib.check(_lib.load().emg3d_b200_pec_zero(dmg.level0.lv.handle.ptr, dmg.e.ptr))
+        info = dmg.solve(sslsolver=sslsolver, semicoarsening=semicoarsening,
+                         linerelaxation=linerelaxation, verb=verb, zero_start=efield is None,
+                         **kwargs)
+        # assemble the field on every rank: owned parts into a zeroed global device array, summed
+        n = int(model.grid.n_edges)
+        full = _lib.DeviceArray(n, dmg.dtype)
+        full.zero()
+        isz = dmg.dtype.itemsize
+        copies, _, _ = gather_plan(dmg.part0, 0, dmg.rank, dmg.gshape[0], dmg.gshape[1])
+        lib = _lib.load()
+        for loff, goff, cnt in copies:
+            _lib.check(lib.emg3d_b200_d2d(full.ptr + goff * isz, dmg.e.ptr + loff * isz, cnt * isz))
+        comm.allreduce_sum(full, n * (2 if dmg.dtype.kind == 'c' else 1))
+        if efield is None:
+            efield = fields.Field(model.grid, dtype=dmg.dtype, frequency=sfield._frequency)
+        elif efield.frequency is None:
+            efield._frequency = sfield._frequency
+        full.download(out=np.asarray(efield.field).view(np.ndarray))
+    finally:
+        dmg.close()
+    if do_return and return_info:
+        return efield, info
+    if do_return:
+        return efield
+    if return_info:
+        return info
+
+
+def _spawned_rank(rank, nranks, uid, model, field, frequency, kwargs, queue):
+    """Worker of :func:`solve_spawn`: one rank of one distributed solve."""
+    try:
+        import emg3d_b200 as eb
+        from emg3d_b200 import _lib
+        _lib.init(rank)
+        comm = NcclComm(rank, nranks, lambda obj: uid)
+        sfield = eb.Field(model.grid, field, frequency=frequency)
+        kw = dict(kwargs)
+        start = kw.pop('efield_array', None)
+        if start is not None:
+            kw['efield'] = eb.Field(model.grid, start, frequency=frequency)
+            kw['always_return'] = True
+        kw['return_info'] = True
+        out = solve_distributed(model, sfield, comm, **kw)
+        comm.destroy()
+        if rank == 0:
+            queue.put(('ok', np.asarray(out[0].field), out[1]))
+    except BaseException as err:            # noqa: BLE001 -- report, the parent re-raises
+        import traceback
+        queue.put(('error', rank, traceback.format_exc()))
+        raise
+
+
+def solve_spawn(model, sfield, n_gpus, efield=None, return_info=False, always_return=False,
+                **kwargs):
+    """What ``emg3d_b200.solve(model, sfield, ..., n_gpus=N)`` runs from a single process: spawns
+    one rank per GPU (devices 0 .. N-1), runs :func:`solve_distributed` in them and returns rank
+    0's result.  Convenience mode: model and fields are pickled to the workers; inside a
+    multi-process launch (torchrun, mpirun) pass ``comm=`` instead."""
+    import ctypes
+    import multiprocessing as mp
+    from emg3d_b200 import _lib, fields
+    uid = ctypes.create_string_buffer(128)
+    _lib.check(_lib.load().emg3d_b200_comm_unique_id(uid))
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    kw = dict(kwargs)
+    if efield is not None:
+        kw['efield_array'] = np.asarray(efield.field)
+    procs = [ctx.Process(target=_spawned_rank,
+                         args=(r, int(n_gpus), bytes(uid.raw), model, np.asarray(sfield.field),
+                               sfield._frequency, kw, queue)) for r in range(int(n_gpus))]
+    for pr in procs:
+        pr.start()
+    msg = queue.get()
+    for pr in procs:
+        pr.join()
+    if msg[0] != 'ok':
+        raise _lib.Emg3dB200Error(f"distributed solve failed on rank {msg[1]}:\n{msg[2]}")
+    _, arr, info = msg
+    if efield is not None:
+        np.asarray(efield.field).view(np.ndarray)[:] = arr
+        out = efield
+    else:
+        out = fields.Field(model.grid, arr, frequency=sfield._frequency)
+    do_return = efield is None or always_return
+    if do_return and return_info:
+        return out, info
+    if do_return:
+        return out
+    if return_info:
+        return info

@@ -391,7 +391,24 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
         Keeps the device-resident coefficients, grid hierarchy and line
         factorisations of ``model`` alive between calls (many sources or
         restarts on one model and frequency).
+    comm : parallel.NcclComm, optional
+        ONE solve on the GPUs of ``comm`` (z-slabs, one process per GPU): a collective call,
+        every rank passes the same arguments and receives the whole field.
+    n_gpus : int, optional
+        Same from a single process: the ranks are spawned (devices 0 .. n_gpus - 1).
     """
+    # one solve on several GPUs (z-slab decomposition, emg3d_b200.parallel): `comm=` inside a
+    # multi-process launch (collective call), or `n_gpus=` to spawn the ranks from here
+    comm, n_gpus = kwargs.pop('comm', None), kwargs.pop('n_gpus', None)
+    if comm is not None or (n_gpus is not None and int(n_gpus) > 1):
+        from emg3d_b200 import parallel
+        if comm is not None:
+            return parallel.solve_distributed(model, sfield, comm, sslsolver=sslsolver,
+                                              semicoarsening=semicoarsening,
+                                              linerelaxation=linerelaxation, verb=verb, **kwargs)
+        return parallel.solve_spawn(model, sfield, int(n_gpus), sslsolver=sslsolver,
+                                    semicoarsening=semicoarsening, linerelaxation=linerelaxation,
+                                    verb=verb, **kwargs)
     always_return = kwargs.pop('always_return', False)
     if kwargs.pop('plain', False):
         sslsolver = False if sslsolver is True else sslsolver
@@ -503,6 +520,11 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     # Bring the result back into the (possibly user-provided) host field.
     d_e.download(out=efield.field.view(np.ndarray))
 
+    return _finish(var, efield, info)
+
+
+def _finish(var, efield, info):
+    """Closing log lines, info dict and return convention of :func:`solve` (solver.py:407-449)."""
     exit_status = int(var.exit_message != 'CONVERGED')
 
     if var.verb in [1, 2]:
@@ -521,6 +543,7 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     elif var.verb == 0 and exit_status == 1:
         var.cprint(f"* WARNING :: {var.exit_message}", -1)
 
+    info_dict = None
     if var.return_info:
         info_dict = {
             'exit': exit_status,
@@ -840,13 +863,52 @@ class _Vec:
                                              b.real, b.imag, y.ptr))
 
 
-def _krylov(lv, s, e, var):
-    """Krylov solvers with multigrid as preconditioner (solver.py:652-784)."""
+class _DeviceOps:
+    """What the device-resident Krylov solvers need from a (single- or multi-GPU) backend:
+    vector algebra, the operator, the multigrid preconditioner and the residual norm."""
+
+    def __init__(self, lv):
+        self.lv, self.vec = lv, _Vec(lv.cplx, lv.n_edges)
+        self.lib = _lib.load()
+
+    def new(self):
+        return _lib.DeviceArray(self.lv.n_edges, self.lv.dtype)
+
+    def norm(self, x):
+        return self.vec.norm(x)
+
+    def dot(self, x, y):
+        return self.vec.dot(x, y)
+
+    def axpby(self, a, x, b, y):
+        self.vec.axpby(a, x, b, y)
+
+    def matvec(self, src, dst):
+        _lib.check(self.lib.emg3d_b200_apply(self.lv.handle.ptr, src.ptr, dst.ptr))
+
+    def psolve(self, src, dst, var):
+        if var.cycle:
+            dst.zero()
+            var.e_is_zero, var.s_norm = True, None      # preconditioner starts from zero
+            _multigrid(self.lv, src, dst, var)
+        else:
+            dst.copy_from(src)
+
+    def residual_norm(self, s, x):
+        return _dev_residual(self.lv, s, x, norm=True)
+
+
+def _krylov(lv, s, e, var, ops=None):
+    """Krylov solvers with multigrid as preconditioner (solver.py:652-784).
+
+    ``ops``: backend (default: this GPU, :class:`_DeviceOps`); the multi-GPU driver passes its own.
+    """
+    ops = _DeviceOps(lv) if ops is None else ops
 
     def record(x):
         var.ssl_it += 1
         var.runtime_at_cycle = np.r_[var.runtime_at_cycle, var.time.elapsed]
-        var.l2 = _dev_residual(lv, s, x, norm=True)
+        var.l2 = ops.residual_norm(s, x)
         var.error_at_cycle = np.r_[var.error_at_cycle, var.l2]
         if var.verb > 3:
             log = f"   [{var.time.now}]   {var.l2/var.l2_refe:.3e} "
@@ -864,7 +926,9 @@ def _krylov(lv, s, e, var):
     x0 = e.copy() if getattr(var, 'user_start', False) else None
     try:
         if var.sslsolver == 'bicgstab':
-            i = _bicgstab(lv, s, e, var, record)
+            i = _bicgstab(ops, s, e, var, record)
+        elif var.sslsolver == 'cgs':
+            i = _cgs(ops, s, e, var, record)
         else:
             i = _scipy_krylov(lv, s, e, var, record)
     except _ConvergenceError:
@@ -892,8 +956,8 @@ def _krylov(lv, s, e, var):
     var.cprint(pre + var.exit_message, 2)
 
 
-def _bicgstab(lv, b, x, var, callback):
-    """Preconditioned BiCGSTAB on the device.
+def _bicgstab(ops, b, x, var, callback):
+    """Preconditioned BiCGSTAB on the device(s).
 
     Same recurrence, breakdown tests and stopping rule as
     ``scipy.sparse.linalg.bicgstab`` (SciPy 1.18, ``_isolve/iterative.py``),
@@ -901,19 +965,7 @@ def _bicgstab(lv, b, x, var, callback):
     ``atol=1e-30``, ``maxiter=ssl_maxit`` and a callback per iteration.
     Returns SciPy's ``info`` code.
     """
-    lib = _lib.load()
-    vec = _Vec(lv.cplx, lv.n_edges)
-    matvec = lambda src, dst: _lib.check(lib.emg3d_b200_apply(lv.handle.ptr, src.ptr, dst.ptr))
-
-    def psolve(src, dst):
-        if var.cycle:
-            dst.zero()
-            var.e_is_zero, var.s_norm = True, None      # preconditioner starts from zero
-            _multigrid(lv, src, dst, var)
-        else:
-            dst.copy_from(src)
-
-    bnrm2 = vec.norm(b)
+    bnrm2 = ops.norm(b)
     atol = max(1e-30, float(var.tol) * bnrm2)
     if bnrm2 == 0:
         x.copy_from(b)
@@ -921,55 +973,110 @@ def _bicgstab(lv, b, x, var, callback):
     rhotol = np.finfo(np.float64).eps ** 2
     omegatol = rhotol
 
-    new = lambda: _lib.DeviceArray(lv.n_edges, lv.dtype)
-    r, rtilde, p, v, s_, t, phat, shat = (new() for _ in range(8))
+    r, rtilde, p, v, s_, t, phat, shat = (ops.new() for _ in range(8))
     # r = b - A x (x may be a user-provided start field)
-    if vec.norm(x) > 0:
-        matvec(x, r)
-        vec.axpby(1.0, b, -1.0, r)
+    if ops.norm(x) > 0:
+        ops.matvec(x, r)
+        ops.axpby(1.0, b, -1.0, r)
     else:
         r.copy_from(b)
     rtilde.copy_from(r)
     rho_prev = omega = alpha = None
 
     for iteration in range(var.ssl_maxit):
-        if vec.norm(r) < atol:
+        if ops.norm(r) < atol:
             return 0
-        rho = vec.dot(rtilde, r)
+        rho = ops.dot(rtilde, r)
         if abs(rho) < rhotol:
             return -10
         if iteration > 0:
             if abs(omega) < omegatol:
                 return -11
             beta = (rho / rho_prev) * (alpha / omega)
-            vec.axpby(-omega, v, 1.0, p)      # p -= omega v
-            vec.axpby(1.0, r, beta, p)        # p = beta p + r
+            ops.axpby(-omega, v, 1.0, p)      # p -= omega v
+            ops.axpby(1.0, r, beta, p)        # p = beta p + r
         else:
             p.copy_from(r)
-        psolve(p, phat)
-        matvec(phat, v)
-        rv = vec.dot(rtilde, v)
+        ops.psolve(p, phat, var)
+        ops.matvec(phat, v)
+        rv = ops.dot(rtilde, v)
         if rv == 0:
             return -11
         alpha = rho / rv
-        vec.axpby(-alpha, v, 1.0, r)          # r -= alpha v
+        ops.axpby(-alpha, v, 1.0, r)          # r -= alpha v
         s_.copy_from(r)
-        if vec.norm(s_) < atol:
-            vec.axpby(alpha, phat, 1.0, x)
+        if ops.norm(s_) < atol:
+            ops.axpby(alpha, phat, 1.0, x)
             return 0
-        psolve(s_, shat)
-        matvec(shat, t)
-        omega = vec.dot(t, s_) / vec.dot(t, t)
-        vec.axpby(alpha, phat, 1.0, x)
-        vec.axpby(omega, shat, 1.0, x)
-        vec.axpby(-omega, t, 1.0, r)
+        ops.psolve(s_, shat, var)
+        ops.matvec(shat, t)
+        omega = ops.dot(t, s_) / ops.dot(t, t)
+        ops.axpby(alpha, phat, 1.0, x)
+        ops.axpby(omega, shat, 1.0, x)
+        ops.axpby(-omega, t, 1.0, r)
+        rho_prev = rho
+        callback(x)
+    return var.ssl_maxit
+
+
+def _cgs(ops, b, x, var, callback):
+    """Preconditioned CGS on the device(s): recurrence, breakdown tests, stopping rule and the
+    recomputed true residual of ``scipy.sparse.linalg.cgs`` (SciPy 1.18), which the reference
+    calls for ``sslsolver='cgs'`` (solver.py:763-765).  Returns SciPy's ``info`` code."""
+    bnrm2 = ops.norm(b)
+    atol = max(1e-30, float(var.tol) * bnrm2)
+    if bnrm2 == 0:
+        x.copy_from(b)
+        return 0
+    rhotol = np.finfo(np.float64).eps ** 2
+    r, rtilde, p, u, q, phat, vhat, uq, uhat = (ops.new() for _ in range(9))
+
+    def true_residual():                      # r = b - A x
+        ops.matvec(x, r)
+        ops.axpby(1.0, b, -1.0, r)
+
+    if ops.norm(x) > 0:
+        true_residual()
+    else:
+        r.copy_from(b)
+    rtilde.copy_from(r)
+    rho_prev = None
+    for iteration in range(var.ssl_maxit):
+        if ops.norm(r) < atol:
+            return 0
+        rho = ops.dot(rtilde, r)
+        if abs(rho) < rhotol:
+            return -10
+        if iteration > 0:
+            beta = rho / rho_prev
+            u.copy_from(r)
+            ops.axpby(beta, q, 1.0, u)        # u = r + beta q
+            ops.axpby(1.0, q, beta, p)        # p = beta p + q
+            ops.axpby(1.0, u, beta, p)        # p = beta (beta p + q) + u
+        else:
+            p.copy_from(r)
+            u.copy_from(r)
+        ops.psolve(p, phat, var)
+        ops.matvec(phat, vhat)
+        rv = ops.dot(rtilde, vhat)
+        if rv == 0:
+            return -11
+        alpha = rho / rv
+        q.copy_from(u)
+        ops.axpby(-alpha, vhat, 1.0, q)       # q = u - alpha vhat
+        uq.copy_from(u)
+        ops.axpby(1.0, q, 1.0, uq)
+        ops.psolve(uq, uhat, var)
+        ops.axpby(alpha, uhat, 1.0, x)
+        true_residual()
         rho_prev = rho
         callback(x)
     return var.ssl_maxit
 
 
 def _scipy_krylov(lv, s, e, var, callback):
-    """CGS / GCROT(m,k): SciPy drives, the GPU applies A and the preconditioner."""
+    """GCROT(m,k): SciPy drives, the GPU applies A and the preconditioner (full vectors cross
+    PCIe per application; BiCGSTAB and CGS are device-resident, see above)."""
     lib = _lib.load()
     n = lv.n_edges
     d_in, d_out = lv.new_field(False), lv.new_field(False)

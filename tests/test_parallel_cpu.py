@@ -255,3 +255,84 @@ def test_exchange_and_gather_with_gloo_world_size_2():
         results = manager.dict()
         mp.spawn(_gloo_worker, args=(world, port, 32, 2, 5, 3, results), nprocs=world, join=True)
         assert dict(results) == {0: True, 1: True}
+
+
+# ---- semicoarsening: per-level z-shifts and the planning of the distributed hierarchies --------
+
+@pytest.mark.parametrize('nz,nranks,zshifts,zmax', [(64, 2, [0, 0, 1, 1], 3), (256, 4, [0, 1, 1, 2], 2),
+                                                      (128, 8, [0, 0, 0], 1), (64, 4, [0, 1, 2], 2)])
+def test_partition_with_z_shifts(nz, nranks, zshifts, zmax):
+    """Levels that do not coarsen z keep plane ownership; local grids stay nested; level 0 depends
+    on (nz, nranks, zmax) only, so hierarchies of several patterns share it."""
+    n_dist = len(zshifts) - 1
+    part = parallel.SlabPartition(nz, nranks, n_dist, zshifts, zmax)
+    ref0 = parallel.SlabPartition(nz, nranks, 0, [0], zmax)
+    for r in range(nranks):
+        assert part.local(0, r) == ref0.local(0, r) and part.owned(0, r) == ref0.owned(0, r)
+    for level in range(n_dist + 1):
+        assert part.nz_level(level) == nz >> zshifts[level]
+        b = part.bounds(level)
+        assert b[0] == 0 and b[-1] == part.nz_level(level) + 1
+        for r in range(nranks):
+            lo, hi = part.local(level, r)
+            p0, p1 = part.owned(level, r)
+            assert 0 <= lo <= p0 and p1 - 1 <= hi <= part.nz_level(level)
+            if r > 0:
+                assert p0 - lo == part.depth(level) == 2 ** (zmax - zshifts[level])
+            if level < n_dist:
+                clo, chi = part.local(level + 1, r)
+                if zshifts[level + 1] == zshifts[level]:
+                    assert (clo, chi) == (lo, hi) and part.owned(level + 1, r) == (p0, p1)
+                else:
+                    assert lo % 2 == 0 and (hi - lo) % 2 == 0 and (clo, chi) == (lo // 2, hi // 2)
+    # halo plans of neighbouring ranks still pair up on every level
+    for level in range(n_dist):
+        for r in range(nranks):
+            parallel.pull_plan(part, level, r, 6, 5)
+            parallel.pull_plan(part, level, r, 6, 5, shared_from_lower=True)
+
+
+def test_hierarchy_plan_follows_the_single_gpu_coarsening():
+    """Global shapes / transitions of the distributed levels equal what the single-GPU driver
+    does level by level (solver._current_sc_dir), for every semicoarsening pattern."""
+    from emg3d_b200 import core, solver
+    shape = (512, 512, 256)
+    var = solver.MGParameters(verb=-1, sslsolver=False, semicoarsening=True, linerelaxation=True,
+                              shape_cells=shape, cycle='F')
+    assert sorted(set(var.raw_sc_cycle)) == [1, 2, 3]
+    for pat in (0, 1, 2, 3):
+        shapes, trans, zs = parallel.hierarchy_plan(shape, pat, 4, int(var.clevel[pat]) - 1)
+        assert shapes[0] == shape and len(shapes) == len(trans) + 1 == len(zs)
+        cur = shape
+        for l, sc in enumerate(trans):
+            assert sc == int(solver._current_sc_dir(pat, parallel._Shape(cur)))
+            flag = core.SC_FLAGS[sc]
+            cur = tuple(n // 2 if f else n for n, f in zip(cur, flag))
+            assert cur == shapes[l + 1] and zs[l + 1] == zs[l] + int(bool(flag[2]))
+        # every distributed level (but the finest) has more than a million cells; the first
+        # replicated one leaves two planes per rank
+        assert all(int(np.prod(s)) > 1_000_000 for s in shapes[1:-1])
+        assert shapes[-1][2] // 4 >= 2
+        if pat == 3:
+            assert zs[-1] == 0                      # z is never coarsened: slabs keep their planes
+        if pat == 1:
+            assert all(s[0] == 512 for s in shapes)
+    with pytest.raises(ValueError):
+        parallel.hierarchy_plan((2, 2, 2), 0, 2, 0)
+
+
+def test_shared_layer_direction_of_the_exchange_plans():
+    """The fz layer between the planes next to an interface travels downwards by default and
+    upwards with shared_from_lower (the lower rank relaxed it last); everything else is equal."""
+    part = parallel.SlabPartition(32, 2, 1)
+    nx, ny = 4, 3
+    up0 = parallel.exchange_plan(part, 0, 0, nx, ny)
+    lo0 = parallel.exchange_plan(part, 0, 0, nx, ny, shared_from_lower=True)
+    up1 = parallel.exchange_plan(part, 0, 1, nx, ny)
+    lo1 = parallel.exchange_plan(part, 0, 1, nx, ny, shared_from_lower=True)
+    pz = (nx + 1) * (ny + 1)
+    only = lambda a, b: [x for x in a if x not in b]
+    assert [(s, c) for s, _, _, c in only(up0, lo0)] == [(0, pz)]      # rank 0 receives the layer ...
+    assert [(s, c) for s, _, _, c in only(lo0, up0)] == [(1, pz)]      # ... or sends it
+    assert [(s, c) for s, _, _, c in only(up1, lo1)] == [(1, pz)]
+    assert [(s, c) for s, _, _, c in only(lo1, up1)] == [(0, pz)]
