@@ -70,6 +70,7 @@ _SIGNATURES = {
     'emg3d_b200_level_window': (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int]),
     'emg3d_b200_level_set_owned': (c_int, [c_void_p, c_int, c_int]),
     'emg3d_b200_level_set_zflip': (c_int, [c_void_p, c_int]),
+    'emg3d_b200_level_line_chain': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_point_schedule_kind': (c_int, [c_void_p, POINTER(c_int)]),
     'emg3d_b200_level_factor_bytes': (c_int, [c_void_p, c_int, POINTER(c_size_t)]),
     'emg3d_b200_level_drop_factors': (c_int, [c_void_p]),

@@ -62,6 +62,8 @@ struct emg3d_b200_level {
     const double* zeta;
     void* fac[3];        // cached line factorisations (device), per direction
     void* fac2[3];       // cached data of the segment-parallel line kernels (gs_line_seg.cu)
+    void* chain_in[3];   // lines cut by multi-GPU slabs: factors entering from the lower rank (owned)
+    int chained[3];      // the direction's lines continue on other ranks (emg3d_b200_level_line_chain)
     void* diag;          // cached diagonal of A per edge (device), point smoother
     double* scratch;     // residual-norm partials
     double* norm2;       // device scalar
@@ -492,6 +494,7 @@ int emg3d_b200_level_destroy(emg3d_b200_level* lv) {
         if (g_levels[i] == lv) { g_levels.erase(g_levels.begin() + i); break; }
     emg3d_b200_level_drop_factors(lv);
     for (int a = 0; a < 3; ++a) {
+        if (lv->chain_in[a]) cudaFree(lv->chain_in[a]);
         if (!lv->is_window) {
             cudaFree(lv->h[a]);
             cudaFree(lv->rh[a]);
@@ -672,7 +675,7 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
     const int dir = ldir - 1;
     const size_t el = lv->cplx ? sizeof(cplx) : sizeof(double);
     // long lines in multicolour order: segment-parallel kernels with their own cached data
-    const bool seg = (order & 0xff) == ORDER_COLOR && line_seg_elems(lv->d, dir) > 0;
+    const bool seg = (order & 0xff) == ORDER_COLOR && !lv->chained[dir] && line_seg_elems(lv->d, dir) > 0;
     if (seg && !lv->fac2[dir]) {
         const size_t nbytes = (size_t)line_seg_elems(lv->d, dir) * el;
         cudaError_t me = malloc_evicting(&lv->fac2[dir], nbytes, lv, dir);
@@ -692,10 +695,13 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
             cudaError_t me = malloc_evicting(&lv->fac[dir], nbytes, lv, dir);
             if (me != cudaSuccess) { lv->fac[dir] = nullptr; return fail("cudaMalloc (line factorisation)", me); }
         }
+        // (an evicted factorisation of a chained direction is rebuilt from the kept incoming factors)
         if (lv->cplx)
-            launch_line_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac[dir], g_stream);
+            launch_line_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac[dir], (const cplx*)lv->chain_in[dir],
+                                     nullptr, g_stream);
         else
-            launch_line_factor<double>(model_of<double>(lv), dir, (double*)lv->fac[dir], g_stream);
+            launch_line_factor<double>(model_of<double>(lv), dir, (double*)lv->fac[dir],
+                                       (const double*)lv->chain_in[dir], nullptr, g_stream);
         CK_LAUNCH("line_factor");
     }
     const void* f2 = seg ? lv->fac2[dir] : nullptr;
@@ -706,6 +712,43 @@ int emg3d_b200_gauss_seidel(emg3d_b200_level* lv, void* e, const void* s, int nu
         launch_gs_line<double>(model_of<double>(lv), dir, (const double*)lv->fac[dir], (const double*)f2,
                                (double*)e, (const double*)s, nu, order, g_stream);
     CK_LAUNCH("gauss_seidel_line");
+    return 0;
+}
+
+// Lines of direction ldir that continue on the neighbouring ranks of a multi-GPU slab
+// decomposition: (re)factorise them as pieces of the global lines.  chain_in (device, or NULL
+// on the first rank): [line slot][10] factors of the last block of the lower rank's pieces;
+// chain_out (device, or NULL): receives those of this rank's last blocks.  *n_elems: elements
+// (of the level's dtype) of either buffer.  The incoming factors are kept (copied) so that an
+// evicted factorisation can be rebuilt.
+int emg3d_b200_level_line_chain(emg3d_b200_level* lv, int ldir, const void* chain_in, void* chain_out,
+                                size_t* n_elems) {
+    NEED_MODEL(lv);
+    if (ldir < 1 || ldir > 3) return fail_msg("level_line_chain: ldir must be 1, 2 or 3");
+    const int dir = ldir - 1;
+    const size_t el = lv->cplx ? sizeof(cplx) : sizeof(double);
+    const size_t ne = (size_t)line_chain_elems(lv->d, dir);
+    if (n_elems) *n_elems = ne;
+    if (!chain_in && !chain_out) return 0;                  // size query
+    lv->chained[dir] = 1;
+    if (chain_in) {
+        if (!lv->chain_in[dir]) CK(cudaMalloc(&lv->chain_in[dir], ne * el));
+        CK(cudaMemcpyAsync(lv->chain_in[dir], chain_in, ne * el, cudaMemcpyDeviceToDevice, g_stream));
+    }
+    if (!lv->fac[dir]) {
+        size_t nbytes;
+        emg3d_b200_level_factor_bytes(lv, ldir, &nbytes);
+        if (nbytes == 0) return 0;
+        cudaError_t me = malloc_evicting(&lv->fac[dir], nbytes, lv, dir);
+        if (me != cudaSuccess) { lv->fac[dir] = nullptr; return fail("cudaMalloc (line factorisation)", me); }
+    }
+    if (lv->cplx)
+        launch_line_factor<cplx>(model_of<cplx>(lv), dir, (cplx*)lv->fac[dir], (const cplx*)lv->chain_in[dir],
+                                 (cplx*)chain_out, g_stream);
+    else
+        launch_line_factor<double>(model_of<double>(lv), dir, (double*)lv->fac[dir],
+                                   (const double*)lv->chain_in[dir], (double*)chain_out, g_stream);
+    CK_LAUNCH("line_factor (chained)");
     return 0;
 }
 

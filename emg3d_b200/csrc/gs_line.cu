@@ -54,23 +54,29 @@ namespace emg {
 //              cell, 8 outer transverse edges of the end faces, 4 zeta;
 //              writes g_m (4) and bL (1)
 //   backward : 11 factor entries, g_m (4), bL (1), 4 zeta; writes T_m (4), L (1)
-template <typename T, int D>
+// PH = 0: the whole sweep; 1: forward pass only, 2: backward pass only (g_m and bL live in E
+// between the two) -- the pieces of a z-line cut by multi-GPU z-slabs run the forward pass rank
+// after rank upwards (g of the lower piece's last node arrives in the halo plane, where the
+// pass reads its start value g_0 = T_0) and the backward pass rank after rank downwards.
+template <typename T, int D, int PH = 0>
 __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
     using A = Ax<D>;
     const Model<T>& m = ln.m;
     const int N = ln.N;
 
-    // ---------------- forward ----------------
     double zc[2][2], zn[2][2], gs[4];
+    CellCoef cc, cn;
+    T rl_c = zero_<T>(), bl_c = zero_<T>();
+    if constexpr (PH != 2) {
+    // ---------------- forward ----------------
     ln.load_zeta(0, zc);
     ln.side_g(zc, gs);
-    CellCoef cc, cn;
     cell_coef<T, D>(ln, gs, ldg(m.rh[A::d]), cc);
     T eo_c[4], eo_n[4];                  // outer parallel neighbours of L in the current / next cell
 #pragma unroll
     for (int k = 0; k < 4; ++k) eo_c[k] = a.ed[a.oLn[k]];
-    T rl_c = ldg(a.fac + (int64_t)(N - 1) * FAC_BS);         // 1 / dL_0
-    T bl_c = line_rhs<T, D>(a, 0, cc, eo_c);
+    rl_c = ldg(a.fac + (int64_t)(N - 1) * FAC_BS);           // 1 / dL_0
+    bl_c = line_rhs<T, D>(a, 0, cc, eo_c);
     a.ed[a.oL] = bl_c;
     // g_0 = T_0: the (fixed) transverse edges on the line's start plane: zero on a PEC
     // boundary, halo data of the neighbouring slab on a multi-GPU z-window
@@ -127,9 +133,10 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
 #pragma unroll
             for (int jq = 0; jq < 2; ++jq) zc[jp][jq] = zn[jp][jq];
     }
-
+    }
+    if constexpr (PH != 1) {
     // ---------------- backward ----------------
-    // cc / rl_c / bl_c now belong to the last cell N-1; T_N is fixed data
+    // cc / rl_c / bl_c now belong to the last cell N-1 (PH = 2: reloaded below); T_N is fixed data
     T tn[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) tn[k] = *a.t_ptr(k, N);
@@ -139,7 +146,7 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
         T X[10];
 #pragma unroll
         for (int e = 0; e < 10; ++e) X[e] = ldg(fp + e * FAC_ES);
-        if (i < N - 2) {                                     // (the last cell's data are at hand)
+        if (PH == 2 || i < N - 2) {                          // (the last cell's data are at hand)
             rl_c = ldg(fp + 10 * FAC_ES);
             bl_c = a.ed[a.oL + a.sd * mn];
             ln.load_zeta(mn, zc);
@@ -165,7 +172,7 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
         }
     }
     // L_0 = (bL_0 - f_0 . (T_0 - T_1)) / dL_0
-    if (N > 1) {
+    if (PH == 2 || N > 1) {
         rl_c = ldg(a.fac + (int64_t)(N - 1) * FAC_BS);
         bl_c = a.ed[a.oL];
         ln.load_zeta(0, zc);
@@ -176,35 +183,39 @@ __device__ void sweep_line(const Line<T, D>& ln, const LineAddr<T, D>& a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) fd += cc.f[k] * (*a.t_ptr(k, 0) - tn[k]);
     a.ed[a.oL] = rl_c * (bl_c - fd);
+    }
 }
 
-template <typename T, int D>
+template <typename T, int D, int PH = 0>
 __device__ __forceinline__ void sweep_line_direct(const Model<T>& m, int tp, int tq, const T* fac,
                                                   const LineSlots& ls, const FieldView<T>& E,
                                                   const FieldView<const T>& S) {
     Line<T, D> ln(m, tp, tq);
     LineAddr<T, D> a(E, S, fac + ls.base(ls.slot(tp, tq), ln.N), tp, tq);
-    sweep_line<T, D>(ln, a);
+    sweep_line<T, D, PH>(ln, a);
 }
 
 
 // ---- kernels ---------------------------------------------------------------
+// xin / xout: [slot][10] factors handed across a z-slab cut (see factor_line), or null
 template <typename T, int D>
 __global__ void __launch_bounds__(64)
-line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c) {
+line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c, const T* xin, T* xout) {
     int tp, tq;
     if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
-    factor_line<T, D, 0>(m, tp, tq, fac + ls.base(ls.slot(tp, tq), m.d.n[Ax<D>::d]));
+    const int64_t slot = ls.slot(tp, tq);
+    factor_line<T, D, 0>(m, tp, tq, fac + ls.base(slot, m.d.n[Ax<D>::d]), xin ? xin + slot * 10 : nullptr,
+                         xout ? xout + slot * 10 : nullptr);
 }
 
-template <typename T, int D>
+template <typename T, int D, int PH>
 __global__ void __launch_bounds__(64)
 gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c) {
     int tp, tq;
     if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
-    sweep_line_direct<T, D>(m, tp, tq, fac, ls, E, S);
+    sweep_line_direct<T, D, PH>(m, tp, tq, fac, ls, E, S);
 }
 
 template <typename T, int D>
@@ -263,23 +274,30 @@ int64_t line_factor_elems(const Dims& d, int dir) {
     return (int64_t)FAC_BS * d.n[dir] * (ls.nl / 32);
 }
 
+int64_t line_chain_elems(const Dims& d, int dir) {
+    const int p = dir == 0 ? 1 : 0, q = dir == 2 ? 1 : 2;
+    if (d.n[p] < 2 || d.n[q] < 2) return 0;
+    LineSlots ls(d.n[p] - 1, d.n[q] - 1);
+    return ls.nl * 10;
+}
+
 template <typename T, int D>
-static void factor_dir(const Model<T>& m, T* fac, cudaStream_t st) {
+static void factor_dir(const Model<T>& m, T* fac, const T* xin, T* xout, cudaStream_t st) {
     using A = Ax<D>;
     const int npi = m.d.n[A::p] - 1, nqi = m.d.n[A::q] - 1;
     if (npi < 1 || nqi < 1) return;
     LineSlots ls(npi, nqi);
     for (int c = 0; c < 4; ++c) {
         if (ls.cnt[c] == 0) continue;
-        ++g_launch_count; line_factor_kernel<T, D><<<(ls.cnt[c] + 63) / 64, 64, 0, st>>>(m, fac, ls, c);
+        ++g_launch_count; line_factor_kernel<T, D><<<(ls.cnt[c] + 63) / 64, 64, 0, st>>>(m, fac, ls, c, xin, xout);
     }
 }
 
 template <typename T>
-void launch_line_factor(const Model<T>& m, int dir, T* fac, cudaStream_t st) {
-    if (dir == 0) factor_dir<T, 0>(m, fac, st);
-    else if (dir == 1) factor_dir<T, 1>(m, fac, st);
-    else factor_dir<T, 2>(m, fac, st);
+void launch_line_factor(const Model<T>& m, int dir, T* fac, const T* xin, T* xout, cudaStream_t st) {
+    if (dir == 0) factor_dir<T, 0>(m, fac, xin, xout, st);
+    else if (dir == 1) factor_dir<T, 1>(m, fac, xin, xout, st);
+    else factor_dir<T, 2>(m, fac, xin, xout, st);
 }
 
 template <typename T, int D>
@@ -289,7 +307,7 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
     const int npi = m.d.n[A::p] - 1, nqi = m.d.n[A::q] - 1;
     if (npi < 1 || nqi < 1) return;
     LineSlots ls(npi, nqi);
-    if (!fac2 && (int64_t)npi * nqi <= 1024) {
+    if (!fac2 && !((order >> 18) & 0x1f) && (int64_t)npi * nqi <= 1024) {
         int threads = 32;
         const int want = order == ORDER_LEX ? nqi : (npi * nqi + 3) / 4;
         while (threads < 256 && threads < want) threads <<= 1;
@@ -300,6 +318,9 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
     // bits 16-17: z-half of a multicolour sweep (see gs_point.cu); x- and y-lines are coloured
     // by (p, z) parity, class index cp + 2 cz
     const int zsel = D == 2 ? 0 : (order >> 16) & 3;
+    // bits 18-19: 1 = forward pass only, 2 = backward pass only; bits 20-22: 1 + the one colour
+    // class to run (0: all) -- the pieces of z-lines cut by z-slabs (see sweep_line)
+    const int phase = (order >> 18) & 3, csel = (order >> 20) & 7;
     order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
@@ -323,12 +344,17 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
                 // that launch is skipped -- 7 instead of 8 colour launches for nu = 2.
                 if (sw > 0 && cc == 0) continue;
                 if (zsel && (cg >> 1) != zsel - 1) continue;
+                if (csel && cg != csel - 1) continue;
                 if (fac2) {          // segment-parallel kernel (gs_line_seg.cu), same colour sequence
                     launch_gs_line_seg_color<T>(m, D, fac2, e, s, c, st);
                     continue;
                 }
                 const int threads = 64;
-                ++g_launch_count; gs_line_color_kernel<T, D><<<(ls.cnt[c] + threads - 1) / threads, threads, 0, st>>>(m, fac, ls, e, s, c);
+                const dim3 grid((ls.cnt[c] + threads - 1) / threads);
+                ++g_launch_count;
+                if (phase == 1) gs_line_color_kernel<T, D, 1><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
+                else if (phase == 2) gs_line_color_kernel<T, D, 2><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
+                else gs_line_color_kernel<T, D, 0><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
             }
         }
     }
@@ -342,8 +368,8 @@ void launch_gs_line(const Model<T>& m, int dir, const T* fac, const T* fac2, T* 
     else gs_dir<T, 2>(m, fac, fac2, e, s, nu, order, st);
 }
 
-template void launch_line_factor<double>(const Model<double>&, int, double*, cudaStream_t);
-template void launch_line_factor<cplx>(const Model<cplx>&, int, cplx*, cudaStream_t);
+template void launch_line_factor<double>(const Model<double>&, int, double*, const double*, double*, cudaStream_t);
+template void launch_line_factor<cplx>(const Model<cplx>&, int, cplx*, const cplx*, cplx*, cudaStream_t);
 template void launch_gs_line<double>(const Model<double>&, int, const double*, const double*, double*,
                                      const double*, int, int, cudaStream_t);
 template void launch_gs_line<cplx>(const Model<cplx>&, int, const cplx*, const cplx*, cplx*, const cplx*, int,

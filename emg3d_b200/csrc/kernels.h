@@ -36,7 +36,8 @@ void launch_edge_diag(const Model<T>& m, T* diag, cudaStream_t st);
 // line smoothers: factor once per (level, direction), then sweep
 int64_t line_factor_elems(const Dims& d, int dir);     // number of T elements
 template <typename T>
-void launch_line_factor(const Model<T>& m, int dir, T* fac, cudaStream_t st);
+void launch_line_factor(const Model<T>& m, int dir, T* fac, const T* xin, T* xout, cudaStream_t st);
+int64_t line_chain_elems(const Dims& d, int dir);
 // `fac`: factors in the one-thread-per-line layout (lexicographic order, small grids, and the
 // multicolour order wherever `fac2` is null); `fac2`: cached data of the segment-parallel
 // kernels (gs_line_seg.cu; multicolour order on long lines) or null

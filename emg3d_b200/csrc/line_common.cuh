@@ -263,8 +263,13 @@ __device__ __forceinline__ T line_rhs(const LineAddr<T, D>& a, int i, const Cell
 // line, entries FAC_ES apart, blocks FAC_BS apart, 1/dL_0 in block N-1.
 // QP > 0: segment layout of gs_line_seg.cu, `fbase` = the line's chunk: block i = 8 q + j
 // at ((j * FAC_NE + e) * QP + q), 1/dL_0 in the header behind the 8 * FAC_NE * QP entries.
+// Lines cut by multi-GPU z-slabs (z-lines only): `xin` = the factors of the block BELOW the
+// line's first one (the last block of the lower rank's piece, 10 entries) continue the global
+// recurrence S_m = D_m - E_m S_{m-1}^{-1} E_m across the cut; `xout` receives the factors of
+// the last block.
 template <typename T, int D, int QP>
-__device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ fbase) {
+__device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ fbase,
+                            const T* __restrict__ xin = nullptr, T* __restrict__ xout = nullptr) {
     using A = Ax<D>;
     Line<T, D> ln(m, tp, tq);
     const int N = ln.N;
@@ -285,6 +290,10 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
         etq_c[j] = ldg(m.eta[A::q] + ln.cbase[0][j]) + ldg(m.eta[A::q] + ln.cbase[1][j]);
     }
     T X[10];                         // factors of S_{m-1}
+    if (xin) {
+#pragma unroll
+        for (int e = 0; e < 10; ++e) X[e] = xin[e];
+    }
     for (int i = 0; i < N - 1; ++i) {                        // node m = i + 1
         ln.load_zeta(i + 1, zn);
         double gn[4];
@@ -326,7 +335,7 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
                 S[tri(r, c)] -= (cc.f[r] * cc.f[c]) * rl_c + (cn.f[r] * cn.f[c]) * rl_n;
         // S_m = D_m - E_m S_{m-1}^{-1} E_m,  E_m = diag(d_c) + rl_c f_c f_c^T: column by column,
         // Z e_c = S_{m-1}^{-1} (E_m e_c) by substitution with the previous block's factors
-        if (i > 0) {
+        if (i > 0 || xin) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 T ecol[4], z[4];
@@ -363,6 +372,10 @@ __device__ void factor_line(const Model<T>& m, int tp, int tq, T* __restrict__ f
         for (int jp = 0; jp < 2; ++jp)
 #pragma unroll
             for (int jq = 0; jq < 2; ++jq) zc[jp][jq] = zn[jp][jq];
+    }
+    if (xout && (N > 1 || xin)) {
+#pragma unroll
+        for (int e = 0; e < 10; ++e) xout[e] = X[e];
     }
 }
 

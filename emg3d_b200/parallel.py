@@ -735,8 +735,57 @@ class DistributedMultigrid:
                         dl.win.ptr, e.ptr, s.ptr, 1, ldir, base | (half << 16)))
                     self.exchange(dl, e, shared_from_lower=(half == low_half))
 
+    def _zline_chain(self, dl):
+        """Factorise the z-lines of a distributed level as pieces of the GLOBAL lines (once): the
+        block recurrence S_m = D_m - E_m S_{m-1}^{-1} E_m runs through the slab cuts, every rank
+        continues from the factors of the lower rank's last blocks (10 numbers per line)."""
+        if getattr(dl, 'zchain', False):
+            return
+        import ctypes
+        lib = self._lib.load()
+        n = ctypes.c_size_t(0)
+        self._lib.check(lib.emg3d_b200_level_line_chain(dl.win.ptr, 3, None, None, ctypes.byref(n)))
+        n, isz = int(n.value), self.dtype.itemsize
+        first, last = self.rank == 0, self.rank == self.nranks - 1
+        xin = None if first else self._lib.DeviceArray(n, self.dtype)
+        xout = None if last else self._lib.DeviceArray(n, self.dtype)
+        if xin is not None:
+            self.comm.sendrecv(xin.ptr, isz, [(0, self.rank - 1, 0, n)])
+        if xin is not None or xout is not None:
+            self._lib.check(lib.emg3d_b200_level_line_chain(
+                dl.win.ptr, 3, None if xin is None else xin.ptr, None if xout is None else xout.ptr, None))
+        if xout is not None:
+            self.comm.sendrecv(xout.ptr, isz, [(1, self.rank + 1, 0, n)])
+        self._lib.sync()                                 # (xin / xout are released on return)
+        dl.zchain = True
+
     def zline_smoothing(self, dl, s, e, nu):
-        raise NotImplementedError("z-line relaxation across z-slabs is not distributed")
+        """z-line relaxation (core.py:1071-1348) with the lines cut by the slabs: EXACT, every global
+        line is solved as on one GPU.  Per colour class the forward block substitution runs rank
+        after rank upwards -- the intermediate g of a piece's last node reaches the next rank in
+        its halo plane, where the kernel reads its start value -- and the backward substitution
+        rank after rank downwards (the true T of the upper piece's first node arrives in the top
+        halo plane).  The shared fz layer of an interface is computed by the lower rank
+        (``shared_from_lower`` exchanges only: the lower rank's copy also parks its intermediate
+        there).  Same colour sequence as the single-GPU kernel (gs_line.cu: gs_dir).  The ranks
+        work one after the other within a colour: z-lines cost ``nranks`` times their share."""
+        if self.order != 1:
+            raise NotImplementedError("z-line relaxation across z-slabs: multicolour order only")
+        lib = self._lib.load()
+        self._zline_chain(dl)
+        n = self.nranks
+        for sweep in range(int(nu)):
+            back = sweep % 2 == 0
+            for cc in range(4):
+                if sweep > 0 and cc == 0:
+                    continue                             # idempotent repeat (gs_line.cu)
+                cg = 3 - cc if back else cc
+                for phase, ranks in ((1, range(n)), (2, range(n - 1, -1, -1))):
+                    order = 1 | (phase << 18) | ((cg + 1) << 20)
+                    for t in ranks:
+                        if t == self.rank:
+                            self._lib.check(lib.emg3d_b200_gauss_seidel(dl.win.ptr, e.ptr, s.ptr, 1, 3, order))
+                        self.exchange(dl, e, shared_from_lower=True)
 
     # ---- the cycle ---------------------------------------------------------------------
     def multigrid(self, var, level=0, new_cycmax=0, s=None, e=None):

@@ -956,6 +956,9 @@ def _krylov(lv, s, e, var, ops=None):
     var.cprint(pre + var.exit_message, 2)
 
 
+_KRYLOV_DEBUG = bool(int(__import__('os').environ.get('EMG3D_B200_KRYLOV_DEBUG', '0')))
+
+
 def _bicgstab(ops, b, x, var, callback):
     """Preconditioned BiCGSTAB on the device(s).
 
@@ -1015,6 +1018,13 @@ def _bicgstab(ops, b, x, var, callback):
         ops.axpby(omega, shat, 1.0, x)
         ops.axpby(-omega, t, 1.0, r)
         rho_prev = rho
+        if _KRYLOV_DEBUG:                     # recurrence residual against the true one
+            tr = ops.new()
+            ops.matvec(x, tr)
+            ops.axpby(1.0, b, -1.0, tr)
+            ops.axpby(-1.0, r, 1.0, tr)
+            print(f"   bicgstab {iteration}: |r| {ops.norm(r):.3e} |b - A x - r| {ops.norm(tr):.3e} "
+                  f"rho {rho:.3e} alpha {alpha:.3e} omega {omega:.3e}", flush=True)
         callback(x)
     return var.ssl_maxit
 

@@ -98,6 +98,17 @@ int emg3d_b200_level_set_owned(emg3d_b200_level* lv, int plane0, int plane1);
  * planes of parity cz ^ flip), so that the "z-half" selection of emg3d_b200_gauss_seidel
  * (bits 16-17 of `order`) names the same global planes on every rank.                      */
 int emg3d_b200_level_set_zflip(emg3d_b200_level* lv, int flip);
+/* Multi-GPU z-slabs, z-line relaxation (emg3d/core.py:1071-1348 `gauss_seidel_z`): the z-lines
+ * are cut by the slabs, every rank holds one piece of each line.  The block recurrence of the
+ * line factorisation runs through the cuts: the first rank factorises its pieces (chain_in = NULL)
+ * and hands the factors of their last blocks (chain_out, [line slot][10] elements of the level's
+ * dtype, *n_elems in total) to the next rank, which passes them as chain_in, and so on.  Both
+ * NULL: size query only.  Sweeps then run piecewise through emg3d_b200_gauss_seidel with the
+ * phase / colour bits of `order` (bits 18-19: 1 = forward pass only, 2 = backward pass only;
+ * bits 20-22: 1 + colour class): forward passes rank after rank upwards, backward passes
+ * downwards, the interface planes exchanged in between (emg3d_b200/parallel.py). */
+int emg3d_b200_level_line_chain(emg3d_b200_level* lv, int ldir, const void* chain_in, void* chain_out,
+                                size_t* n_elems);
 /* Multicolour point schedule used for this level's shape: 0 = one block (<= 512 interior
  * nodes), 1 = one launch per node colour, 2 = tile-fused (tiles coloured by LOCAL tile index). */
 int emg3d_b200_point_schedule_kind(const emg3d_b200_level* lv, int* kind);
