@@ -51,6 +51,31 @@ def vcycle_work(shape, nu_pre=2, nu_post=2, nu_coarse=1):
     return work
 
 
+def workload_config(size, world, order):
+    """`config` of the JSON line: the workload, a function of the command line only -- both arms
+    (`--impl b200` and `--impl reference`) print the same dict.  Run-time facts (number of
+    distributed levels, halo transport, the CPU sample) go to other keys."""
+    from emg3d_b200 import recipes
+    if world == 1:
+        shape = (size, size, size)
+        what = (f"plain V(2,2) multigrid cycle (nu_coarse=1) on the {size}^3 marine CSEM model of "
+                "BASELINE.json configs[2], complex128, VTI")
+        par = "single GPU"
+    else:
+        shape = tuple(recipes.bench_shape(world, size))
+        what = ("plain V(2,2) multigrid cycle (nu_coarse=1) on the marine CSEM model of BASELINE.json "
+                f"configs[2] grown to {shape[0]}x{shape[1]}x{shape[2]} cells ({size}^3 per GPU), "
+                "complex128, VTI")
+        par = (f"one solve on {world} GPUs: z-slabs of {shape[2] // world} cell layers, the levels with "
+               "more than ~1 M cells distributed, coarser levels replicated; halo exchange of E after "
+               "every half sweep (a true Gauss-Seidel sweep across slabs), residual and prolongation")
+    work = vcycle_work(shape)
+    return {"workload": f"{what}; {work} cell-sweeps per step", "order": order,
+            "cells": int(np.prod(shape)), "cell_sweeps_per_step": int(work),
+            "l2": "working set 3.2 GB per GPU and step, far larger than the 126 MB L2",
+            "parallelism": par}
+
+
 def peaks():
     fn = os.path.join(HERE, 'MEASURED_PEAKS.json')
     if os.path.exists(fn):
@@ -162,50 +187,89 @@ def _cpu_cycle(n):
     return info['cell_sweeps'], time.perf_counter() - t0
 
 
-def cpu_baseline(n=128):
+def cpu_baseline(n=128, repeats=3):
+    """One thread of the C oracle port on the n^3 sibling: median of `repeats` cycles."""
     import oracle
     oracle.build()
+    oracle.lib()
     _cpu_cycle(16)                                   # warm-up (library load)
-    work, sec = _cpu_cycle(n)
+    runs = [_cpu_cycle(n) for _ in range(repeats)]
+    work = runs[0][0]
+    secs = sorted(r[1] for r in runs)
+    sec = secs[len(secs) // 2]
     return {"value": work / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "spread": [work / secs[-1], work / secs[0]],
             "sample": f"one plain V(2,2)-cycle of the C oracle on the {n}^3 sibling of the "
-                      f"workload ({work} cell-sweeps, {sec:.1f} s, 1 thread)"}
+                      f"workload ({work} cell-sweeps, median {sec:.1f} s of {repeats} runs, 1 thread)"}
+
+
+def _pinned_cycle(job):
+    """Pool worker: pin to one core (no migration between the repeats), run one cycle."""
+    core, n = job
+    try:
+        os.sched_setaffinity(0, {core})
+    except (AttributeError, OSError):
+        pass
+    return _cpu_cycle(n)
 
 
 def run_reference(args):
-    """--impl reference: CPU implementation on all host cores, bounded sample."""
+    """--impl reference: the CPU implementation of the path on all host cores.
+
+    The reference's own parallel mode is a process pool of independent solves
+    (emg3d/_multiprocessing.py:33-65), one per core; the kernels are single-threaded.  A step
+    = one plain V(2,2)-cycle per core, all cores at once, on a bounded sibling of the workload
+    (128^3 when the run has at most 10 steps + warm-ups, else 96^3: about 4-12 s per step);
+    throughput = cell-sweeps of all cores / time of the slowest.  Workers are forked AFTER the
+    oracle library is loaded, pinned to one core each and warmed on the same size."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import multiprocessing as mp
     import oracle
     oracle.build()
-    cores = os.cpu_count() or 1
-    n = 64
+    oracle.lib()                                      # loaded before the fork: workers inherit it
+    try:
+        cores_avail = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores_avail = list(range(os.cpu_count() or 1))
+    cores = len(cores_avail)
+    n = 128 if args.steps + args.warmup <= 10 else 96
+    if args.size < 128:
+        n = min(n, args.size)
+    one = cpu_baseline(n, repeats=1)                  # one thread, same size, machine otherwise idle
+    jobs = [(c, n) for c in cores_avail]
+    per_step = []
     with mp.get_context('fork').Pool(cores) as pool:
         for _ in range(args.warmup):
-            pool.map(_cpu_cycle, [32] * cores)
+            pool.map(_pinned_cycle, jobs, chunksize=1)
         work, sec = 0, 0.0
         for _ in range(args.steps):
-            res = pool.map(_cpu_cycle, [n] * cores)
-            work += sum(r[0] for r in res)
-            sec += max(r[1] for r in res)     # the cycles only, input building excluded
+            t0 = time.perf_counter()
+            res = pool.map(_pinned_cycle, jobs, chunksize=1)
+            wall = time.perf_counter() - t0
+            w = sum(r[0] for r in res)
+            work += w
+            sec += wall                              # wall clock of the step (dispatch included)
+            per_step.append(w / wall)
     value = work / sec
+    per_step.sort()
     sample = (f"{cores} concurrent independent plain V(2,2)-cycles (one per host core, the "
               f"reference's process-pool mode) of the C oracle port on the {n}^3 sibling of "
-              f"the workload, {args.steps} steps")
+              f"the workload per step, {args.steps} steps after {args.warmup} warm-up steps of the same "
+              f"size; wall clock per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "plain V(2,2) multigrid cycle (nu_coarse=1) on the 256^3 marine CSEM "
-                               "model of BASELINE.json configs[2], complex128, VTI",
-                   "order": "lex (the reference's order)", "parallelism": f"{cores} host cores",
-                   "sample": f"the same cycle on the {n}^3 sibling of the workload (bounded CPU "
-                             "sample; throughput in cell-sweeps/s is size-independent to ~20 %)"},
+        "config": workload_config(args.size, args.gpus, args.order),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "order": "lex (the reference's order)",
+                         "per_core": value / cores,
+                         "one_thread_alone": one["value"],
+                         "median_step": per_step[len(per_step) // 2],
+                         "spread": [per_step[0], per_step[-1]]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -450,14 +514,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"plain V(2,2) multigrid cycle (nu_coarse=1) on the {n}^3 marine "
-                                   "CSEM model of BASELINE.json configs[2], complex128, VTI; "
-                                   f"{work} cell-sweeps per step",
-                       "order": args.order, "cells": int(cells), "cell_sweeps_per_step": int(work),
-                       "l2": "working set 3.2 GB per step, far larger than the 126 MB L2",
-                       "parallelism": ("single GPU" if world == 1 else
-                                       f"{world} independent replicas (one solve per GPU, the "
-                                       "reference's own parallel mode)")},
+            "config": workload_config(n, 1, args.order),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "device": _lib.device_name(),
@@ -657,21 +714,12 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"plain V(2,2) multigrid cycle (nu_coarse=1) on the marine CSEM model of "
-                                   f"BASELINE.json configs[2] grown to {shape[0]}x{shape[1]}x{shape[2]} cells "
-                                   f"({args.size}^3 per GPU), complex128, VTI; {work} cell-sweeps per step",
-                       "order": args.order, "cells": int(np.prod(shape)),
-                       "cell_sweeps_per_step": int(work),
-                       "l2": "working set 3.2 GB per GPU and step, far larger than the 126 MB L2",
-                       "parallelism": f"one solve on {world} GPUs: z-slabs of {shape[2] // world} cell layers, "
-                                      f"{n_dist} distributed levels, coarser levels replicated; halo "
-                                      "exchange of E after every half sweep (the colour classes of even "
-                                      "/ odd z-parity: a true Gauss-Seidel sweep across slabs), residual "
-                                      "and prolongation by "
-                                      + ("one peer-memory kernel per exchange (CUDA IPC mapping of the "
-                                         "neighbours' slabs, remote loads over NVLink, flag handshake)"
-                                         if comm.p2p else "ncclSend/ncclRecv over NVLink")
-                                      + "; norms all-reduced (NCCL)"},
+            "config": workload_config(args.size, world, args.order),
+            "run": {"distributed_levels": int(n_dist),
+                    "halo_transport": ("one peer-memory kernel per exchange (CUDA IPC mapping of the "
+                                       "neighbours' slabs, remote loads over NVLink, flag handshake)"
+                                       if comm.p2p else "ncclSend/ncclRecv over NVLink"),
+                    "norms": "all-reduced (NCCL)"},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
             "halo_exchange": {"transport": "peer-memory kernel" if comm.p2p else "nccl", "ms": halo_ms,
                               "bytes_sent_per_rank": int(halo_bytes),

@@ -267,10 +267,23 @@ class DeviceArray:
         self.free()
 
 
+def _host_free(ptr):
+    try:
+        load().emg3d_b200_host_free(ptr)
+    except Exception:
+        pass
+
+
 class PinnedArray:
-    """Page-locked host buffer exposed as a NumPy array."""
+    """Page-locked host buffer exposed as a NumPy array.
+
+    The memory belongs to the array: it is released when the LAST NumPy view of it is gone (a
+    finalizer on the ctypes object every view keeps alive through its base chain), so a Field
+    returned by ``solve(..., workspace=Workspace(pinned_result=True))`` stays valid after the
+    workspace dropped or replaced the buffer."""
 
     def __init__(self, size, dtype):
+        import weakref
         self.dtype = np.dtype(dtype)
         self.size = int(size)
         self.nbytes = self.size * self.dtype.itemsize
@@ -278,19 +291,13 @@ class PinnedArray:
         check(init().emg3d_b200_host_alloc(byref(p), self.nbytes))
         self.ptr = p.value
         buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        weakref.finalize(buf, _host_free, self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=self.size)
 
     def free(self):
-        if getattr(self, 'ptr', None):
-            self.array = None
-            try:
-                load().emg3d_b200_host_free(self.ptr)
-            except Exception:
-                pass
-            self.ptr = None
-
-    def __del__(self):
-        self.free()
+        """Drop this object's reference; views handed out keep the memory alive."""
+        self.array = None
+        self.ptr = None
 
 
 class Event:

@@ -2,35 +2,41 @@
 
 New functionality relative to the reference (which only runs independent solves
 in a process pool, emg3d/_multiprocessing.py:33-65): ONE solve is spread over N
-GPUs, one process per GPU.
+GPUs, one process per GPU, through ``emg3d_b200.solve(..., comm=)`` (inside a multi-process
+launch) or ``solve(..., n_gpus=)`` (ranks spawned) -- same arguments, log, info dict and return
+conventions as on one GPU.
 
 * **Partition.**  z is the slowest axis of every array, so a z-slab of a field or
   coefficient array is one contiguous range.  Node planes are owned in contiguous
-  blocks whose boundaries are multiples of ``2**n_dist``, so that ownership
-  coarsens consistently over the ``n_dist`` distributed levels.  Every rank works
-  on a *local grid*: its owned planes, one halo plane above and, below, as many
-  halo planes as are needed to keep the local grid aligned with its own
-  coarsening (``2**(n_dist - level)``); the unchanged single-GPU kernels then run
-  on local grids, local boundaries playing the role of the PEC boundary.
-* **Halo exchange between smoothing sweeps** (the variant ``north_star`` names):
-  after every Gauss-Seidel sweep, residual evaluation and prolongation the owner's
-  planes next to an interface are sent to the neighbour with ncclSend/ncclRecv
-  pairs in one NCCL group (``emg3d_b200_comm_sendrecv``), GPU to GPU over NVLink.
-  Nodes at an interface therefore see neighbour values that are at most one sweep
-  old (block-Jacobi across slabs, Gauss-Seidel inside).
-* **Norms** are sums over owned edges, all-reduced with NCCL.
-* **Coarse levels are replicated**: at level ``n_dist`` the restricted residual is
-  all-gathered (NCCL point-to-point into the global layout) and every rank runs
-  the remaining coarse sub-cycle redundantly with the single-GPU driver; each rank
-  then keeps its slab of the correction -- no scatter is needed.
+  blocks whose boundaries are multiples of ``2**zmax`` (``zmax``: the largest number of
+  z-coarsenings of any distributed hierarchy), so that ownership coarsens consistently.  Every
+  rank works on a *local grid*: its owned planes, one halo plane above and, below, as many
+  halo planes as keep the local grid aligned with its own coarsening; the unchanged
+  single-GPU kernels run on z-windows of the local grids, window boundaries playing the role
+  of the PEC boundary.
+* **Hierarchies.**  One chain of distributed levels per semicoarsening pattern of the cycle
+  (:func:`hierarchy_plan`: patterns 1 / 2 keep halving z, pattern 3 leaves z alone), sharing
+  the finest level; a level is distributed while it has more than about a million cells.
+* **Smoothing is a true Gauss-Seidel sweep across slabs** (``exact=True``, default): every
+  multicolour sweep runs as its two z-halves with a halo exchange after each
+  (:meth:`DistributedMultigrid.smoothing`); ``exact=False`` exchanges once per sweep (the
+  relaxed variant ``north_star`` words: block-Jacobi across slabs).  Point smoother, x- and
+  y-lines work on the slab; **z-lines are cut by the slabs** and solved exactly as pieces of
+  the global lines (:meth:`DistributedMultigrid.zline_smoothing`).
+* **Halo exchange** = one peer-memory kernel per exchange (CUDA IPC mapping of the
+  neighbours' arrays, remote loads over NVLink, flag handshake; csrc/comm.cu), NCCL
+  send/recv groups as the fallback.
+* **Norms and dot products** are sums over owned edges, all-reduced with NCCL; BiCGSTAB and
+  CGS run around the distributed cycle through the backend-neutral drivers of solver.py.
+* **Coarse levels are replicated**: below the distributed levels the restricted residual is
+  all-gathered and every rank runs the remaining coarse sub-cycle redundantly with the
+  single-GPU driver; each rank keeps its slab of the correction.
 
-Supported in this mode: standard coarsening (``semicoarsening=False``), point
-smoother or x/y line relaxation (``linerelaxation`` in {0, 1, 2, 6}), V/W/F cycles,
-no Krylov wrapper.  z-lines cross slabs and are not distributed yet.
+Multicolour order only (``order='color'``); GCROT(m,k) is not distributed.
 
 The index arithmetic (:class:`SlabPartition`, :func:`exchange_plan`,
-:func:`gather_plan`) is pure Python and is tested on CPU with two ``gloo`` ranks;
-the transport is pluggable (:class:`NcclComm` on device pointers,
+:func:`gather_plan`, :func:`hierarchy_plan`) is pure Python and is tested on CPU with two
+``gloo`` ranks; the transport is pluggable (:class:`NcclComm` on device pointers,
 ``tests/test_parallel_cpu.py`` plugs in a gloo transport on host arrays).
 """
 import numpy as np

@@ -117,6 +117,17 @@ def config(name, n=None):
     raise ValueError(f"unknown configuration {name!r}")
 
 
+def bench_shape(n_gpus, n=256):
+    """Cells of the weak-scaling workload of bench.py (see :func:`bench_grid`)."""
+    shape = [n, n, n]
+    k, a = n_gpus, 0
+    while k > 1:
+        shape[a % 3] *= 2
+        k //= 2
+        a += 1
+    return shape
+
+
 def bench_grid(n_gpus, n=256):
     """Weak-scaling workload of bench.py: the marine model on n^3 cells per GPU.
 
@@ -124,12 +135,7 @@ def bench_grid(n_gpus, n=256):
     count along x, then y, then z: 2: 2n x n x n, 4: 2n x 2n x n (configs[3] shape),
     8: (2n)^3 (configs[4] shape).  Decomposed into z-slabs.
     """
-    shape = [n, n, n]
-    k, a = n_gpus, 0
-    while k > 1:
-        shape[a % 3] *= 2
-        k //= 2
-        a += 1
+    shape = bench_shape(n_gpus, n)
     alpha = [{512: 1.02, 256: 1.03, 128: 1.04, 64: 1.06, 32: 1.10}.get(m, 1.02 if m > 512 else 1.10)
              for m in shape]
     h, origin = grid_arrays(*shape, *alpha)
