@@ -6,12 +6,14 @@ Python host code calling hand-written sm_100a CUDA kernels through a C ABI
 """
 from emg3d_b200._lib import Emg3dB200Error
 from emg3d_b200.meshes import BaseMesh, TensorMesh
-from emg3d_b200.fields import Field, get_source_field, get_magnetic_field
+from emg3d_b200.fields import (Field, SourceField, DeviceField, get_source_field, get_magnetic_field,
+                               get_receiver)
 from emg3d_b200.models import Model, VolumeModel
-from emg3d_b200 import batch, core, solver
+from emg3d_b200 import batch, core, maps, solver
 from emg3d_b200.batch import solve_many
 from emg3d_b200.solver import solve, solve_source, Workspace, __version__
 
 __all__ = ['solve', 'solve_source', 'Model', 'VolumeModel', 'Field',
-           'get_source_field', 'get_magnetic_field', 'solve_many', 'batch', 'TensorMesh', 'BaseMesh', 'core', 'solver', 'Workspace',
+           'get_source_field', 'get_magnetic_field', 'get_receiver', 'SourceField', 'DeviceField', 'maps',
+           'solve_many', 'batch', 'TensorMesh', 'BaseMesh', 'core', 'solver', 'Workspace',
            'Emg3dB200Error']

@@ -100,6 +100,19 @@ _SIGNATURES = {
     'emg3d_b200_axpby': (c_int, [c_int, c_longlong, c_double, c_double, c_void_p,
                                  c_double, c_double, c_void_p]),
     'emg3d_b200_host_amat_x': (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 13),
+    'emg3d_b200_fill_scatter': (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
+    'emg3d_b200_volume_average': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    'emg3d_b200_edges_to_vol_averages': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p]),
+    'emg3d_b200_gradient_field': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_double,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    'emg3d_b200_spline_filter3': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
+    'emg3d_b200_pad_edge3': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'emg3d_b200_interp_points': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                         c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                         ctypes.c_longlong, c_int, c_int, c_int, c_double, c_double,
+                                         c_int, c_void_p]),
     'emg3d_b200_host_gauss_seidel': (c_int, [c_int] * 6 + [c_void_p] * 13 + [c_int]),
     'emg3d_b200_host_solve': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'emg3d_b200_comm_unique_id': (c_int, [c_void_p]),
@@ -231,6 +244,14 @@ class DeviceArray:
         check(init().emg3d_b200_h2d_sparse(self.ptr, _hptr(arr), self.size, self.dtype.itemsize,
                                            byref(used)))
         return bool(used.value)
+
+    def fill_scatter(self, fill, idx, val):
+        """self[:] = fill; self[idx] = val (a sparse source field: emg3d_b200_fill_scatter)."""
+        fill = np.array([fill], dtype=self.dtype)
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        val = np.ascontiguousarray(val, dtype=self.dtype)
+        check(init().emg3d_b200_fill_scatter(self.ptr, self.size, self.dtype.itemsize, _hptr(fill),
+                                             _hptr(idx), _hptr(val), idx.size))
 
     def upload_ptr(self, hptr, nbytes=None):
         check(init().emg3d_b200_h2d(self.ptr, hptr, self.nbytes if nbytes is None else nbytes))

@@ -376,6 +376,48 @@ int emg3d_b200_h2d_sparse(void* dst, const void* src, size_t n, int elsize, int*
     return 0;
 }
 
+// A source field given as what it is: a constant background and `count` (index, value) pairs
+// (emg3d_b200/fields.py: SourceField) -- no dense host array is ever built or scanned.
+int emg3d_b200_fill_scatter(void* dst, size_t n, int elsize, const void* fill_value, const long long* idx,
+                            const void* val, size_t count) {
+    NEED_INIT();
+    if (elsize != 8 && elsize != 16) return fail_msg("fill_scatter: elsize must be 8 or 16");
+    if (n == 0) return 0;
+    for (size_t k = 0; k < count; ++k)
+        if (idx[k] < 0 || (size_t)idx[k] >= n) return fail_msg("fill_scatter: index out of range");
+    const int bs = 256;
+    ++emg::g_launch_count;
+    if (elsize == 16) {
+        double2 v;
+        memcpy(&v, fill_value, 16);
+        fill_kernel<double2><<<148 * 8, bs, 0, g_stream>>>((double2*)dst, v, (long long)n);
+    } else {
+        double v;
+        memcpy(&v, fill_value, 8);
+        fill_kernel<double><<<148 * 8, bs, 0, g_stream>>>((double*)dst, v, (long long)n);
+    }
+    CK_LAUNCH("fill");
+    if (count) {
+        void* tmp = nullptr;
+        CK(cudaMalloc(&tmp, count * (8 + (size_t)elsize)));
+        char* dval = (char*)tmp + 8 * count;
+        CK(cudaMemcpyAsync(tmp, idx, 8 * count, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(dval, val, count * (size_t)elsize, cudaMemcpyHostToDevice, g_stream));
+        const unsigned gs = (unsigned)((count + bs - 1) / bs);
+        ++emg::g_launch_count;
+        if (elsize == 16)
+            scatter_kernel<double2><<<gs, bs, 0, g_stream>>>((double2*)dst, (const long long*)tmp, (const double2*)dval,
+                                                             (long long)count);
+        else
+            scatter_kernel<double><<<gs, bs, 0, g_stream>>>((double*)dst, (const long long*)tmp, (const double*)dval,
+                                                            (long long)count);
+        CK_LAUNCH("scatter");
+        CK(cudaStreamSynchronize(g_stream));
+        cudaFree(tmp);
+    }
+    return 0;
+}
+
 int emg3d_b200_host_alloc(void** hptr, size_t nbytes) {
     CK(cudaMallocHost(hptr, nbytes ? nbytes : 16));
     return 0;
@@ -941,6 +983,84 @@ int emg3d_b200_magnetic_field(emg3d_b200_level* lv, const void* e, void* hfield,
         launch_edge_curl<double, double>(lv->d, (const double*)e, (double*)hfield, lv->h[0], lv->h[1],
                                          lv->h[2], lv->zeta, scale_re, g_stream);
     CK_LAUNCH("edge_curl");
+    return 0;
+}
+
+// ---- interpolation next to the solve (interp.cu; emg3d/maps.py, emg3d/fields.py:522-615) -------
+int emg3d_b200_volume_average(const double* values, int nx, int ny, int nz, double* out, int mx, int my,
+                              int mz, const double* const* w, const int* const* iin, const int* const* start,
+                              const double* const* hnew, int log_scale, int add) {
+    NEED_INIT();
+    if (nx < 1 || ny < 1 || nz < 1 || mx < 1 || my < 1 || mz < 1) return fail_msg("volume_average: empty grid");
+    launch_volume_average(values, nx, ny, out, mx, my, mz, w, iin, start, hnew, log_scale, add, g_stream);
+    CK_LAUNCH("volume_average");
+    return 0;
+}
+
+int emg3d_b200_edges_to_vol_averages(int is_cplx, int nx, int ny, int nz, const void* field, const double* hx,
+                                     const double* hy, const double* hz, void* out) {
+    NEED_INIT();
+    if (nx < 1 || ny < 1 || nz < 1) return fail_msg("edges_to_vol_averages: need at least 1 cell per axis");
+    Dims d = {};
+    d.n[0] = nx; d.n[1] = ny; d.n[2] = nz;
+    if (is_cplx) launch_edges_to_vol<cplx>(d, (const cplx*)field, hx, hy, hz, (cplx*)out, g_stream);
+    else launch_edges_to_vol<double>(d, (const double*)field, hx, hy, hz, (double*)out, g_stream);
+    CK_LAUNCH("edges_to_vol_averages");
+    return 0;
+}
+
+int emg3d_b200_gradient_field(int nx, int ny, int nz, const void* efield, const void* bfield, double smu0_re,
+                              double smu0_im, const double* hx, const double* hy, const double* hz, double* out) {
+    NEED_INIT();
+    if (nx < 1 || ny < 1 || nz < 1) return fail_msg("gradient_field: need at least 1 cell per axis");
+    Dims d = {};
+    d.n[0] = nx; d.n[1] = ny; d.n[2] = nz;
+    launch_gradient_field(d, (const cplx*)efield, (const cplx*)bfield, make_c(smu0_re, smu0_im), hx, hy, hz, out,
+                          g_stream);
+    CK_LAUNCH("gradient_field");
+    return 0;
+}
+
+int emg3d_b200_spline_filter3(int is_cplx, int n0, int n1, int n2, void* data, int reflect) {
+    NEED_INIT();
+    if (is_cplx) launch_spline_filter<cplx>((cplx*)data, n0, n1, n2, reflect, g_stream);
+    else launch_spline_filter<double>((double*)data, n0, n1, n2, reflect, g_stream);
+    CK_LAUNCH("spline_filter3");
+    return 0;
+}
+
+int emg3d_b200_pad_edge3(int is_cplx, int n0, int n1, int n2, const void* src, int npad, void* dst) {
+    NEED_INIT();
+    if (is_cplx) launch_pad_edge<cplx>((const cplx*)src, n0, n1, n2, npad, (cplx*)dst, g_stream);
+    else launch_pad_edge<double>((const double*)src, n0, n1, n2, npad, (double*)dst, g_stream);
+    CK_LAUNCH("pad_edge3");
+    return 0;
+}
+
+int emg3d_b200_interp_points(int is_cplx, int method, int n0, int n1, int n2, const void* data, int npad, int mode,
+                             double fill_re, double fill_im, const double* cx, const double* cy, const double* cz,
+                             long long npts, int tensor, int m0, int m1, double scale_re, double scale_im,
+                             int accumulate, void* out) {
+    NEED_INIT();
+    if (method != 1 && method != 3) return fail_msg("interp_points: method must be 1 (linear) or 3 (cubic)");
+    if (npts <= 0) return 0;
+    if (is_cplx) {
+        const cplx fill = make_c(fill_re, fill_im), scale = make_c(scale_re, scale_im);
+        if (method == 3)
+            launch_spline_eval<cplx>((const cplx*)data, n0, n1, n2, npad, mode, fill, cx, cy, cz, npts, tensor, m0, m1,
+                                     scale, accumulate, (cplx*)out, g_stream);
+        else
+            launch_linear_eval<cplx>((const cplx*)data, n0, n1, n2, fill, cx, cy, cz, npts, tensor, m0, m1, scale,
+                                     accumulate, (cplx*)out, g_stream);
+    } else {
+        if (method == 3)
+            launch_spline_eval<double>((const double*)data, n0, n1, n2, npad, mode, fill_re, cx, cy, cz, npts, tensor,
+                                       m0, m1, scale_re, accumulate, (double*)out, g_stream);
+        else
+            launch_linear_eval<double>((const double*)data, n0, n1, n2, fill_re, cx, cy, cz, npts, tensor, m0, m1,
+                                       scale_re, accumulate, (double*)out, g_stream);
+    }
+    CK_LAUNCH("interp_points");
     return 0;
 }
 

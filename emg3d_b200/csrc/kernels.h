@@ -83,6 +83,28 @@ template <typename T, typename Z>
 void launch_edge_curl(const Dims& d, const T* e, T* hf, const double* hx, const double* hy,
                       const double* hz, const Z* zeta, T scale, cudaStream_t st);
 
+// interpolation next to the solve (interp.cu)
+void launch_volume_average(const double* values, int nx, int ny, double* out, int mx, int my, int mz,
+                           const double* const* w, const int* const* iin, const int* const* start,
+                           const double* const* hnew, int log_scale, int add, cudaStream_t st);
+template <typename T>
+void launch_edges_to_vol(const Dims& d, const T* e, const double* hx, const double* hy, const double* hz, T* out,
+                         cudaStream_t st);
+void launch_gradient_field(const Dims& d, const cplx* e, const cplx* b, cplx smu0, const double* hx,
+                           const double* hy, const double* hz, double* out, cudaStream_t st);
+template <typename T>
+void launch_spline_filter(T* data, int n0, int n1, int n2, int reflect, cudaStream_t st);
+template <typename T>
+void launch_pad_edge(const T* src, int n0, int n1, int n2, int npad, T* dst, cudaStream_t st);
+template <typename T>
+void launch_spline_eval(const T* coef, int n0, int n1, int n2, int npad, int mode, T cval, const double* cx,
+                        const double* cy, const double* cz, int64_t npts, int tensor, int m0, int m1, T scale,
+                        int accumulate, T* out, cudaStream_t st);
+template <typename T>
+void launch_linear_eval(const T* data, int n0, int n1, int n2, T fill, const double* cx, const double* cy,
+                        const double* cz, int64_t npts, int tensor, int m0, int m1, T scale, int accumulate, T* out,
+                        cudaStream_t st);
+
 // vector helpers
 template <typename T>
 void launch_pec_zero(const Dims& d, T* e, cudaStream_t st);

@@ -10,7 +10,7 @@ the CUDA library works on, so host<->device transfers are plain copies.
 import numpy as np
 from scipy.constants import mu_0
 
-__all__ = ['Field', 'get_source_field']
+__all__ = ['Field', 'SourceField', 'get_source_field', 'get_receiver', 'get_magnetic_field']
 
 
 class Field:
@@ -101,8 +101,29 @@ class Field:
         self._view(2)[...] = v
 
     @property
+    def dtype(self):
+        return self._field.dtype
+
+    @property
     def frequency(self):
         return None if self._frequency is None else abs(self._frequency)
+
+    def interpolate_to_grid(self, grid, **interpolate_opts):
+        """The field on another grid (emg3d/fields.py:303-346): every component is interpolated
+        with :func:`emg3d_b200.maps.interpolate`; defaults ``method='cubic'``, ``log=False``,
+        ``extrapolate=False``.  Returns ``self`` if the grids are identical."""
+        from emg3d_b200 import maps
+        if grid == self.grid:
+            return self
+        opts = {'method': 'cubic', 'extrapolate': False, 'log': False, **interpolate_opts,
+                'grid': self.grid, 'xi': grid}
+        data = np.concatenate([maps.interpolate(values=f, **opts).ravel('F')
+                               for f in (self.fx, self.fy, self.fz)])
+        return Field(grid, data, frequency=self._frequency, electric=self.electric)
+
+    def get_receiver(self, receiver, method='cubic'):
+        """Responses at receiver coordinates: :func:`get_receiver`."""
+        return get_receiver(self, receiver, method)
 
     @property
     def sval(self):
@@ -130,7 +151,9 @@ def _segment_vector(grid, p0, p1):
     Per cell crossed: clip the segment to the cell, take the midpoint of the
     clipped piece and spread (piece length / total length) bilinearly onto the
     four parallel edges of each direction; finally scale each component by the
-    segment's extent in that direction (emg3d/fields.py:792-938).
+    segment's extent in that direction (emg3d/fields.py:792-938).  Returns the
+    non-zero entries ``{flat index in [fx | fy | fz]: value}`` (a segment touches a
+    handful of edges; no dense array is built).
     """
     nodes = [np.round(grid.nodes_x, 9), np.round(grid.nodes_y, 9),
              np.round(grid.nodes_z, 9)]
@@ -142,8 +165,9 @@ def _segment_vector(grid, p0, p1):
     length = np.linalg.norm(d)
     if length < 1e-15:
         raise ValueError(f"Provided finite dipole has no length: {np.r_[[p0, p1]]}.")
-    out = Field(grid, dtype=float)
-    comps = (out.fx, out.fy, out.fz)
+    shapes = (grid.shape_edges_x, grid.shape_edges_y, grid.shape_edges_z)
+    offs = (0, grid.n_edges_x, grid.n_edges_x + grid.n_edges_y)
+    out = {}
     # cell index ranges touched by the segment
     rng = []
     for a in range(3):
@@ -177,10 +201,50 @@ def _segment_vector(grid, p0, p1):
                             j[v] += dv
                             wu = r[u] if du else 1 - r[u]
                             wv = r[v] if dv else 1 - r[v]
-                            comps[c][tuple(j)] += wu * wv * frac
-    for c in range(3):
-        comps[c][...] *= d[c]
+                            flat = offs[c] + j[0] + shapes[c][0] * (j[1] + shapes[c][1] * j[2])
+                            out[flat] = out.get(flat, 0.0) + wu * wv * frac
+    for flat in out:
+        c = 0 if flat < offs[1] else 1 if flat < offs[2] else 2
+        out[flat] *= d[c]
     return out
+
+
+class SourceField(Field):
+    """Source field of dipoles / wires kept as what it is: a constant background and a handful
+    of non-zero edges (``sparse`` = (indices, values)).  ``solve`` sends only those to the device
+    (``emg3d_b200_fill_scatter``); the dense array of the Field contract is materialised on first
+    access of ``field`` / ``fx`` ... -- after which the dense array is authoritative (a caller may
+    have edited it) and is uploaded like any other field."""
+
+    def __init__(self, grid, indices, values, background, frequency):
+        self.grid, self._frequency, self.electric = grid, frequency, True
+        self._dense = None
+        self._sparse = (np.asarray(indices, dtype=np.int64), np.asarray(values))
+        self._background = np.asarray(values).dtype.type(background)
+
+    @property
+    def sparse(self):
+        """(indices, values, background), or None once the dense array was handed out."""
+        return None if self._sparse is None else (*self._sparse, self._background)
+
+    @property
+    def dtype(self):
+        return self._background.dtype if self._dense is None else self._dense.dtype
+
+    @property
+    def _field(self):
+        if self._dense is None:
+            idx, val = self._sparse
+            self._dense = np.full(self.grid.n_edges, self._background, dtype=val.dtype)
+            self._dense[idx] = val
+            self._sparse = None
+        return self._dense
+
+    def copy(self):
+        if self._sparse is not None:
+            return SourceField(self.grid, self._sparse[0].copy(), self._sparse[1].copy(),
+                               self._background, self._frequency)
+        return Field(self.grid, self._dense.copy(), self._frequency)
 
 
 def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
@@ -191,6 +255,7 @@ def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
     (a dipole of ``length`` metres centred there; emg3d/electrodes.py:752-755),
     ``(x0, x1, y0, y1, z0, z1)``, or an array of shape ``(n, 3)`` of wire
     points.  Magnetic sources and point sources are outside the hot path.
+    Returns a :class:`SourceField`: same values as the reference's dense field, held sparsely.
     """
     src = np.asarray(source, dtype=float)
     if src.size == 5:
@@ -200,14 +265,103 @@ def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
         pts = np.array([[src[0], src[2], src[4]], [src[1], src[3], src[5]]])
     else:
         pts = src.reshape(-1, 3)
-    vec = np.zeros(grid.n_edges)
+    total = {}
     for a, b in zip(pts[:-1], pts[1:]):
-        vec += _segment_vector(grid, a, b).field
-    sfield = Field(grid, data=vec, frequency=frequency)
-    sfield.field *= strength
+        for flat, v in _segment_vector(grid, a, b).items():
+            total[flat] = total.get(flat, 0.0) + v
+    idx = np.array(sorted(total), dtype=np.int64)
+    # the reference's sequence of operations on the dense array, applied to the non-zeros and to
+    # one background zero (same bits as its dense result)
+    if frequency is not None and frequency == 0:
+        raise ValueError(
+            "`frequency` must be f>0 (frequency domain) or f<0 "
+            f"(Laplace domain). Provided: {frequency} Hz.")
+    dtype = np.complex128 if frequency is not None and frequency > 0 else np.float64
+    vals = np.array([total[i] for i in idx] + [0.0]).astype(dtype)
+    vals *= strength
     if frequency is not None:
-        sfield.field *= -sfield.smu0
-    return sfield
+        sval = np.array(2j * np.pi * frequency) if frequency > 0 else np.array(-frequency)
+        vals *= -(sval * mu_0)
+    return SourceField(grid, idx, vals[:-1], vals[-1], frequency)
+
+
+def get_receiver(field, receiver, method='cubic'):
+    """Field (response) at receiver coordinates (emg3d/fields.py:522-615).
+
+    ``receiver``: ``(x, y, z, azimuth, elevation)`` (scalars or arrays), an object with
+    ``coordinates``, or a list of such.  The three components are interpolated (``'cubic'`` or
+    ``'linear'``) and combined with the direction cosines; receivers outside the grid or inside
+    the outermost cells (PEC boundary) are NaN.  ``field``: a :class:`Field` (uploaded) or a
+    :class:`DeviceField` (the device-resident result of ``solve(..., return_field='device')``);
+    the interpolation runs on the GPU (csrc/interp.cu), only the responses come back.
+    """
+    from emg3d_b200 import _lib, maps
+    if hasattr(receiver, 'coordinates'):
+        coordinates = receiver.coordinates
+    elif hasattr(tuple(receiver)[0], 'coordinates'):
+        coordinates = tuple(np.array([r.coordinates for r in receiver], dtype=float).T)
+    else:
+        coordinates = receiver
+        if len(coordinates) != 5:
+            raise ValueError(
+                "`receiver` needs to be in the form "
+                "(x, y, z, azimuth, elevation). "
+                f"Length of provided `receiver`: {len(coordinates)}.")
+    if method not in ('cubic', 'linear'):
+        raise ValueError(f"get_receiver: method must be 'cubic' or 'linear'; provided: {method!r}.")
+    grid = field.grid
+    xyz = np.broadcast_arrays(*[np.atleast_1d(np.asarray(c, dtype=float)) for c in coordinates[:3]])
+    shape = xyz[0].shape
+    xyz = [c.ravel() for c in xyz]
+    factors = [np.broadcast_to(f, shape).ravel() for f in _rotation(np.asarray(coordinates[3], dtype=float),
+                                                                    np.asarray(coordinates[4], dtype=float))]
+    dtype = np.dtype(field.dtype)
+    if isinstance(field, DeviceField):
+        comps = maps.field_components(field.array, grid, dtype)
+    else:
+        d_f = _lib.DeviceArray.from_host(np.asarray(field.field))
+        comps = maps.field_components(d_f, grid, dtype)
+    d_out = _lib.DeviceArray(xyz[0].size, dtype)
+    d_out.zero()
+    # per component: out += factor * interpolated value, on the device; one factor per receiver
+    # is applied on the host afterwards when the factors differ between receivers
+    uniform = all(np.ptp(f) == 0 for f in factors)
+    parts = []
+    for k, (comp, f) in enumerate(zip(comps, factors)):
+        if not np.any(np.abs(f) > 1e-10):
+            continue
+        points, _, _, _ = maps._points_from_grids(grid, comp.shape, tuple(xyz), method)
+        if uniform:
+            maps.sample_points(comp, points, xyz, method, mode='constant', fill=np.nan, d_out=d_out,
+                               scale=float(f[0]), accumulate=True)
+        else:
+            parts.append(f * maps.sample_points(comp, points, xyz, method, mode='constant',
+                                                fill=np.nan).download())
+    resp = d_out.download() if uniform else (np.sum(parts, axis=0) if parts else np.zeros(xyz[0].size, dtype))
+    # PEC: receivers in the outermost cells are not to be trusted
+    pec = np.zeros(xyz[0].size, dtype=bool)
+    for c, name in zip(xyz, 'xyz'):
+        nodes = getattr(grid, 'nodes_' + name)
+        pec |= (c < nodes[1]) | (c > nodes[-2])
+    resp = np.array(resp)
+    resp[pec] = np.nan
+    return resp.reshape(shape, order='F')
+
+
+class DeviceField:
+    """Result field left on the device (``solve(..., return_field='device')``): ``array`` is the
+    device buffer in the Field layout; ``download()`` gives the host :class:`Field`."""
+
+    def __init__(self, grid, array, dtype, frequency):
+        self.grid, self.array, self.dtype, self._frequency = grid, array, np.dtype(dtype), frequency
+
+    def get_receiver(self, receiver, method='cubic'):
+        return get_receiver(self, receiver, method)
+
+    def download(self):
+        f = Field(self.grid, dtype=self.dtype, frequency=self._frequency)
+        self.array.download(out=f.field)
+        return f
 
 
 def get_magnetic_field(model, efield):

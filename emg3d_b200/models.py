@@ -74,6 +74,20 @@ class Model:
         return (f"Model: {self.map.name}; {self.case}; "
                 f"{self.shape[0]} x {self.shape[1]} x {self.shape[2]}")
 
+    def interpolate_to_grid(self, grid, **interpolate_opts):
+        """The model on another grid (emg3d/models.py:322-380): every property is interpolated with
+        :func:`emg3d_b200.maps.interpolate`; defaults ``method='volume'``, ``extrapolate=True`` and
+        ``log=True`` unless the mapping is logarithmic already.  Returns ``self`` if the grids
+        are identical."""
+        from emg3d_b200 import maps
+        if grid == self.grid:
+            return self
+        opts = {'method': 'volume', 'extrapolate': True, 'log': not self.map.name.startswith('L'),
+                **interpolate_opts, 'grid': self.grid, 'xi': grid}
+        props = {name: maps.interpolate(values=getattr(self, name), **opts)
+                 for name in self._properties if getattr(self, name) is not None}
+        return Model(grid, mapping=self.map.name, **props)
+
 
 class VolumeModel:
     """Volume-averaged eta_{x,y,z} and zeta for one Laplace parameter."""

@@ -502,7 +502,7 @@ class DistributedMultigrid:
         self.gshape = tuple(int(n) for n in model.grid.shape_cells)
         nx, ny, nz = self.gshape
         self.model_grid = model.grid
-        self.dtype = np.dtype(np.asarray(sfield.field).dtype)
+        self.dtype = solver._field_dtype(sfield)
         self.frequency = sfield._frequency
 
         # --- plan the hierarchies of every semicoarsening pattern of the cycle -----------
@@ -1027,11 +1027,11 @@ def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
     try:
         do_return = efield is None or always_return
         if efield is not None:
-            if sfield.field.dtype != efield.field.dtype:
+            if dmg.dtype != efield.field.dtype:
                 raise ValueError(
                     "Source field and electric field must have the same "
                     "dtype; complex (f-domain) or real (s-domain). Provided:"
-                    f"sfield: {sfield.field.dtype}; efield: {efield.field.dtype}.")
+                    f"sfield: {dmg.dtype}; efield: {efield.field.dtype}.")
             dmg.upload_field(efield)
             # PEC: tangential edges on the six GLOBAL boundary faces are zero (solver.py:350-355);
             # the local z-boundaries of inner ranks are halo planes, refreshed by the solve

@@ -149,7 +149,7 @@ class _Level:
         ``VolumeModel`` for property maps the device kernel does not know.
         """
         map_name = getattr(model.map, 'name', None)
-        dtype = np.dtype(np.asarray(sfield.field).dtype)
+        dtype = _field_dtype(sfield)
         if map_name not in cls._MAPS:
             return cls.from_volume_model(models.VolumeModel(model, sfield), dtype)
         grid = meshes.BaseMesh(model.grid.h, model.grid.origin)
@@ -301,7 +301,7 @@ class Workspace:
         return tuple(fp)
 
     def level(self, model, sfield):
-        key = (id(model), complex(sfield.sval), np.dtype(np.asarray(sfield.field).dtype).str)
+        key = (id(model), complex(sfield.sval), _field_dtype(sfield).str)
         fp = self._fingerprint(model)
         hit = self._levels.get(key)
         if hit is not None and hit[0] == fp:
@@ -373,6 +373,12 @@ def _dev_prolongation(child, e_fine):
 # Public API
 # =========================================================================== #
 
+def _field_dtype(f):
+    """dtype of a field without touching its array (a SourceField stays sparse)."""
+    dt = getattr(f, 'dtype', None)
+    return np.dtype(dt) if dt is not None else np.dtype(np.asarray(f.field).dtype)
+
+
 def solve(model, sfield, sslsolver=True, semicoarsening=True,
           linerelaxation=True, verb=0, **kwargs):
     r"""Solve the 3-D EM diffusion problem with multigrid on the GPU.
@@ -391,6 +397,14 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
         Keeps the device-resident coefficients, grid hierarchy and line
         factorisations of ``model`` alive between calls (many sources or
         restarts on one model and frequency).
+    receivers : tuple or receiver object(s), optional
+        ``(x, y, z, azimuth, elevation)``: the responses at these receivers are sampled on the
+        device right after the solve (:func:`emg3d_b200.fields.get_receiver`,
+        ``receiver_method`` 'cubic' or 'linear') and returned after the field.
+    return_field : {True, False, 'device'}, default True
+        False: the field is not downloaded (with ``receivers``: only the responses cross PCIe);
+        'device': a :class:`emg3d_b200.fields.DeviceField` is returned (valid until the next
+        solve with the same workspace).  A provided ``efield`` is only updated when True.
     comm : parallel.NcclComm, optional
         ONE solve on the GPUs of ``comm`` (z-slabs, one process per GPU): a collective call,
         every rank passes the same arguments and receives the whole field.
@@ -417,6 +431,11 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     efield = kwargs.pop('efield', None)
     order = kwargs.pop('order', None)
     workspace = kwargs.pop('workspace', None)
+    receivers = kwargs.pop('receivers', None)
+    receiver_method = kwargs.pop('receiver_method', 'cubic')
+    return_field = kwargs.pop('return_field', True)
+    if return_field not in (True, False, 'device'):
+        raise ValueError(f"return_field must be True, False or 'device'; provided: {return_field!r}.")
     core.order_id(order)  # validate early
 
     var = MGParameters(
@@ -441,7 +460,7 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     # Coefficients to the device: eta/zeta are computed there from the property
     # arrays (models.VolumeModel, emg3d/models.py:654-691); a workspace keeps
     # them (and the whole level hierarchy) alive across calls.
-    dtype = sfield.field.dtype
+    dtype = _field_dtype(sfield)
     if workspace is not None:
         level = workspace.level(model, sfield)
     else:
@@ -451,7 +470,12 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     else:
         d_s = _lib.DeviceArray(level.n_edges, dtype)
     # dipole / wire sources are zero on all but a few edges: only those cross PCIe
-    var.sparse_source = d_s.upload_sparse(np.asarray(sfield.field))
+    sparse = getattr(sfield, 'sparse', None)
+    if sparse is not None:                               # fields.SourceField: nothing dense exists
+        d_s.fill_scatter(sparse[2], sparse[0], sparse[1])
+        var.sparse_source = True
+    else:
+        var.sparse_source = d_s.upload_sparse(np.asarray(sfield.field))
     info = ""
 
     # Reference error for the tolerance: ||b||_2 (solver.py:312), on the device.
@@ -474,11 +498,11 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
         # zero start: the initial residual is the source itself, ||r|| = ||b||
         var.e_is_zero, var.s_norm = not var.sslsolver, var.l2_refe
     else:
-        if sfield.field.dtype != efield.field.dtype:
+        if dtype != efield.field.dtype:
             raise ValueError(
                 "Source field and electric field must have the same "
                 "dtype; complex (f-domain) or real (s-domain). Provided:"
-                f"sfield: {sfield.field.dtype}; efield: {efield.field.dtype}."
+                f"sfield: {dtype}; efield: {efield.field.dtype}."
             )
         if efield.frequency is None:
             efield._frequency = sfield._frequency
@@ -517,13 +541,23 @@ def solve(model, sfield, sslsolver=True, semicoarsening=True,
     elif var.cycle:
         _multigrid(level, d_s, d_e, var)
 
-    # Bring the result back into the (possibly user-provided) host field.
-    d_e.download(out=efield.field.view(np.ndarray))
+    # Responses at the receivers, sampled where the field is (fields.get_receiver on the device).
+    responses = None
+    if receivers is not None:
+        responses = fields.get_receiver(fields.DeviceField(model.grid, d_e, dtype, sfield._frequency),
+                                        receivers, receiver_method)
+    if return_field is True:
+        # Bring the result back into the (possibly user-provided) host field.
+        d_e.download(out=efield.field.view(np.ndarray))
+    elif return_field == 'device':
+        efield = fields.DeviceField(model.grid, d_e, dtype, sfield._frequency)
+    else:
+        efield = None
 
-    return _finish(var, efield, info)
+    return _finish(var, efield, info, responses)
 
 
-def _finish(var, efield, info):
+def _finish(var, efield, info, responses=None):
     """Closing log lines, info dict and return convention of :func:`solve` (solver.py:407-449)."""
     exit_status = int(var.exit_message != 'CONVERGED')
 
@@ -560,12 +594,18 @@ def _finish(var, efield, info):
             'log': var.log_message,
         }
 
-    if var.do_return and var.return_info:
-        return efield, info_dict
-    elif var.do_return:
-        return efield
-    elif var.return_info:
-        return info_dict
+    # the reference's conventions (efield / (efield, info) / info / None), with the responses
+    # of `receivers=` after the field
+    out = []
+    if var.do_return and efield is not None:
+        out.append(efield)
+    if responses is not None:
+        out.append(responses)
+    if var.return_info:
+        out.append(info_dict)
+    if not out:
+        return None
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def solve_source(model, source, frequency, **kwargs):
@@ -611,7 +651,7 @@ def _down(dev, field):
 
 def multigrid(model, sfield, efield, var, **kwargs):
     """Multigrid V/W/F cycling (solver.py:471-649); ``efield`` updated in place."""
-    lv = _as_level(model, np.asarray(sfield.field).dtype
+    lv = _as_level(model, _field_dtype(sfield)
                    if not isinstance(sfield, _lib.DeviceArray) else sfield.dtype)
     d_s, d_e = _up(sfield), _up(efield)
     _multigrid(lv, d_s, d_e, var, **kwargs)
@@ -620,7 +660,7 @@ def multigrid(model, sfield, efield, var, **kwargs):
 
 def krylov(model, sfield, efield, var):
     """Krylov solver with optional MG preconditioner (solver.py:652-784)."""
-    lv = _as_level(model, np.asarray(sfield.field).dtype
+    lv = _as_level(model, _field_dtype(sfield)
                    if not isinstance(sfield, _lib.DeviceArray) else sfield.dtype)
     d_s, d_e = _up(sfield), _up(efield)
     _krylov(lv, d_s, d_e, var)
@@ -629,7 +669,7 @@ def krylov(model, sfield, efield, var):
 
 def smoothing(model, sfield, efield, nu, lr_dir, order=None):
     """``nu`` Gauss-Seidel sweeps with line relaxation ``lr_dir`` (solver.py:788-846)."""
-    lv = _as_level(model, np.asarray(sfield.field).dtype)
+    lv = _as_level(model, _field_dtype(sfield))
     d_s, d_e = _up(sfield), _up(efield)
     _dev_smoothing(lv, d_s, d_e, nu, lr_dir, core.order_id(order))
     _down(d_e, efield)
@@ -664,7 +704,7 @@ class _CoarseModel:
 
 def restriction(model, sfield, residual, sc_dir):
     """Coarse grid, coarse model and restricted residual (solver.py:849-944)."""
-    dtype = np.asarray(sfield.field).dtype
+    dtype = _field_dtype(sfield)
     lv = _as_level(model, dtype)
     child = _dev_restriction(lv, _up(residual), sc_dir)
     freq = getattr(sfield, '_frequency', None)
@@ -698,7 +738,7 @@ def prolongation(efield, cefield, sc_dir):
 
 def residual(model, sfield, efield, norm=False):
     """Residual field ``s - A e`` or its l2-norm (solver.py:1022-1070)."""
-    dtype = np.asarray(sfield.field).dtype
+    dtype = _field_dtype(sfield)
     lv = _as_level(model, dtype)
     d_s, d_e = _up(sfield), _up(efield)
     if norm:

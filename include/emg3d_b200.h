@@ -55,6 +55,11 @@ int emg3d_b200_d2d(void* dst_dev, const void* src_dev, size_t nbytes);
  * copy.  The device array is bit-identical to emg3d_b200_h2d either way.       */
 int emg3d_b200_h2d_sparse(void* dst_dev, const void* src_host, size_t n_elems, int elsize,
                           int* used_sparse);
+/* Device array = `fill_value` (one element, host) everywhere except idx[k] <- val[k], k < count
+ * (host arrays; indices must be distinct): a dipole / wire source field assembled from its few
+ * non-zero edges (emg3d/fields.py:386-519) without a dense host array. */
+int emg3d_b200_fill_scatter(void* dst_dev, size_t n_elems, int elsize, const void* fill_value,
+                            const long long* idx, const void* val, size_t count);
 int emg3d_b200_host_alloc(void** hptr, size_t nbytes);   /* pinned host memory */
 int emg3d_b200_host_free(void* hptr);
 
@@ -251,6 +256,48 @@ int emg3d_b200_host_gauss_seidel(int cplx, int ldir, int order, int nx, int ny, 
                                  const void* sz, const void* eta_x, const void* eta_y,
                                  const void* eta_z, const double* zeta, const double* hx,
                                  const double* hy, const double* hz, int nu);
+
+/* ---- interpolation on either side of a solve; device pointers ---------
+ *
+ * emg3d/maps.py:556-617 `interp_volume_average(nodes_x, nodes_y, nodes_z, values, new_nodes_x,
+ * new_nodes_y, new_nodes_z, new_values, new_vol)`, the numba kernel behind
+ * maps.interpolate(method='volume') / Model.interpolate_to_grid (emg3d/models.py:322-380).
+ * values (nx, ny, nz), out (mx, my, mz), x fastest.  Per axis a: the merged segments of
+ * maps.py:620-665 `_volume_average_weights` sorted by output cell -- w[a] (weights), iin[a]
+ * (input cell), start[a] (mx + 1 offsets: the segments of output cell o are start[o] ..
+ * start[o + 1]) -- and hnew[a], the widths of the new grid (new_vol = their product).
+ * log_scale = 1: log10 on the way in, 10** on the way out (maps.py:306-308, 366-367).
+ * add = 1: the sums are added to the content of `out` before the division, like the reference. */
+int emg3d_b200_volume_average(const double* values, int nx, int ny, int nz, double* out, int mx, int my,
+                              int mz, const double* const* w, const int* const* iin, const int* const* start,
+                              const double* const* hnew, int log_scale, int add);
+/* emg3d/maps.py:668-720 `interp_edges_to_vol_averages(ex, ey, ez, volumes, ox, oy, oz)`: field in
+ * the [fx | fy | fz] layout, out = [ox | oy | oz], three arrays of nx ny nz values of the field's
+ * dtype; hx, hy, hz: cell widths (device). */
+int emg3d_b200_edges_to_vol_averages(int is_cplx, int nx, int ny, int nz, const void* field, const double* hx,
+                                     const double* hy, const double* hz, void* out);
+/* The same fused with emg3d/simulations.py:1028-1031: the edge values are Re(b * smu0 * e) of the
+ * forward and the back-propagated field (complex128); out: three real arrays (the gradient on the
+ * computational grid). */
+int emg3d_b200_gradient_field(int nx, int ny, int nz, const void* efield, const void* bfield, double smu0_re,
+                              double smu0_im, const double* hx, const double* hy, const double* hz, double* out);
+/* Cubic B-spline coefficients of an (n0, n1, n2) array (x fastest), in place: what
+ * scipy.ndimage.spline_filter(order=3) computes inside map_coordinates, which the reference calls
+ * through emg3d/maps.py:500-553 `interp_spline_3d`.  reflect = 0: mirror boundaries (modes
+ * 'constant', 'mirror'); 1: reflect (mode 'nearest', after emg3d_b200_pad_edge3 with npad = 12). */
+int emg3d_b200_spline_filter3(int is_cplx, int n0, int n1, int n2, void* data, int reflect);
+int emg3d_b200_pad_edge3(int is_cplx, int n0, int n1, int n2, const void* src, int npad, void* dst);
+/* Values at points: method 3 = cubic spline (data = coefficients of emg3d_b200_spline_filter3;
+ * mode 0 'constant': `fill` outside the data; mode 1 'nearest': data is the padded array, npad
+ * samples per side), method 1 = linear (scipy RegularGridInterpolator, maps.py:355-362; a NaN
+ * coordinate marks a point that gets `fill`).  Coordinates in index units of the (unpadded) array:
+ * tensor = 0: point p = (cx[p], cy[p], cz[p]); tensor = 1: p = a + m0 (b + m1 c) = (cx[a], cy[b],
+ * cz[c]).  out[p] = scale * value, added to out[p] if accumulate (get_receiver sums the three
+ * components weighted by the receiver's direction cosines, emg3d/fields.py:596-604). */
+int emg3d_b200_interp_points(int is_cplx, int method, int n0, int n1, int n2, const void* data, int npad, int mode,
+                             double fill_re, double fill_im, const double* cx, const double* cy, const double* cz,
+                             long long npts, int tensor, int m0, int m1, double scale_re, double scale_im,
+                             int accumulate, void* out);
 
 /* core.solve (core.py:1481-1482): amat has 6 n entries, bvec n; both in place. */
 /* Magnetic field on the faces from the electric field on the edges (Faraday's law):

@@ -18,6 +18,9 @@ not on the hot path); ``_refstubs/`` provides two-line stand-ins.  Outputs:
     hfield.npz    get_magnetic_field / _edge_curl_factor (the first "next" row of
                   SURVEY.md 8f that shares the stencil family of amat_x)
 
+    maps.npz      volume averaging, edges -> cell averages, receiver sampling (cubic, linear),
+                  grid-to-grid interpolation of fields and models
+
 The fixtures travel to the GPU box; the reference does not.
 """
 import io
@@ -308,11 +311,93 @@ def make_hfield():
     np.savez_compressed(os.path.join(HERE, 'hfield.npz'), **out)
 
 
+def make_maps():
+    """Interpolation next to the solve: volume averaging, edges -> cell
+    averages, receiver sampling, grid-to-grid interpolation of fields and models."""
+    from emg3d import fields, maps
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def grid_of(n, scale, shift=0.0):
+        h = [scale * 1.1 ** rng.uniform(-2, 2, m) for m in n]
+        return emg3d.TensorMesh(h, tuple(-0.5 * hh.sum() + shift for hh in h))
+
+    # --- interp_volume_average: output grid inside, across and beyond the input grid
+    cases = [((7, 5, 6), (4, 6, 3), 1.3, 10.), ((6, 6, 6), (9, 8, 7), 0.8, -5.), ((5, 4, 3), (5, 4, 3), 1.0, 0.)]
+    for k, (n_in, n_out, sc, shift) in enumerate(cases):
+        gi, go = grid_of(n_in, 50.), grid_of(n_out, 50. * sc * np.array(n_in).mean() / np.array(n_out).mean(), shift)
+        vals = np.asfortranarray(10 ** rng.uniform(-1, 2, gi.shape_cells))
+        new = np.zeros(go.shape_cells, order='F')
+        maps.interp_volume_average(gi.nodes_x, gi.nodes_y, gi.nodes_z, vals, go.nodes_x, go.nodes_y,
+                                   go.nodes_z, new, go.cell_volumes.reshape(go.shape_cells, order='F'))
+        p = f"va{k}_"
+        out[p + 'h_in'] = np.concatenate(gi.h); out[p + 'n_in'] = np.array(n_in)
+        out[p + 'o_in'] = np.array(gi.origin, float)
+        out[p + 'h_out'] = np.concatenate(go.h); out[p + 'n_out'] = np.array(n_out)
+        out[p + 'o_out'] = np.array(go.origin, float)
+        out[p + 'values'], out[p + 'new'] = vals, new
+        out[p + 'new_log'] = maps.interpolate(gi, vals, go, method='volume', log=True)
+        for ax, (a, b) in enumerate(zip((gi.nodes_x, gi.nodes_y, gi.nodes_z), (go.nodes_x, go.nodes_y, go.nodes_z))):
+            w, ii, io = maps._volume_average_weights(a, b)
+            out[p + f'w{ax}'], out[p + f'ii{ax}'], out[p + f'io{ax}'] = w, ii, io
+    out['n_va'] = len(cases)
+
+    # --- interp_edges_to_vol_averages, real and complex
+    for k, (n, cplx) in enumerate([((5, 4, 6), False), ((3, 7, 4), True), ((1, 2, 3), True)]):
+        g = grid_of(n, 30.)
+        f = emg3d.Field(g, frequency=1.0 if cplx else -1.0)
+        f.field[:] = rng.standard_normal(f.field.size) + (1j * rng.standard_normal(f.field.size) if cplx else 0)
+        vol = g.cell_volumes.reshape(g.shape_cells, order='F')
+        o = [np.zeros(g.shape_cells, order='F', dtype=f.field.dtype) for _ in range(3)]
+        maps.interp_edges_to_vol_averages(f.fx, f.fy, f.fz, vol, *o)
+        p = f"ev{k}_"
+        out[p + 'h'] = np.concatenate(g.h); out[p + 'n'] = np.array(n)
+        out[p + 'field'] = np.asarray(f.field)
+        out[p + 'ox'], out[p + 'oy'], out[p + 'oz'] = o
+    out['n_ev'] = 3
+
+    # --- receivers (cubic / linear) and grid-to-grid interpolation of a field and a model
+    for k, (n, cplx) in enumerate([((12, 10, 9), True), ((8, 9, 7), False)]):
+        g = grid_of(n, 40.)
+        f = emg3d.Field(g, frequency=0.8 if cplx else -0.8)
+        # a smooth field plus noise
+        for comp, arr in enumerate((f.fx, f.fy, f.fz)):
+            arr[...] = rng.standard_normal(arr.shape) + (1j * rng.standard_normal(arr.shape) if cplx else 0)
+        nrec = 40
+        lo = [g.nodes_x[0], g.nodes_y[0], g.nodes_z[0]]
+        hi = [g.nodes_x[-1], g.nodes_y[-1], g.nodes_z[-1]]
+        rec = [rng.uniform(l - 20, h + 20, nrec) for l, h in zip(lo, hi)]
+        rec[0][:4] = [g.nodes_x[1], g.nodes_x[-2], g.nodes_x[2], 0.0]     # on the PEC limits / nodes
+        rec += [rng.uniform(-180, 180, nrec), rng.uniform(-90, 90, nrec)]
+        rec[3][:6] = [0, 90, 0, 0, 45, 0]; rec[4][:6] = [0, 0, 90, -90, 0, 0]
+        p = f"rc{k}_"
+        out[p + 'h'] = np.concatenate(g.h); out[p + 'n'] = np.array(n)
+        out[p + 'origin'] = np.array(g.origin, float)
+        out[p + 'field'] = np.asarray(f.field); out[p + 'frequency'] = f.frequency if cplx else -f.sval.real / (2 * np.pi) * -1
+        out[p + 'freq_arg'] = 0.8 if cplx else -0.8
+        out[p + 'rec'] = np.array(rec)
+        out[p + 'cubic'] = np.asarray(fields.get_receiver(f, tuple(rec), 'cubic'))
+        out[p + 'linear'] = np.asarray(fields.get_receiver(f, tuple(rec), 'linear'))
+        g2 = grid_of(tuple(m - 2 for m in n), 55., 15.)
+        out[p + 'h2'] = np.concatenate(g2.h); out[p + 'n2'] = np.array(g2.shape_cells)
+        out[p + 'origin2'] = np.array(g2.origin, float)
+        out[p + 'f2_cubic'] = np.asarray(f.interpolate_to_grid(g2).field)
+        out[p + 'f2_linear'] = np.asarray(f.interpolate_to_grid(g2, method='linear').field)
+        out[p + 'f2_cubic_extrap'] = np.asarray(f.interpolate_to_grid(g2, extrapolate=True).field)
+        rx = 10 ** rng.uniform(-0.5, 1.5, g.shape_cells)
+        m = emg3d.Model(g, rx, 2 * rx, 3 * rx, mapping='Resistivity')
+        m2 = m.interpolate_to_grid(g2)
+        out[p + 'prop'] = rx
+        out[p + 'prop2_x'], out[p + 'prop2_z'] = m2.property_x, m2.property_z
+    out['n_rc'] = 2
+    np.savez_compressed(os.path.join(HERE, 'maps.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield']
+    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield', 'maps']
     for w in which:
         globals()['make_' + w]()
-    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield'):
+    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield', 'maps'):
         fn = os.path.join(HERE, f + '.npz')
         if os.path.exists(fn):
             print(f, os.path.getsize(fn) // 1024, 'KiB')

@@ -68,3 +68,14 @@ def hfield_case(gh, k):
     d['frequency'] = float(gh[p + 'frequency'])
     d['shape'] = (d['hx'].size, d['hy'].size, d['hz'].size)
     return d
+
+
+def maps_grid(gm, prefix, suffix=''):
+    """(h list, origin) of a grid stored in maps.npz as concatenated widths + cell counts."""
+    key_h = {'': 'h', '_in': 'h_in', '_out': 'h_out', '2': 'h2'}[suffix]
+    key_n = {'': 'n', '_in': 'n_in', '_out': 'n_out', '2': 'n2'}[suffix]
+    key_o = {'': 'origin', '_in': 'o_in', '_out': 'o_out', '2': 'origin2'}[suffix]
+    h, n = gm[prefix + key_h], [int(v) for v in gm[prefix + key_n]]
+    hs = [h[:n[0]], h[n[0]:n[0] + n[1]], h[n[0] + n[1]:]]
+    origin = gm[prefix + key_o] if prefix + key_o in gm.files else np.zeros(3)
+    return hs, origin

@@ -6,7 +6,8 @@ Bars (fp64 throughout):
 * ``amat_x`` / residual, restriction, prolongation, cell sums: <= 1e-13
   (pure stencils, no solves);
 * smoothers in ``order='lex'`` against the reference's own outputs (golden) and
-  against the oracle on larger grids, after a call: point smoother <= 1e-11 (every
+  against the oracle on larger grids, after a call: point smoother <= 5e-12 (10 x the measured
+  4e-13; every
   update is a 6x6 solve; the reference itself is only defined to ~1e-13 because
   numba runs with fastmath); line smoothers <= 2e-10: the CUDA kernels eliminate
   the line edges before the transverse edges (4x4 blocks, csrc/gs_line.cu) while
@@ -29,7 +30,7 @@ from helpers import hfield_case, kernel_case, split_faces, split_field
 pytestmark = pytest.mark.gpu
 
 GS = ['gauss_seidel', 'gauss_seidel_x', 'gauss_seidel_y', 'gauss_seidel_z']
-TOL_GS = [1e-11, 2e-10, 2e-10, 2e-10]          # point, x-, y-, z-lines (see above)
+TOL_GS = [5e-12, 2e-10, 2e-10, 2e-10]          # point, x-, y-, z-lines (see above)
 
 
 @pytest.fixture(scope='module')
@@ -362,7 +363,7 @@ def test_residual_and_smoothing_wrappers(golden):
             g = mg.Grid([c['hx'], c['hy'], c['hz']])
             ovm = mg.VolumeModel.from_arrays(g, c['eta_x'], c['eta_y'], c['eta_z'], c['zeta'])
             mg.smoothing(ovm, c['s'], e2, 2, lr_dir)
-            assert rel_err(e1.field, e2) < (1e-11 if lr_dir == 0 else 2e-10), (k, lr_dir)
+            assert rel_err(e1.field, e2) < (5e-12 if lr_dir == 0 else 2e-10), (k, lr_dir)
 
 
 def test_volume_model_on_device(golden):
