@@ -244,7 +244,8 @@ def _points_from_grids(grid, shape, xi, method):
         if is_grid:
             new_points.append(getattr(xi, prop + c))
     if is_grid:
-        return points, new_points, tuple(len(p) for p in new_points), True
+        shape_out = tuple(xi.shape_cells) if method == 'volume' else tuple(len(p) for p in new_points)
+        return points, new_points, shape_out, True
     if isinstance(xi, tuple):
         arrs = np.broadcast_arrays(*[np.atleast_1d(np.asarray(a, dtype=float)) for a in xi])
         out_shape = arrs[0].shape
