@@ -37,6 +37,15 @@ class _Map:
     def backward(self, mapped):
         return self._fwd[self.name][1](mapped)
 
+    def derivative_chain(self, gradient, mapped):
+        """Chain rule from conductivity to the mapping's space, in place (maps.py:100-228)."""
+        if self.name == 'Conductivity':
+            return
+        sigma = self.backward(mapped)
+        gradient *= {'LgConductivity': sigma * np.log(10), 'LnConductivity': sigma,
+                     'Resistivity': -sigma ** 2, 'LgResistivity': -sigma * np.log(10),
+                     'LnResistivity': -sigma}[self.name]
+
 
 class Model:
     """Resistivity/conductivity model with triaxial anisotropy, mu_r, eps_r."""
