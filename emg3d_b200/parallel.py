@@ -547,6 +547,7 @@ class DistributedMultigrid:
         self.e = lv0.new_field()
         self.upload_source(sfield)
         self._sums = _lib.DeviceArray(8, np.float64)
+        self._krylov_pool = []
         self._sums.zero()
 
     def chain(self, pattern):
@@ -567,6 +568,13 @@ class DistributedMultigrid:
             self.comm.p2p_release()
         self._slots.clear()
         self._graphs.clear()
+        # Every rank has now unmapped its neighbours' arrays; nobody may FREE its own (exported)
+        # arrays before all ranks got here -- freeing memory a peer still has open through CUDA IPC
+        # is undefined (seen as an illegal address in a later, unrelated solve of the same
+        # process).  One all-reduce + sync is the barrier.
+        if hasattr(self.comm, 'allreduce_sum') and getattr(self, '_sums', None) is not None:
+            self.comm.allreduce_sum(self._sums, 1)
+            self._lib.sync()
 
     # ---- setup helpers ------------------------------------------------------------
     def _build_global_level(self, chain):
@@ -919,11 +927,20 @@ class DistributedMultigrid:
     # ---- Krylov backend (solver._DeviceOps interface) ------------------------------------
     class _Ops:
         def __init__(self, dmg):
-            self.dmg, self.dl = dmg, dmg.level0
+            self.dmg, self.dl, self._next = dmg, dmg.level0, 0
             self.vec = dmg._solver._Vec(int(dmg.dtype.kind == 'c'), dmg.level0.lv.n_edges)
 
         def new(self):
-            a = self.dmg.level0.lv.new_field()
+            # Work vectors are kept by the solver and reused by later solves: an exchanged array
+            # is registered with the neighbours by ADDRESS (peer-memory slots); a vector freed
+            # after one solve and another allocated at the same address by the next would be
+            # served by the stale mapping of the neighbour's freed array.
+            pool = self.dmg._krylov_pool
+            if self._next == len(pool):
+                pool.append(self.dmg.level0.lv.new_field())
+            a = pool[self._next]
+            self._next += 1
+            a.zero()
             return a
 
         def norm(self, x):

@@ -102,8 +102,10 @@ def main():
         warm = None
         if kw.get('warm'):                             # second solve on a live solver: warm timings
             kw2 = {k: v for k, v in kw.items() if k != 'warm'}
-            dmg = parallel.DistributedMultigrid(model, sfield, comm, semicoarsening=kw2.get('semicoarsening', True),
-                                                linerelaxation=kw2.get('linerelaxation', True))
+            for key in ('sslsolver', 'semicoarsening', 'linerelaxation'):      # solve()'s defaults
+                kw2.setdefault(key, True)
+            dmg = parallel.DistributedMultigrid(model, sfield, comm, semicoarsening=kw2['semicoarsening'],
+                                                linerelaxation=kw2['linerelaxation'])
             dmg.solve(**kw2)
             _lib.sync()
             dist.barrier()
