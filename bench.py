@@ -680,40 +680,70 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
     halo_ms = max_over_ranks(x0.elapsed_ms(x1) / 10)
     halo_bytes = sum(cnt for is_send, _, _, cnt in dl.plan if is_send) * dmg.dtype.itemsize
 
-    # end to end: every step uploads the rank's slab of the source from pinned host
-    # memory, runs the cycle through the public distributed driver and reads the
-    # rank's slab of the field back into pinned host memory
-    e2e = None
+    # end to end through the public API (see the single-GPU arm): per step the source is assembled
+    # on the host from its coordinates and every rank sends the non-zero edges of its slab; the
+    # cycle runs on the N GPUs; the field is gathered on rank 0's GPU over NVLink, the receiver
+    # responses are sampled there and only they come back to the hosts.  `e2e_full_field`: every
+    # rank's slab of the field is read back into pinned host memory instead.
+    e2e = e2e_full = None
     if not args.no_e2e:
         nloc = lv.n_edges
-        pin_s = _lib.PinnedArray(nloc, dmg.dtype)
-        pin_s.array[:] = dmg._slab(np.asarray(sfield.field))
-        pin_e = _lib.PinnedArray(nloc, dmg.dtype)
         nst = max(1, min(args.steps, 5))
+        src, freq = cfg['source'], cfg['frequency']
+        nrec = 101
+        rec = (np.linspace(0.5 * (grid.nodes_x[0] + src[0]), 0.5 * (grid.nodes_x[-1] + src[0]), nrec),
+               float(src[1]), float(src[2]), 0.0, 0.0)
+        probe = eb.get_source_field(grid, src, freq)
+        n_special = int(probe.sparse[0].size)
+        call = dict(comm=comm, dist_solver=dmg, plain=True, cycle='V', maxit=1, verb=-1, order=args.order)
 
-        def e2e_step():
-            dmg.s.upload(pin_s.array)
+        def survey_step():
+            return eb.solve(model, eb.get_source_field(grid, src, freq), receivers=rec, return_field=False, **call)
+
+        for _ in range(2):
+            resp = survey_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            resp = survey_step()
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        assert resp.shape == (nrec,) and np.all(np.isfinite(resp)) and float(np.abs(resp).max()) > 0
+        e2e = {"value": work * nst / sec, "unit": UNIT, "steps": nst, "ms_per_step": 1e3 * sec / nst,
+               "h2d_bytes_per_step": int(n_special * (8 + probe.dtype.itemsize) + 3 * nrec * 8),
+               "d2h_bytes_per_step": int(world * nrec * 16),
+               "call": "emg3d_b200.solve(model, get_source_field(grid, src, f), comm=comm, dist_solver=dmg, "
+                       "plain=True, cycle='V', maxit=1, receivers=rec, return_field=False)",
+               "note": "per step: source assembled on the host, its non-zero edges sent to the slabs that hold "
+                       f"them; cycle on {world} GPUs; field gathered on rank 0's GPU over NVLink, {nrec} receiver "
+                       "responses sampled there (cubic spline) and shared; model coefficients, slab hierarchies "
+                       "and the NCCL communicator stay alive between steps (dist_solver)"}
+
+        pin_e = _lib.PinnedArray(nloc, dmg.dtype)
+
+        def full_step():
+            dmg.upload_source(eb.get_source_field(grid, src, freq))
             info = dmg.solve(cycle='V', maxit=1, verb=-1)
             dmg.e.download(out=pin_e.array)
             return info
 
         for _ in range(2):
-            e2e_step()
+            full_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(nst):
-            info = e2e_step()
+            full_step()
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
         assert float(np.abs(pin_e.array[::1000]).max()) > 0
         import torch
         nb = torch.tensor([float(nloc * dmg.dtype.itemsize)], dtype=torch.float64, device='cuda')
         dist.all_reduce(nb)
-        e2e = {"value": work * nst / sec, "unit": UNIT, "steps": nst, "ms_per_step": 1e3 * sec / nst,
-               "h2d_bytes_per_step": int(nb.item()), "d2h_bytes_per_step": int(nb.item()),
-               "call": "DistributedMultigrid.solve(cycle='V', maxit=1) with the source slab uploaded "
-                       "from and the field slab downloaded to pinned host memory on every rank",
-               "note": "model coefficients, slab hierarchy and NCCL communicator stay alive between steps"}
+        e2e_full = {"value": work * nst / sec, "unit": UNIT, "steps": nst, "ms_per_step": 1e3 * sec / nst,
+                    "h2d_bytes_per_step": int(n_special * (8 + probe.dtype.itemsize)),
+                    "d2h_bytes_per_step": int(nb.item()),
+                    "call": "DistributedMultigrid.upload_source(sparse) + .solve(cycle='V', maxit=1) + the field "
+                            "slab of every rank downloaded to pinned host memory"}
 
     n_dist = dmg.n_dist
     dmg.close()
@@ -733,7 +763,7 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
                                        "neighbours' slabs, remote loads over NVLink, flag handshake)"
                                        if comm.p2p else "ncclSend/ncclRecv over NVLink"),
                     "norms": "all-reduced (NCCL)"},
-            "roofline": roofline, "cpu_baseline": None, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "e2e_full_field": e2e_full,
             "halo_exchange": {"transport": "peer-memory kernel" if comm.p2p else "nccl", "ms": halo_ms,
                               "bytes_sent_per_rank": int(halo_bytes),
                               "GBs_per_direction": halo_bytes / 2 / (halo_ms * 1e-3) / 1e9 if halo_ms else None},

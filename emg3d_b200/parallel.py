@@ -638,7 +638,37 @@ class DistributedMultigrid:
         return out
 
     def upload_source(self, sfield):
-        self.s.upload(self._slab(np.asarray(sfield.field)))
+        """The rank's slab of the source field; a sparse source (fields.SourceField) sends only the
+        non-zero edges that fall into the slab (halo planes included)."""
+        sparse = getattr(sfield, 'sparse', None)
+        if sparse is None:
+            self.s.upload(self._slab(np.asarray(sfield.field)))
+            return
+        idx, val, bg = sparse
+        loc_i, loc_v = [], []
+        for goff, loff, n in scatter_ranges(self.part0, 0, self.rank, self.gshape[0], self.gshape[1]):
+            m = (idx >= goff) & (idx < goff + n)
+            loc_i.append(idx[m] - goff + loff)
+            loc_v.append(val[m])
+        self.s.fill_scatter(bg, np.concatenate(loc_i), np.concatenate(loc_v))
+
+    def gather_to_root(self, src=None, root=0):
+        """The whole field on the device of rank ``root`` (global layout): every rank sends its owned
+        parts over NVLink (NCCL send / recv).  Returns the device array on ``root``, None elsewhere."""
+        src = self.e if src is None else src
+        isz = self.dtype.itemsize
+        nx, ny = self.gshape[0], self.gshape[1]
+        copies, sends, recvs = gather_plan(self.part0, 0, self.rank, nx, ny)
+        if self.rank == root:
+            n = sum(c for _, _, c in copies) + sum(c for _, _, c in recvs)
+            full = self._lib.DeviceArray(n, self.dtype)
+            lib = self._lib.load()
+            for loff, goff, cnt in copies:
+                self._lib.check(lib.emg3d_b200_d2d(full.ptr + goff * isz, src.ptr + loff * isz, cnt * isz))
+            self.comm.sendrecv_two(src.ptr, full.ptr, isz, [], recvs)
+            return full
+        self.comm.sendrecv_two(src.ptr, src.ptr, isz, [(p, o, c) for p, o, c in sends if p == root], [])
+        return None
 
     def upload_field(self, efield, dst=None):
         (self.e if dst is None else dst).upload(self._slab(np.asarray(efield.field)))
@@ -1037,21 +1067,32 @@ class DistributedMultigrid:
 
 def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
                       linerelaxation=True, verb=0, efield=None, order=None, always_return=False,
-                      return_info=False, exact=None, **kwargs):
+                      return_info=False, exact=None, receivers=None, receiver_method='cubic',
+                      return_field=True, dist_solver=None, **kwargs):
     """What ``emg3d_b200.solve(model, sfield, ..., comm=comm)`` runs: COLLECTIVE over the ranks of
     ``comm`` (one process per GPU; every rank passes the same global model, source field and
     options).  Same arguments, log, info dict and return conventions as the single-GPU solve;
-    every rank receives the whole field."""
+    every rank receives the whole field -- unless ``return_field=False``: with ``receivers`` the
+    field is gathered on rank 0's GPU over NVLink, sampled there and only the responses are
+    handed to every rank.  ``dist_solver``: a live :class:`DistributedMultigrid` of this model,
+    frequency and option set to reuse (its coefficients, hierarchies and factorisations stay on
+    the GPUs between solves, like a single-GPU ``Workspace``); it is not closed."""
     from emg3d_b200 import _lib, fields
     if kwargs.pop('plain', False):
         sslsolver = False if sslsolver is True else sslsolver
         semicoarsening = False if semicoarsening is True else semicoarsening
         linerelaxation = False if linerelaxation is True else linerelaxation
     kwargs.pop('workspace', None)
+    if return_field not in (True, False):
+        raise ValueError("distributed solve: return_field must be True or False")
     if sfield.frequency is None and getattr(sfield, '_frequency', None) is None:
         raise ValueError("Source field is missing frequency information.")
-    dmg = DistributedMultigrid(model, sfield, comm, order=order, exact=exact,
-                               semicoarsening=semicoarsening, linerelaxation=linerelaxation)
+    if dist_solver is None:
+        dmg = DistributedMultigrid(model, sfield, comm, order=order, exact=exact,
+                                   semicoarsening=semicoarsening, linerelaxation=linerelaxation)
+    else:
+        dmg = dist_solver
+        dmg.upload_source(sfield)
     try:
         do_return = efield is None or always_return
         if efield is not None:
@@ -1067,29 +1108,56 @@ def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
         info = dmg.solve(sslsolver=sslsolver, semicoarsening=semicoarsening,
                          linerelaxation=linerelaxation, verb=verb, zero_start=efield is None,
                          **kwargs)
-        # assemble the field on every rank: owned parts into a zeroed global device array, summed
-        n = int(model.grid.n_edges)
-        full = _lib.DeviceArray(n, dmg.dtype)
-        full.zero()
-        isz = dmg.dtype.itemsize
-        copies, _, _ = gather_plan(dmg.part0, 0, dmg.rank, dmg.gshape[0], dmg.gshape[1])
-        lib = _lib.load()
-        for loff, goff, cnt in copies:
-            _lib.check(lib.emg3d_b200_d2d(full.ptr + goff * isz, dmg.e.ptr + loff * isz, cnt * isz))
-        comm.allreduce_sum(full, n * (2 if dmg.dtype.kind == 'c' else 1))
-        if efield is None:
-            efield = fields.Field(model.grid, dtype=dmg.dtype, frequency=sfield._frequency)
-        elif efield.frequency is None:
-            efield._frequency = sfield._frequency
-        full.download(out=np.asarray(efield.field).view(np.ndarray))
+        responses = None
+        if receivers is not None:
+            # the spline prefilter of the cubic interpolation runs along whole grid lines: the
+            # field is gathered on ONE device (NVLink), sampled there, the responses shared
+            full = dmg.gather_to_root()
+            coords = np.broadcast_arrays(*[np.atleast_1d(np.asarray(c, dtype=float)) for c in
+                                           (receivers.coordinates if hasattr(receivers, 'coordinates')
+                                            else receivers)[:3]])
+            d_r = _lib.DeviceArray(2 * coords[0].size, np.float64)
+            d_r.zero()
+            if full is not None:
+                resp = fields.get_receiver(fields.DeviceField(model.grid, full, dmg.dtype, sfield._frequency),
+                                           receivers, receiver_method)
+                d_r.upload(np.ascontiguousarray(resp.ravel(), dtype=np.complex128).view(np.float64))
+                del full
+            comm.allreduce_sum(d_r, d_r.size)
+            responses = d_r.download().view(np.complex128).reshape(coords[0].shape)
+            if dmg.dtype.kind != 'c':
+                responses = responses.real
+        if return_field:
+            # assemble the field on every rank: owned parts into a zeroed global device array, summed
+            n = int(model.grid.n_edges)
+            full = _lib.DeviceArray(n, dmg.dtype)
+            full.zero()
+            isz = dmg.dtype.itemsize
+            copies, _, _ = gather_plan(dmg.part0, 0, dmg.rank, dmg.gshape[0], dmg.gshape[1])
+            lib = _lib.load()
+            for loff, goff, cnt in copies:
+                _lib.check(lib.emg3d_b200_d2d(full.ptr + goff * isz, dmg.e.ptr + loff * isz, cnt * isz))
+            comm.allreduce_sum(full, n * (2 if dmg.dtype.kind == 'c' else 1))
+            if efield is None:
+                efield = fields.Field(model.grid, dtype=dmg.dtype, frequency=sfield._frequency)
+            elif efield.frequency is None:
+                efield._frequency = sfield._frequency
+            full.download(out=np.asarray(efield.field).view(np.ndarray))
+        else:
+            efield = None
     finally:
-        dmg.close()
-    if do_return and return_info:
-        return efield, info
-    if do_return:
-        return efield
+        if dist_solver is None:
+            dmg.close()
+    out = []
+    if do_return and efield is not None:
+        out.append(efield)
+    if responses is not None:
+        out.append(responses)
     if return_info:
-        return info
+        out.append(info)
+    if not out:
+        return None
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 def _spawned_rank(rank, nranks, uid, model, field, frequency, kwargs, queue):
