@@ -140,20 +140,23 @@ class ClockSampler:
 
 
 def recorded_traffic(kernel_prefix):
-    """DRAM bytes per launch (read + write) of a kernel from the committed ncu capture
-    (profiles/r1_ncu_stalls.csv, `ncu --set full`, 256^3 workload); None if absent.
-    bench.py never runs under a profiler, so this is a recorded, not a live, number."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_stalls.csv')
+    """DRAM bytes per launch (read + write, mean over the captured launches) of a kernel from the
+    committed ncu capture of the shipped kernels (profiles/r2_ncu_full_summary.csv, `ncu --set
+    full`, 256^3 workload); None if absent.  bench.py never runs under a profiler, so this is a
+    recorded, not a live, number."""
+    import csv
+    path = os.path.join(HERE, 'profiles', 'r2_ncu_full_summary.csv')
     unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     try:
-        rows = [ln.rstrip('\n').split(',') for ln in open(path) if not ln.startswith('#')]
-        col = next(i for i, name in enumerate(rows[0]) if name.startswith(kernel_prefix))
+        rows = [r for r in csv.reader(ln for ln in open(path) if not ln.startswith('#'))]
+        names = next(r for r in rows if r[0] == 'Kernel Name')
+        cols = [i for i, n in enumerate(names) if i >= 2 and kernel_prefix in n]
         total = 0.0
         for want in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-            val, u = next(r[col] for r in rows if r[0] == want).split()
-            total += float(val) * unit[u]
+            r = next(r for r in rows if r[0] == want)
+            total += sum(float(r[i]) for i in cols) / len(cols) * unit[r[1]]
         return total
-    except (OSError, StopIteration, ValueError, KeyError, IndexError):
+    except (OSError, StopIteration, ValueError, KeyError, IndexError, ZeroDivisionError):
         return None
 
 

@@ -108,6 +108,7 @@ _SIGNATURES = {
     'emg3d_b200_gradient_field': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_double,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_spline_filter3': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
+    'emg3d_b200_copy_box3': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'emg3d_b200_pad_edge3': (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'emg3d_b200_interp_points': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                          c_double, c_double, c_void_p, c_void_p, c_void_p,

@@ -1029,6 +1029,19 @@ int emg3d_b200_spline_filter3(int is_cplx, int n0, int n1, int n2, void* data, i
     return 0;
 }
 
+int emg3d_b200_copy_box3(int is_cplx, int n0, int n1, int n2, const void* src, const int* lo, const int* m,
+                         void* dst) {
+    NEED_INIT();
+    for (int a = 0; a < 3; ++a) {
+        const int n = a == 0 ? n0 : a == 1 ? n1 : n2;
+        if (lo[a] < 0 || m[a] < 1 || lo[a] + m[a] > n) return fail_msg("copy_box3: box outside the array");
+    }
+    if (is_cplx) launch_copy_box<cplx>((const cplx*)src, n0, n1, lo, m, (cplx*)dst, g_stream);
+    else launch_copy_box<double>((const double*)src, n0, n1, lo, m, (double*)dst, g_stream);
+    CK_LAUNCH("copy_box3");
+    return 0;
+}
+
 int emg3d_b200_pad_edge3(int is_cplx, int n0, int n1, int n2, const void* src, int npad, void* dst) {
     NEED_INIT();
     if (is_cplx) launch_pad_edge<cplx>((const cplx*)src, n0, n1, n2, npad, (cplx*)dst, g_stream);

@@ -244,6 +244,25 @@ void launch_pad_edge(const T* src, int n0, int n1, int n2, int npad, T* dst, cud
 template void launch_pad_edge<double>(const double*, int, int, int, int, double*, cudaStream_t);
 template void launch_pad_edge<cplx>(const cplx*, int, int, int, int, cplx*, cudaStream_t);
 
+// sub-box [lo, lo + m) of an (n0, n1, n2) array (x fastest) into a compact (m0, m1, m2) array
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_box_kernel(const T* __restrict__ src, int n0, int n1, int l0, int l1, int l2, int m0, int m1, int m2,
+                T* __restrict__ dst) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)m0 * m1 * m2) return;
+    const int i = (int)(t % m0), j = (int)((t / m0) % m1), k = (int)(t / ((int64_t)m0 * m1));
+    dst[t] = ldg(src + (l0 + i) + (int64_t)n0 * ((l1 + j) + (int64_t)n1 * (l2 + k)));
+}
+template <typename T>
+void launch_copy_box(const T* src, int n0, int n1, const int* lo, const int* m, T* dst, cudaStream_t st) {
+    const int64_t n = (int64_t)m[0] * m[1] * m[2];
+    ++g_launch_count;
+    copy_box_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, n0, n1, lo[0], lo[1], lo[2], m[0], m[1], m[2], dst);
+}
+template void launch_copy_box<double>(const double*, int, int, const int*, const int*, double*, cudaStream_t);
+template void launch_copy_box<cplx>(const cplx*, int, int, const int*, const int*, cplx*, cudaStream_t);
+
 // ---- evaluation at points ------------------------------------------------------------------
 // Points: scattered (tensor = 0: point p has coordinates cx[p], cy[p], cz[p]) or a tensor grid
 // (tensor = 1: p = a + m0 (b + m1 c) has cx[a], cy[b], cz[c]).  Coordinates are in index units of

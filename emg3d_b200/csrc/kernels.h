@@ -95,6 +95,8 @@ void launch_gradient_field(const Dims& d, const cplx* e, const cplx* b, cplx smu
 template <typename T>
 void launch_spline_filter(T* data, int n0, int n1, int n2, int reflect, cudaStream_t st);
 template <typename T>
+void launch_copy_box(const T* src, int n0, int n1, const int* lo, const int* m, T* dst, cudaStream_t st);
+template <typename T>
 void launch_pad_edge(const T* src, int n0, int n1, int n2, int npad, T* dst, cudaStream_t st);
 template <typename T>
 void launch_spline_eval(const T* coef, int n0, int n1, int n2, int npad, int mode, T cval, const double* cx,

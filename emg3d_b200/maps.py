@@ -141,11 +141,20 @@ class _Sampler:
     """Cubic / linear interpolation of ONE device-resident 3-D array at many point sets: the
     spline coefficients are computed once (a copy; the data are not touched)."""
 
-    def __init__(self, d_values, shape, dtype, method, mode='constant'):
+    def __init__(self, d_values, shape, dtype, method, mode='constant', box=None):
         self.shape, self.dtype = tuple(int(n) for n in shape), np.dtype(dtype)
         self.cplx = int(self.dtype.kind == 'c')
         self.method, self.mode = method, mode
         lib = _lib.load()
+        self.lo = (0, 0, 0)
+        if box is not None and method == 'cubic' and mode == 'constant':
+            # only the part of the array the points can see (see _sample_box): a compact copy
+            lo, m = box
+            if tuple(m) != self.shape:
+                sub = _lib.DeviceArray(int(np.prod(m)), self.dtype)
+                i3 = ctypes.c_int * 3
+                _lib.check(lib.emg3d_b200_copy_box3(self.cplx, *self.shape, d_values.ptr, i3(*lo), i3(*m), sub.ptr))
+                d_values, self.shape, self.lo = sub, tuple(int(v) for v in m), tuple(int(v) for v in lo)
         n0, n1, n2 = self.shape
         self.npad = 0
         if method == 'cubic':
@@ -157,8 +166,11 @@ class _Sampler:
                                                     self.data.ptr))
                 _lib.check(lib.emg3d_b200_spline_filter3(self.cplx, *m, self.data.ptr, 1))
             elif mode == 'constant':
-                self.data = _lib.DeviceArray(int(np.prod(self.shape)), self.dtype)
-                _lib.check(lib.emg3d_b200_d2d(self.data.ptr, d_values.ptr, self.data.nbytes))
+                if self.lo != (0, 0, 0) or getattr(d_values, '_scratch', False) or tuple(self.shape) != tuple(shape):
+                    self.data = d_values                 # (the compact copy made above)
+                else:
+                    self.data = _lib.DeviceArray(int(np.prod(self.shape)), self.dtype)
+                    _lib.check(lib.emg3d_b200_d2d(self.data.ptr, d_values.ptr, self.data.nbytes))
                 _lib.check(lib.emg3d_b200_spline_filter3(self.cplx, n0, n1, n2, self.data.ptr, 0))
             else:
                 raise ValueError(f"cubic interpolation: mode must be 'constant' or 'nearest'; provided: {mode!r}.")
@@ -260,6 +272,26 @@ def _points_from_grids(grid, shape, xi, method):
     return points, new_points, out_shape, False
 
 
+_SPLINE_MARGIN = 48      # 0.268^48 = 4e-28: the reach of the B-spline prefilter in double precision
+
+
+def _sample_box(coords, shape):
+    """Index box of an array of ``shape`` that holds everything cubic-spline values at ``coords``
+    (index units, per axis) depend on to double precision: their bounding box grown by the reach
+    of the prefilter's exponentially decaying impulse response, clipped to the array."""
+    lo, m = [], []
+    for c, n in zip(coords, shape):
+        inside = c[(c >= 0) & (c <= n - 1)]
+        if inside.size == 0:
+            a, b = 0, min(n, 4)
+        else:
+            a = max(int(np.floor(inside.min())) - _SPLINE_MARGIN, 0)
+            b = min(int(np.ceil(inside.max())) + _SPLINE_MARGIN + 1, n)
+        lo.append(a)
+        m.append(b - a)
+    return tuple(lo), tuple(m)
+
+
 def sample_points(values, points, new_points, method, mode='constant', fill=0.0, tensor=False,
                   d_out=None, scale=1.0, accumulate=False):
     """Device core of the cubic / linear interpolation: ``values`` (host array or
@@ -267,14 +299,22 @@ def sample_points(values, points, new_points, method, mode='constant', fill=0.0,
     arrays: per point, or per axis when ``tensor``).  Returns the device array of results
     (``d_out`` if given: ``d_out = scale * value (+ d_out)``)."""
     d_val, shape, dtype = _device_view(values)
-    sampler = _Sampler(d_val, shape, dtype, method, mode)
-    coords = []
+    host_coords = []
     for pts, new, n in zip(points, new_points, shape):
-        c = _index_coordinates(pts, new, method)
+        c = np.asarray(_index_coordinates(pts, new, method), dtype=float)
         if method == 'linear' and fill is not None:          # outside the grid: NaN marks `fill`
             new = np.asarray(new, dtype=float)
             c = np.where((new < pts[0]) | (new > pts[-1]), np.nan, c)
-        coords.append(_lib.DeviceArray.from_host(np.ascontiguousarray(c, dtype=float)))
+        host_coords.append(c)
+    box = None
+    if method == 'cubic' and mode == 'constant':
+        # a few receivers on a large grid: prefilter only what they can see; points outside the
+        # array (-> `fill`) are marked by NaN before the coordinates are shifted into the box
+        box = _sample_box(host_coords, shape)
+        host_coords = [np.where((c < 0) | (c > n - 1), np.nan, c - lo)
+                       for c, n, lo in zip(host_coords, shape, box[0])]
+    sampler = _Sampler(d_val, shape, dtype, method, mode, box=box)
+    coords = [_lib.DeviceArray.from_host(np.ascontiguousarray(c, dtype=float)) for c in host_coords]
     tshape = tuple(len(p) for p in new_points) if tensor else None
     npts = int(np.prod(tshape)) if tensor else coords[0].size
     if d_out is None:

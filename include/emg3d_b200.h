@@ -289,6 +289,11 @@ int emg3d_b200_gradient_field(int nx, int ny, int nz, const void* efield, const 
  * 'constant', 'mirror'); 1: reflect (mode 'nearest', after emg3d_b200_pad_edge3 with npad = 12). */
 int emg3d_b200_spline_filter3(int is_cplx, int n0, int n1, int n2, void* data, int reflect);
 int emg3d_b200_pad_edge3(int is_cplx, int n0, int n1, int n2, const void* src, int npad, void* dst);
+/* dst (m[0], m[1], m[2]) = the sub-box src[lo : lo + m] of an (n0, n1, n2) array (lo, m: host).  The
+ * spline prefilter decays like 0.268^k: coefficients computed on a box that extends 48 samples
+ * beyond the requested points equal those of the whole array to 1e-27 (emg3d_b200/maps.py). */
+int emg3d_b200_copy_box3(int is_cplx, int n0, int n1, int n2, const void* src, const int* lo, const int* m,
+                         void* dst);
 /* Values at points: method 3 = cubic spline (data = coefficients of emg3d_b200_spline_filter3;
  * mode 0 'constant': `fill` outside the data; mode 1 'nearest': data is the padded array, npad
  * samples per side), method 1 = linear (scipy RegularGridInterpolator, maps.py:355-362; a NaN
