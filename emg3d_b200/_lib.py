@@ -47,6 +47,8 @@ _SIGNATURES = {
     'emg3d_b200_launch_count': (c_int, [POINTER(c_longlong)]),
     'emg3d_b200_malloc': (c_int, [POINTER(c_void_p), c_size_t]),
     'emg3d_b200_free': (c_int, [c_void_p]),
+    'emg3d_b200_malloc_scratch': (c_int, [POINTER(c_void_p), c_size_t]),
+    'emg3d_b200_free_scratch': (c_int, [c_void_p]),
     'emg3d_b200_memset': (c_int, [c_void_p, c_int, c_size_t]),
     'emg3d_b200_h2d': (c_int, [c_void_p, c_void_p, c_size_t]),
     'emg3d_b200_d2h': (c_int, [c_void_p, c_void_p, c_size_t]),
@@ -214,18 +216,23 @@ def _hptr(a):
 class DeviceArray:
     """Owned device buffer with a NumPy-like dtype/size."""
 
-    def __init__(self, size, dtype):
+    def __init__(self, size, dtype, scratch=False):
+        """scratch: a short-lived work array from the stream-ordered pool (emg3d_b200_malloc_scratch)."""
         self.dtype = np.dtype(dtype)
         self.size = int(size)
         self.nbytes = self.size * self.dtype.itemsize
+        self.scratch = bool(scratch)
         p = c_void_p(0)
-        check(init().emg3d_b200_malloc(byref(p), self.nbytes))
+        if self.scratch:
+            check(init().emg3d_b200_malloc_scratch(byref(p), self.nbytes))
+        else:
+            check(init().emg3d_b200_malloc(byref(p), self.nbytes))
         self.ptr = p.value
 
     @classmethod
-    def from_host(cls, arr):
+    def from_host(cls, arr, scratch=False):
         arr = np.ascontiguousarray(arr.ravel('F') if arr.ndim > 1 else arr)
-        self = cls(arr.size, arr.dtype)
+        self = cls(arr.size, arr.dtype, scratch)
         self.upload(arr)
         return self
 
@@ -280,7 +287,10 @@ class DeviceArray:
     def free(self):
         if getattr(self, 'ptr', None):
             try:
-                load().emg3d_b200_free(self.ptr)
+                if getattr(self, 'scratch', False):
+                    load().emg3d_b200_free_scratch(self.ptr)
+                else:
+                    load().emg3d_b200_free(self.ptr)
             except Exception:
                 pass
             self.ptr = None

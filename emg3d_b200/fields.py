@@ -321,7 +321,7 @@ def get_receiver(field, receiver, method='cubic'):
     else:
         d_f = _lib.DeviceArray.from_host(np.asarray(field.field))
         comps = maps.field_components(d_f, grid, dtype)
-    d_out = _lib.DeviceArray(xyz[0].size, dtype)
+    d_out = _lib.DeviceArray(xyz[0].size, dtype, scratch=True)
     d_out.zero()
     # per component: out += factor * interpolated value, on the device; one factor per receiver
     # is applied on the host afterwards when the factors differ between receivers

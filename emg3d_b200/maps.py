@@ -151,7 +151,7 @@ class _Sampler:
             # only the part of the array the points can see (see _sample_box): a compact copy
             lo, m = box
             if tuple(m) != self.shape:
-                sub = _lib.DeviceArray(int(np.prod(m)), self.dtype)
+                sub = _lib.DeviceArray(int(np.prod(m)), self.dtype, scratch=True)
                 i3 = ctypes.c_int * 3
                 _lib.check(lib.emg3d_b200_copy_box3(self.cplx, *self.shape, d_values.ptr, i3(*lo), i3(*m), sub.ptr))
                 d_values, self.shape, self.lo = sub, tuple(int(v) for v in m), tuple(int(v) for v in lo)
@@ -161,7 +161,7 @@ class _Sampler:
             if mode == 'nearest':
                 self.npad = 12
                 m = [n + 2 * self.npad for n in self.shape]
-                self.data = _lib.DeviceArray(int(np.prod(m)), self.dtype)
+                self.data = _lib.DeviceArray(int(np.prod(m)), self.dtype, scratch=True)
                 _lib.check(lib.emg3d_b200_pad_edge3(self.cplx, n0, n1, n2, d_values.ptr, self.npad,
                                                     self.data.ptr))
                 _lib.check(lib.emg3d_b200_spline_filter3(self.cplx, *m, self.data.ptr, 1))
@@ -169,7 +169,7 @@ class _Sampler:
                 if self.lo != (0, 0, 0) or getattr(d_values, '_scratch', False) or tuple(self.shape) != tuple(shape):
                     self.data = d_values                 # (the compact copy made above)
                 else:
-                    self.data = _lib.DeviceArray(int(np.prod(self.shape)), self.dtype)
+                    self.data = _lib.DeviceArray(int(np.prod(self.shape)), self.dtype, scratch=True)
                     _lib.check(lib.emg3d_b200_d2d(self.data.ptr, d_values.ptr, self.data.nbytes))
                 _lib.check(lib.emg3d_b200_spline_filter3(self.cplx, n0, n1, n2, self.data.ptr, 0))
             else:
@@ -314,11 +314,11 @@ def sample_points(values, points, new_points, method, mode='constant', fill=0.0,
         host_coords = [np.where((c < 0) | (c > n - 1), np.nan, c - lo)
                        for c, n, lo in zip(host_coords, shape, box[0])]
     sampler = _Sampler(d_val, shape, dtype, method, mode, box=box)
-    coords = [_lib.DeviceArray.from_host(np.ascontiguousarray(c, dtype=float)) for c in host_coords]
+    coords = [_lib.DeviceArray.from_host(np.ascontiguousarray(c, dtype=float), scratch=True) for c in host_coords]
     tshape = tuple(len(p) for p in new_points) if tensor else None
     npts = int(np.prod(tshape)) if tensor else coords[0].size
     if d_out is None:
-        d_out = _lib.DeviceArray(npts, dtype)
+        d_out = _lib.DeviceArray(npts, dtype, scratch=True)
     sampler(coords, d_out, tshape, fill=0.0 if fill is None else fill, scale=scale, accumulate=accumulate)
     _lib.sync()
     return d_out

@@ -44,6 +44,11 @@ int emg3d_b200_launch_count(long long* count);
 /* ---- memory -------------------------------------------------------------- */
 int emg3d_b200_malloc(void** dptr, size_t nbytes);
 int emg3d_b200_free(void* dptr);
+/* Short-lived work arrays: stream-ordered allocations from the device's memory pool (no device
+ * synchronisation; not exportable to other processes -- arrays exchanged between GPUs come from
+ * emg3d_b200_malloc). */
+int emg3d_b200_malloc_scratch(void** dptr, size_t nbytes);
+int emg3d_b200_free_scratch(void* dptr);
 int emg3d_b200_memset(void* dptr, int byte, size_t nbytes);
 int emg3d_b200_h2d(void* dst_dev, const void* src_host, size_t nbytes);
 int emg3d_b200_d2h(void* dst_host, const void* src_dev, size_t nbytes);
