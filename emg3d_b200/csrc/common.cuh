@@ -105,6 +105,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned nb
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
+// asynchronous copy of one 8- or 16-byte element from global to shared memory (SASS LDGSTS)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 // nbytes (multiple of 16) from global memory into the L2, no destination
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned nbytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(nbytes) : "memory");

@@ -22,6 +22,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace emg {
 
 // Local system of one node in structured form.  Unknown order as in the
@@ -477,6 +480,216 @@ __device__ __forceinline__ void node_eliminate(NodeSys<T>& n) {
 }
 #undef SS
 
+// ---- tile-fused sweep with the tile's E box in shared memory (r2) -----------------
+// ncu on the kernel above (r1 / r2): 50 loads per node go to global memory, 42 of them 16-byte
+// loads with stride 2 between lanes (L1 wavefronts 68 % of peak, half of every sector unused per
+// colour phase), and every colour phase starts with a long-scoreboard wait on its load batch.
+// Here a block first copies the tile's box of E values (the edges of its nodes plus one layer of
+// outer edges: 6336 values = 101 KB for 64 x 4 x 4 nodes) into shared memory, the x index split by
+// parity (even entries of a row first, then the odd ones) so that the stride-2 accesses of a
+// colour phase become conflict-free unit-stride 16-byte accesses; the eight colour phases read
+// and update E there (results also go straight to global memory, fire and forget).  What does
+// not depend on E -- sources, diagonal, zeta, 1/h of the NEXT phase's node -- is loaded into
+// registers while the current phase computes (NodeIn), so a phase no longer starts with a trip to
+// DRAM.  Same node order and arithmetic as gs_point_tile_kernel.
+template <typename T>
+struct TileBox {
+    static constexpr int HX = (TX + 2 + 1) / 2;          // half a row: rows hold up to TX + 2 entries
+    static constexpr int ROW = 2 * HX;
+    static constexpr int NY0 = TY + 2, NZ0 = TZ + 2;     // ex: y-nodes, z-nodes (x-cells along the row)
+    static constexpr int NY1 = TY + 1, NZ1 = TZ + 2;     // ey: y-cells, z-nodes
+    static constexpr int NY2 = TY + 2, NZ2 = TZ + 1;     // ez: y-nodes, z-cells
+    static constexpr int OFF1 = ROW * NY0 * NZ0;
+    static constexpr int OFF2 = OFF1 + ROW * NY1 * NZ1;
+    static constexpr int SIZE = OFF2 + ROW * NY2 * NZ2;
+    T* base;
+    int o[3];                                            // global index of local index 0: (x0-1, y0-1, z0-1)
+    __device__ __forceinline__ static int pos(int x) { return (x & 1) * HX + (x >> 1); }
+    __device__ __forceinline__ static int ny(int c) { return c == 0 ? NY0 : c == 1 ? NY1 : NY2; }
+    __device__ __forceinline__ static int off(int c) { return c == 0 ? 0 : c == 1 ? OFF1 : OFF2; }
+    // element of component c at GLOBAL index q (cell index along c, node indices otherwise)
+    __device__ __forceinline__ T& at(int c, const int* q) const {
+        return base[off(c) + ROW * ((q[1] - o[1]) + ny(c) * (q[2] - o[2])) + pos(q[0] - o[0])];
+    }
+};
+
+// E-independent inputs of one node
+template <typename T>
+struct NodeIn {
+    T s[6], dg[6];            // source and diagonal of [x-, x+, y-, y+, z-, z+]
+    double z[2][2][2];        // zeta of the 8 cells around the node
+    double rh[3][2];
+};
+
+template <typename T>
+__device__ __forceinline__ void tile_node_load(const Model<T>& m, const FieldView<const T>& S, int ix, int iy,
+                                               int iz, NodeIn<T>& in) {
+    const int nd[3] = {ix, iy, iz};
+    const int64_t cs[3] = {1, m.d.n[0], (int64_t)m.d.n[0] * m.d.n[1]};
+    const int64_t c0 = (ix - 1) + cs[1] * (iy - 1) + cs[2] * (iz - 1);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        in.rh[a][0] = ldg(m.rh[a] + nd[a] - 1);
+        in.rh[a][1] = ldg(m.rh[a] + nd[a]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) in.z[i][j][k] = ldg(m.zeta + c0 + i + cs[1] * j + cs[2] * k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            int q[3] = {ix, iy, iz};
+            q[c] += sg - 1;
+            const int64_t id = S.idx(c, q);
+            in.s[2 * c + sg] = ldg(S.p[c] + id);
+            in.dg[2 * c + sg] = ldg(m.diag + (S.p[c] - S.p[0]) + id);
+        }
+}
+
+// outer edges of the face in plane (P, Q), quadrant (SP, SQ) from the box (see Faces::quad)
+template <typename T, int P, int Q, int SP, int SQ>
+__device__ __forceinline__ void tile_face(const TileBox<T>& box, int ix, int iy, int iz, const NodeIn<T>& in,
+                                          NodeSys<T>& n) {
+    int qo[3] = {ix, iy, iz};
+    qo[P] -= SP;
+    qo[Q] += SQ ? -1 : 1;
+    int ro[3] = {ix, iy, iz};
+    ro[Q] -= SQ;
+    ro[P] += SP ? -1 : 1;
+    face_acc<T, P, Q, SP, SQ>(in.z, in.rh, box.at(P, qo), box.at(Q, ro), n);
+}
+
+template <typename T>
+__device__ __forceinline__ void tile_node_relax(const TileBox<T>& box, const FieldView<T>& E, int ix, int iy,
+                                                int iz, const NodeIn<T>& in) {
+    NodeSys<T> n;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n.B[j][k] = 0.0;
+    n.cyz[0][0] = n.cyz[0][1] = n.cyz[1][0] = n.cyz[1][1] = 0.0;
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+        n.dX[sg] = in.dg[sg];
+        n.bX[sg] = in.s[sg];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        n.dT[k] = in.dg[2 + k];
+        n.bT[k] = in.s[2 + k];
+    }
+    // the three coordinate planes, four quadrants each, in the order of node_update
+    tile_face<T, 0, 1, 0, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 1, 0, 1>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 1, 1, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 1, 1, 1>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 2, 0, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 2, 0, 1>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 2, 1, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 0, 2, 1, 1>(box, ix, iy, iz, in, n);
+    tile_face<T, 1, 2, 0, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 1, 2, 0, 1>(box, ix, iy, iz, in, n);
+    tile_face<T, 1, 2, 1, 0>(box, ix, iy, iz, in, n);
+    tile_face<T, 1, 2, 1, 1>(box, ix, iy, iz, in, n);
+    node_eliminate<T>(n);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            int q[3] = {ix, iy, iz};
+            q[c] += sg - 1;
+            const T v = c == 0 ? n.bX[sg] : n.bT[2 * (c - 1) + sg];
+            box.at(c, q) = v;
+            E.p[c][E.idx(c, q)] = v;
+        }
+}
+
+// Measured (r2, 256^3, B200; profiles/r2_notes.md): correct (same parity tests) but SLOWER than
+// gs_point_tile_kernel -- 0.35 ms instead of 0.159 ms per tile-colour launch.  The 101 KB box
+// allows two blocks = 8 warps per SM (12 before), the prefetched inputs push the kernel to 250
+// registers, and the generic shared-memory addressing doubles the instruction count (112 M warp
+// instructions per launch against 56 M): 6.7 cycles per issued instruction x 2 warps per
+// scheduler loses against 8.6 x 3.  DRAM traffic is unchanged (0.50 GB read + 0.10 GB written
+// per launch): the tile's halo re-reads were L2 hits already.  Kept as an option
+// (-DEMG_PT_SMEM=1), off by default.
+#ifndef EMG_PT_SMEM
+#define EMG_PT_SMEM 0             // 1: tile kernel with the E box in shared memory, 0: all loads global
+#endif
+#ifndef EMG_SMEM_MINB
+#define EMG_SMEM_MINB 2
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS, EMG_SMEM_MINB)
+gs_point_tile_smem_kernel(Model<T> m, T* e, const T* s, int tcx, int tcy, int tcz, int back) {
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    using B = TileBox<T>;
+    B box;
+    box.base = reinterpret_cast<T*>(tile_smem);
+    const int x0 = 1 + (2 * blockIdx.x + tcx) * TX;
+    const int y0 = 1 + (2 * blockIdx.y + tcy) * TY;
+    const int z0 = 1 + (2 * blockIdx.z + tcz) * TZ;
+    box.o[0] = x0 - 1; box.o[1] = y0 - 1; box.o[2] = z0 - 1;
+    const int t = threadIdx.x;
+    const int i = t % (TX / 2), j = (t / (TX / 2)) % (TY / 2), k = t / ((TX / 2) * (TY / 2));
+    FieldView<T> E(e, m.d);
+    FieldView<const T> S(s, m.d);
+    const int nx = m.d.n[0], ny = m.d.n[1], nz = m.d.n[2];
+
+    auto node_of = [&](int cc, int& ix, int& iy, int& iz) {
+        const int c = back ? 7 - cc : cc;
+        ix = x0 + 2 * i + (c & 1);
+        iy = y0 + 2 * j + ((c >> 1) & 1);
+        iz = z0 + 2 * k + ((c >> 2) & 1);
+        return ix < nx && iy < ny && iz < nz;
+    };
+    // inputs of the first phase: in flight while the box is copied
+    NodeIn<T> cur;
+    int ix, iy, iz;
+    bool valid = node_of(0, ix, iy, iz);
+    if (valid) tile_node_load<T>(m, S, ix, iy, iz, cur);
+
+    // ---- the tile's box of E: asynchronous element copies (LDGSTS), all in flight at once ----
+    {
+        constexpr int R0 = B::NY0 * B::NZ0, R1 = B::NY1 * B::NZ1, R2 = B::NY2 * B::NZ2;
+        constexpr int LEN = TX + 2;                      // entries per row (ex uses TX + 1 of them)
+        for (int el = t; el < (R0 + R1 + R2) * LEN; el += TILE_THREADS) {
+            const int row = el / LEN, lx = el - row * LEN;
+            const int c = row < R0 ? 0 : row < R0 + R1 ? 1 : 2;
+            const int rr = row - (c == 0 ? 0 : c == 1 ? R0 : R0 + R1);
+            const int nyc = B::ny(c);
+            const int lz = rr / nyc, ly = rr - lz * nyc;
+            const int gx = box.o[0] + lx, gy = box.o[1] + ly, gz = box.o[2] + lz;
+            // extents of component c: cells along c, nodes otherwise
+            const bool ok = gx <= (c == 0 ? nx - 1 : nx) && gy <= (c == 1 ? ny - 1 : ny) &&
+                            gz <= (c == 2 ? nz - 1 : nz) && !(c == 0 && lx > TX);
+            if (ok)
+                cp_async_elem<(int)sizeof(T)>(box.base + B::off(c) + B::ROW * (ly + nyc * lz) + B::pos(lx),
+                                              E.p[c] + E.idx(c, gx, gy, gz));
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    for (int cc = 0; cc < 8; ++cc) {
+        NodeIn<T> nxt;
+        int jx = 0, jy = 0, jz = 0;
+        bool nvalid = false;
+        if (cc < 7) {
+            nvalid = node_of(cc + 1, jx, jy, jz);
+            if (nvalid) tile_node_load<T>(m, S, jx, jy, jz, nxt);
+        }
+        if (valid) tile_node_relax<T>(box, E, ix, iy, iz, cur);
+        __syncthreads();
+        cur = nxt;
+        valid = nvalid; ix = jx; iy = jy; iz = jz;
+    }
+}
+
 // One column (ix, iz), nodes iy = y_first, y_first + DIR, ... (count nodes).
 template <typename T, int DIR>
 __device__ __forceinline__ void march_column(const Model<T>& m, const FieldView<T>& E,
@@ -745,6 +958,26 @@ void launch_gs_point(const Model<T>& m, T* e, const T* s, int nu, int order, cud
                 if (g.x == 0 || g.y == 0 || g.z == 0) continue;
 #if EMG_PT_MARCH
                 ++g_launch_count; gs_point_march_kernel<T><<<g, 32, 0, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
+#elif EMG_PT_SMEM
+                {
+                    constexpr int smem = TileBox<T>::SIZE * (int)sizeof(T);
+                    static bool attr_set = false;
+                    if (!attr_set) {
+                        cudaFuncSetAttribute(gs_point_tile_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                        cudaFuncSetAttribute(gs_point_tile_smem_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared);
+                        attr_set = true;
+                        if (getenv("EMG3D_B200_DEBUG")) {
+                            int nb = 0;
+                            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gs_point_tile_smem_kernel<T>,
+                                                                          TILE_THREADS, smem);
+                            fprintf(stderr, "gs_point_tile_smem_kernel: %d bytes of shared memory, %d blocks per SM\n",
+                                    smem, nb);
+                        }
+                    }
+                    ++g_launch_count;
+                    gs_point_tile_smem_kernel<T><<<g, TILE_THREADS, smem, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
+                }
 #else
                 ++g_launch_count; gs_point_tile_kernel<T><<<g, TILE_THREADS, 0, st>>>(m, e, s, tcx, tcy, tcz, back ? 1 : 0);
 #endif
