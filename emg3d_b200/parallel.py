@@ -252,6 +252,17 @@ def scatter_ranges(part, level, rank, nx, ny):
             (goz + gz * lo, oz, pz * (hi - lo))]
 
 
+def slab_sparse(part, rank, nx, ny, idx, val):
+    """The entries (global flat indices ``idx``, values ``val``) of a sparse field that fall into
+    the local slab of ``rank`` (halo planes included), as local flat indices and values."""
+    loc_i, loc_v = [], []
+    for goff, loff, n in scatter_ranges(part, 0, rank, nx, ny):
+        m = (idx >= goff) & (idx < goff + n)
+        loc_i.append(idx[m] - goff + loff)
+        loc_v.append(val[m])
+    return np.concatenate(loc_i), np.concatenate(loc_v)
+
+
 # =========================================================================== #
 # Device transport and distributed driver
 # =========================================================================== #
@@ -645,12 +656,8 @@ class DistributedMultigrid:
             self.s.upload(self._slab(np.asarray(sfield.field)))
             return
         idx, val, bg = sparse
-        loc_i, loc_v = [], []
-        for goff, loff, n in scatter_ranges(self.part0, 0, self.rank, self.gshape[0], self.gshape[1]):
-            m = (idx >= goff) & (idx < goff + n)
-            loc_i.append(idx[m] - goff + loff)
-            loc_v.append(val[m])
-        self.s.fill_scatter(bg, np.concatenate(loc_i), np.concatenate(loc_v))
+        loc_i, loc_v = slab_sparse(self.part0, self.rank, self.gshape[0], self.gshape[1], idx, val)
+        self.s.fill_scatter(bg, loc_i, loc_v)
 
     def gather_to_root(self, src=None, root=0):
         """The whole field on the device of rank ``root`` (global layout): every rank sends its owned

@@ -336,3 +336,29 @@ def test_shared_layer_direction_of_the_exchange_plans():
     assert [(s, c) for s, _, _, c in only(lo0, up0)] == [(1, pz)]      # ... or sends it
     assert [(s, c) for s, _, _, c in only(up1, lo1)] == [(1, pz)]
     assert [(s, c) for s, _, _, c in only(lo1, up1)] == [(0, pz)]
+
+
+def test_sparse_source_slab_equals_dense_slab():
+    """A sparse source (indices, values) cut to a rank's slab places the same entries as slicing
+    the dense field (halo planes included), for every rank of 1-, 2- and 4-rank partitions."""
+    from emg3d_b200 import parallel
+    nx, ny, nz = 6, 5, 16
+    n_edges = nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz
+    rng = np.random.default_rng(7)
+    idx = np.sort(rng.choice(n_edges, 60, replace=False)).astype(np.int64)
+    val = rng.standard_normal(60) + 1j * rng.standard_normal(60)
+    dense = np.zeros(n_edges, dtype=complex)
+    dense[idx] = val
+    for nranks in (1, 2, 4):
+        part = parallel.SlabPartition(nz, nranks, 0, [0], 2)
+        for rank in range(nranks):
+            ranges = parallel.scatter_ranges(part, 0, rank, nx, ny)
+            nloc = sum(n for _, _, n in ranges)
+            want = np.zeros(nloc, dtype=complex)
+            for goff, loff, n in ranges:
+                want[loff:loff + n] = dense[goff:goff + n]
+            li, lv = parallel.slab_sparse(part, rank, nx, ny, idx, val)
+            got = np.zeros(nloc, dtype=complex)
+            got[li] = lv
+            assert np.array_equal(got, want), (nranks, rank)
+            assert len(np.unique(li)) == len(li)
