@@ -49,10 +49,24 @@ struct NodeSys {
 
 // Contribution of the face in plane (P, Q), quadrant (SP, SQ) of the node.
 // All indices are template parameters so that everything stays in registers.
+// Addresses relative to the node: pe[c] points at element (ix, iy, iz) of component c, an
+// element at offset (dx, dy, dz) is pe[c] + dx + dy s1[c] + dz s2[c] with COMPILE-TIME offsets in
+// {-1, 0, 1}: the x-offset becomes an immediate of the load, the few distinct (dy, dz) rows are
+// shared sub-expressions -- instead of a 64-bit index polynomial per access (r2: 850 instructions
+// per node, ~ 300 of them integer / address arithmetic; the kernel is latency-, i.e. instruction-
+// bound at 12 warps per SM).
+template <typename P_>
+struct NodePtr {
+    P_* pe[3];
+    int64_t s1[3], s2[3];
+    template <int C, int DX, int DY, int DZ>
+    __device__ __forceinline__ P_* at() const { return pe[C] + DX + DY * s1[C] + DZ * s2[C]; }
+};
+
 template <typename T>
 struct Faces {
     template <int P, int Q, int SP, int SQ>
-    static __device__ __forceinline__ void quad(const FieldView<T>& E, int ix, int iy, int iz,
+    static __device__ __forceinline__ void quad(const NodePtr<T>& E,
                                                 const double (&z)[2][2][2], const double (&rh)[3][2],
                                                 NodeSys<T>& n) {
         constexpr int W = 3 - P - Q;
@@ -66,14 +80,13 @@ struct Faces {
         const double al_p = SQ ? -rq : rq;   // stencil entry of the local P-edge
         const double al_q = SP ? rp : -rp;   // stencil entry of the local Q-edge
         // outer P-edge: same P-cell, Q-node moved away from the node
-        int qo[3] = {ix, iy, iz};
-        qo[P] -= SP;
-        qo[Q] += SQ ? -1 : 1;
-        const T ep = E.p[P][E.idx(P, qo)];
-        int ro[3] = {ix, iy, iz};
-        ro[Q] -= SQ;
-        ro[P] += SP ? -1 : 1;
-        const T eq = E.p[Q][E.idx(Q, ro)];
+        constexpr int dq = SQ ? -1 : 1, dp = SP ? -1 : 1;
+        constexpr int qx = (P == 0 ? -SP : 0) + (Q == 0 ? dq : 0), qy = (P == 1 ? -SP : 0) + (Q == 1 ? dq : 0),
+                      qz = (P == 2 ? -SP : 0) + (Q == 2 ? dq : 0);
+        const T ep = *E.template at<P, qx, qy, qz>();
+        constexpr int rx = (Q == 0 ? -SQ : 0) + (P == 0 ? dp : 0), ry = (Q == 1 ? -SQ : 0) + (P == 1 ? dp : 0),
+                      rz = (Q == 2 ? -SQ : 0) + (P == 2 ? dp : 0);
+        const T eq = *E.template at<Q, rx, ry, rz>();
         const T out = al_p * ep + al_q * eq;   // = -(c_out . e_out)
         constexpr int kq = 2 * (Q - 1) + (1 - SQ);      // transverse index of the Q-edge
         // (diagonal entries come precombined from m.diag, see edge_diag_kernel)
@@ -89,13 +102,13 @@ struct Faces {
         n.bT[kq] += (g * al_q) * out;
     }
     template <int P, int Q>
-    static __device__ __forceinline__ void plane(const FieldView<T>& E, int ix, int iy, int iz,
+    static __device__ __forceinline__ void plane(const NodePtr<T>& E,
                                                  const double (&z)[2][2][2], const double (&rh)[3][2],
                                                  NodeSys<T>& n) {
-        quad<P, Q, 0, 0>(E, ix, iy, iz, z, rh, n);
-        quad<P, Q, 0, 1>(E, ix, iy, iz, z, rh, n);
-        quad<P, Q, 1, 0>(E, ix, iy, iz, z, rh, n);
-        quad<P, Q, 1, 1>(E, ix, iy, iz, z, rh, n);
+        quad<P, Q, 0, 0>(E, z, rh, n);
+        quad<P, Q, 0, 1>(E, z, rh, n);
+        quad<P, Q, 1, 0>(E, z, rh, n);
+        quad<P, Q, 1, 1>(E, z, rh, n);
     }
 };
 
@@ -131,17 +144,30 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
         for (int k = 0; k < 4; ++k) n.B[j][k] = 0.0;
     n.cyz[0][0] = n.cyz[0][1] = n.cyz[1][0] = n.cyz[1][1] = 0.0;
 
+    // pointers at the node's own position in every component (E, source, diagonal share the
+    // field layout); the edge below the node along its own axis is one own-axis stride back
+    NodePtr<T> pe;
+    const T* ps[3];
+    const T* pd[3];
+    int64_t own[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int64_t id = E.idx(c, ix, iy, iz);
+        pe.pe[c] = E.p[c] + id;
+        pe.s1[c] = E.s1[c];
+        pe.s2[c] = E.s2[c];
+        ps[c] = S.p[c] + id;
+        pd[c] = m.diag + (S.p[c] - S.p[0]) + id;
+        own[c] = c == 0 ? 1 : c == 1 ? E.s1[1] : E.s2[2];
+    }
     // diagonal of A at the six local edges (precombined per level: four face terms
     // minus 1/4 of the eta sum, see edge_diag_kernel); rhs: source
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-            int q[3] = {ix, iy, iz};
-            q[c] += sg - 1;
-            const int64_t id = S.idx(c, q);
-            const T src = ldg(S.p[c] + id);
-            const T dg = ldg(m.diag + (S.p[c] - S.p[0]) + id);
+            const T src = sg ? ldg(ps[c]) : ldg(ps[c] - own[c]);
+            const T dg = sg ? ldg(pd[c]) : ldg(pd[c] - own[c]);
             if (c == 0) {
                 n.dX[sg] = dg;
                 n.bX[sg] = src;
@@ -153,9 +179,9 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
     }
 
     // the three coordinate planes (p, q), four quadrants each (compile-time indices)
-    Faces<T>::template plane<0, 1>(E, ix, iy, iz, z, rh, n);
-    Faces<T>::template plane<0, 2>(E, ix, iy, iz, z, rh, n);
-    Faces<T>::template plane<1, 2>(E, ix, iy, iz, z, rh, n);
+    Faces<T>::template plane<0, 1>(pe, z, rh, n);
+    Faces<T>::template plane<0, 2>(pe, z, rh, n);
+    Faces<T>::template plane<1, 2>(pe, z, rh, n);
 
     // eliminate the x-edges: S = C - B^T dX^-1 B,  bT' = bT - B^T dX^-1 bX
     T rX[2], tX[2];
@@ -235,9 +261,8 @@ __device__ __forceinline__ void node_update(const Model<T>& m, const FieldView<T
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-            int q[3] = {ix, iy, iz};
-            q[c] += sg - 1;
-            E.p[c][E.idx(c, q)] = c == 0 ? n.bX[sg] : n.bT[2 * (c - 1) + sg];
+            T* dst = sg ? pe.pe[c] : pe.pe[c] - own[c];
+            *dst = c == 0 ? n.bX[sg] : n.bT[2 * (c - 1) + sg];
         }
     }
 }
