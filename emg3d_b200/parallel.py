@@ -252,6 +252,22 @@ def scatter_ranges(part, level, rank, nx, ny):
             (goz + gz * lo, oz, pz * (hi - lo))]
 
 
+def zline_schedule(nranks, nbatch, rank):
+    """Steps of one colour class of the z-line relaxation across slabs, for ``rank``: a list of
+    ``(phase, batch)``, phase 1 = forward substitution (ranks bottom-up), 2 = backward (top-down);
+    ``batch`` = the batch of lines this rank relaxes in the step, or None (it only takes part in
+    the interface exchange that follows EVERY step on every rank).  Batch b reaches rank r in
+    forward step b + r and in backward step b + (nranks - 1 - r): a pipeline of
+    ``nbatch + nranks - 1`` steps per phase."""
+    steps = []
+    for phase in (1, 2):
+        pos = rank if phase == 1 else nranks - 1 - rank
+        for t in range(nbatch + nranks - 1):
+            b = t - pos
+            steps.append((phase, b if 0 <= b < nbatch else None))
+    return steps
+
+
 def slab_sparse(part, rank, nx, ny, idx, val):
     """The entries (global flat indices ``idx``, values ``val``) of a sparse field that fall into
     the local slab of ``rank`` (halo planes included), as local flat indices and values."""
@@ -840,14 +856,11 @@ class DistributedMultigrid:
                 if sweep > 0 and cc == 0:
                     continue                             # idempotent repeat (gs_line.cu)
                 cg = 3 - cc if back else cc
-                for phase in (1, 2):
-                    pos = self.rank if phase == 1 else n - 1 - self.rank
-                    for t in range(nb + n - 1):
-                        b = t - pos
-                        if 0 <= b < nb:
-                            order = 1 | (phase << 18) | ((cg + 1) << 20) | (b << 23) | ((nb - 1) << 27)
-                            self._lib.check(lib.emg3d_b200_gauss_seidel(dl.win.ptr, e.ptr, s.ptr, 1, 3, order))
-                        self.exchange(dl, e, shared_from_lower=True)
+                for phase, b in zline_schedule(n, nb, self.rank):
+                    if b is not None:
+                        order = 1 | (phase << 18) | ((cg + 1) << 20) | (b << 23) | ((nb - 1) << 27)
+                        self._lib.check(lib.emg3d_b200_gauss_seidel(dl.win.ptr, e.ptr, s.ptr, 1, 3, order))
+                    self.exchange(dl, e, shared_from_lower=True)
 
     # ---- the cycle ---------------------------------------------------------------------
     def multigrid(self, var, level=0, new_cycmax=0, s=None, e=None):

@@ -362,3 +362,70 @@ def test_sparse_source_slab_equals_dense_slab():
             got[li] = lv
             assert np.array_equal(got, want), (nranks, rank)
             assert len(np.unique(li)) == len(li)
+
+
+@pytest.mark.parametrize('nranks,nbatch', [(1, 1), (2, 1), (2, 4), (4, 4), (8, 8), (8, 3)])
+def test_zline_schedule_is_a_pipeline(nranks, nbatch):
+    """Every rank takes the same number of steps (each is followed by a collective exchange); a
+    batch is relaxed by rank r only after rank r - 1 (forward) resp. r + 1 (backward) relaxed it
+    and exchanged; the backward phase of a batch starts after its forward phase on the top rank."""
+    from emg3d_b200.parallel import zline_schedule
+    sched = [zline_schedule(nranks, nbatch, r) for r in range(nranks)]
+    assert len({len(s) for s in sched}) == 1 and len(sched[0]) == 2 * (nbatch + nranks - 1)
+    when = {}
+    for r, steps in enumerate(sched):
+        for t, (phase, b) in enumerate(steps):
+            if b is not None:
+                assert (phase, b, r) not in when
+                when[(phase, b, r)] = t
+    for b in range(nbatch):
+        for r in range(nranks):
+            assert (1, b, r) in when and (2, b, r) in when
+            if r > 0:
+                assert when[(1, b, r)] > when[(1, b, r - 1)]
+            if r < nranks - 1:
+                assert when[(2, b, r)] > when[(2, b, r + 1)]
+        assert when[(2, b, nranks - 1)] > when[(1, b, nranks - 1)]
+
+
+def test_chained_line_solve_equals_the_global_solve():
+    """The scheme of the z-lines cut by slabs (parallel.zline_smoothing, csrc/gs_line.cu) on a scalar
+    tridiagonal model: pivots continued through the cuts, forward substitution rank after rank
+    with the intermediate of the piece's last node handed up through the halo, backward substitution
+    downwards with the solved value handed down -- equals the solve of the whole line."""
+    rng = np.random.default_rng(3)
+    n, cuts = 40, [0, 9, 23, 31, 40]                    # unknowns 0 .. n-1, four pieces
+    lo = rng.uniform(-1, 1, n)
+    up = np.r_[lo[1:], 0.0]                             # symmetric: up[i] = lo[i + 1]
+    dg = 2.5 + np.abs(lo) + np.abs(up) + 1j * rng.uniform(0, 1, n)
+    rhs = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    A = np.diag(dg) + np.diag(lo[1:], -1) + np.diag(up[:-1], 1)
+    want = np.linalg.solve(A, rhs)
+    # factorisation chained through the cuts (level_line_chain): pivot of the piece's first unknown
+    # continues from the lower piece's last pivot
+    piv = np.zeros(n, dtype=complex)
+    carry = None
+    for p0, p1 in zip(cuts[:-1], cuts[1:]):
+        for i in range(p0, p1):
+            prev = carry if i == p0 else piv[i - 1]
+            piv[i] = dg[i] - (0 if prev is None else lo[i] * up[i - 1] / prev)
+        carry = piv[p1 - 1]
+    # forward bottom-up: halo value = g of the lower piece's last unknown
+    g = np.zeros(n, dtype=complex)
+    halo = 0.0
+    for p0, p1 in zip(cuts[:-1], cuts[1:]):
+        prev = halo
+        for i in range(p0, p1):
+            g[i] = (rhs[i] - lo[i] * prev) / piv[i]
+            prev = g[i]
+        halo = g[p1 - 1]
+    # backward top-down: halo value = solved value of the upper piece's first unknown
+    x = np.zeros(n, dtype=complex)
+    halo = 0.0
+    for p0, p1 in reversed(list(zip(cuts[:-1], cuts[1:]))):
+        nxt = halo
+        for i in range(p1 - 1, p0 - 1, -1):
+            x[i] = g[i] - up[i] * nxt / piv[i]
+            nxt = x[i]
+        halo = x[p0]
+    assert np.linalg.norm(x - want) < 1e-13 * np.linalg.norm(want)
