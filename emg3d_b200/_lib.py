@@ -128,7 +128,7 @@ _SIGNATURES = {
     'emg3d_b200_p2p_init': (c_int, [POINTER(c_int)]),
     'emg3d_b200_p2p_register': (c_int, [c_void_p, POINTER(c_int)]),
     'emg3d_b200_p2p_release': (c_int, []),
-    'emg3d_b200_p2p_exchange': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'emg3d_b200_p2p_exchange': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     'emg3d_b200_p2p_status': (c_int, [POINTER(c_int)]),
     'emg3d_b200_p2p_shutdown': (c_int, []),
 }

@@ -154,6 +154,10 @@ int emg3d_b200_comm_allreduce_sum(double* dev, int n) {
 //   4. last block: tell the neighbours "I have read yours"  (done flag), then wait
 //      for their done flags, so that the next kernel in the stream may overwrite
 //      my boundary planes.
+// PUSH variant (r2, same kernel, `push` = 1): step 1 means "my halo planes may be overwritten",
+// step 3 WRITES my boundary planes into the neighbours' halo planes (posted remote stores do not
+// wait for a round trip per 16 bytes like remote loads do), step 4 means "my planes have arrived
+// at yours" and the final wait is for the neighbours' planes to have arrived here.
 // Flags carry a sequence number that lives in device memory and is advanced by the
 // kernel itself, so the launch is replayable from a CUDA graph.  Latency per
 // exchange: one launch + two NVLink flag round trips, instead of an NCCL group
@@ -177,6 +181,7 @@ struct P2pArgs {
     u64* seq;             // device: number of the next exchange (starts at 1)
     unsigned* counter;    // device: blocks that finished copying
     int* status;          // device: 1 after a spin timed out
+    int push;             // 1: src is local, dst is peer memory
 };
 
 __device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
@@ -237,11 +242,12 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(P2pArgs a) {
             for (u64 i = tid; i < n; i += nth) dst[i] = __ldcg(src + i);
         }
     }
-    __threadfence();
+    __threadfence_system();                               // (push: the stores went to another GPU)
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned prev = atomicAdd(a.counter, 1u);
         if (prev == gridDim.x - 1) {                     // last block: everything is copied
+            __threadfence_system();
             *a.counter = 0;
             *a.seq = seq + 1;
             if (a.peer_flags[0]) st_release_sys(a.peer_flags[0] + 3, seq);
@@ -391,7 +397,7 @@ int emg3d_b200_p2p_register(void* dev_ptr, int* slot) {
 // (from_upper[i] ? rank + 1 : rank - 1) registered in the same slot, to byte offset
 // my_off[i] of mine.  One kernel launch on the library stream; see above.
 int emg3d_b200_p2p_exchange(int slot, int n, const size_t* my_off, const size_t* peer_off,
-                            const size_t* nbytes, const int* from_upper) {
+                            const size_t* nbytes, const int* from_upper, int push) {
     if (!g_p2p.on || slot < 0 || slot >= (int)g_p2p.slots.size())
         return emg3d_b200_internal_fail("p2p_exchange: unknown slot");
     if (n > P2P_MAX_SEG) return emg3d_b200_internal_fail("p2p_exchange: too many segments");
@@ -402,12 +408,18 @@ int emg3d_b200_p2p_exchange(int slot, int n, const size_t* my_off, const size_t*
     for (int i = 0; i < n; ++i) {
         const int q = from_upper[i] ? 1 : 0;
         if (!s.peer[q]) return emg3d_b200_internal_fail("p2p_exchange: no such neighbour");
-        a.seg[i].src = s.peer[q] + peer_off[i];
-        a.seg[i].dst = s.local + my_off[i];
+        if (push) {
+            a.seg[i].src = s.local + my_off[i];
+            a.seg[i].dst = s.peer[q] + peer_off[i];
+        } else {
+            a.seg[i].src = s.peer[q] + peer_off[i];
+            a.seg[i].dst = s.local + my_off[i];
+        }
         a.seg[i].nbytes = nbytes[i];
         total += nbytes[i];
     }
     a.nseg = n;
+    a.push = push ? 1 : 0;
     a.my_flags = g_p2p.flags;
     a.peer_flags[0] = g_p2p.peer_flags[0];
     a.peer_flags[1] = g_p2p.peer_flags[1];

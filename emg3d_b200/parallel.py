@@ -212,6 +212,21 @@ def pull_plan(part, level, rank, nx, ny, shared_from_lower=False):
     return out
 
 
+def push_plan(part, level, rank, nx, ny, shared_from_lower=False):
+    """The halo exchange seen from the SENDING side: ``[(to_upper, my_offset, peer_offset, count)]``,
+    the ``count`` elements at ``my_offset`` of this rank's local field belong at ``peer_offset`` of
+    the neighbour's (``rank + 1`` if ``to_upper`` else ``rank - 1``): the neighbours' pull plans
+    read backwards."""
+    out = []
+    for q in (rank - 1, rank + 1):
+        if q < 0 or q >= part.nranks:
+            continue
+        for from_upper, q_off, my_off, cnt in pull_plan(part, level, q, nx, ny, shared_from_lower):
+            if bool(from_upper) == (rank > q):           # q pulls this one from me
+                out.append((int(q > rank), my_off, q_off, cnt))
+    return out
+
+
 def gather_plan(part, level, rank, nx, ny):
     """All-gather of the owned parts of a local field into the global layout.
 
@@ -356,9 +371,9 @@ class NcclComm:
                 A(*[c * itemsize for _, _, _, c in pulls]),
                 (ctypes.c_int * n)(*[u for u, _, _, _ in pulls]))
 
-    def p2p_exchange(self, slot, args):
+    def p2p_exchange(self, slot, args, push=False):
         if args[0]:
-            self._lib.check(self._lib.load().emg3d_b200_p2p_exchange(slot, *args))
+            self._lib.check(self._lib.load().emg3d_b200_p2p_exchange(slot, *args, int(bool(push))))
 
     def p2p_release(self):
         """Unmap every registered array (before the arrays are freed)."""
@@ -392,6 +407,10 @@ class _DLevel:
         self.plan_low = exchange_plan(part, level, rank, nx, ny, shared_from_lower=True)
         self.pulls_low = pull_plan(part, level, rank, nx, ny, shared_from_lower=True)
         self.pull_args_low = None
+        # the same two exchanges from the sending side (push variant of the peer-memory kernel)
+        self.pushes = push_plan(part, level, rank, nx, ny)
+        self.pushes_low = push_plan(part, level, rank, nx, ny, shared_from_lower=True)
+        self.push_args = self.push_args_low = None
         self.owned = owned_ranges(part, level, rank, nx, ny)
         # Smoother and residual run on the z-window [p0 - 1, hi] of the local grid:
         # one halo plane on either side, refreshed by the exchange and fixed during a
@@ -573,6 +592,8 @@ class DistributedMultigrid:
         self.s = lv0.new_field()
         self.e = lv0.new_field()
         self.upload_source(sfield)
+        import os
+        self.p2p_push = os.environ.get('EMG3D_B200_P2P_PUSH', '1') != '0'
         self._sums = _lib.DeviceArray(8, np.float64)
         self._krylov_pool = []
         self._sums.zero()
@@ -712,6 +733,16 @@ class DistributedMultigrid:
             slot = self._slots.get(field.ptr)
             if slot is None:                         # first exchange of this array: collective
                 slot = self._slots[field.ptr] = self.comm.p2p_register(field.ptr)
+            if slot >= 0 and self.p2p_push:
+                if shared_from_lower:
+                    if dl.push_args_low is None:
+                        dl.push_args_low = self.comm.p2p_args(dl.pushes_low, self.dtype.itemsize)
+                    self.comm.p2p_exchange(slot, dl.push_args_low, push=True)
+                    return
+                if dl.push_args is None:
+                    dl.push_args = self.comm.p2p_args(dl.pushes, self.dtype.itemsize)
+                self.comm.p2p_exchange(slot, dl.push_args, push=True)
+                return
             if slot >= 0:
                 if shared_from_lower:
                     if dl.pull_args_low is None:

@@ -245,8 +245,11 @@ int emg3d_b200_p2p_register(void* dev_ptr, int* slot);
 /* Forget all registered arrays and unmap the neighbours' copies.  Call on every rank before
  * the registered arrays are freed; synchronise the ranks before registering again.        */
 int emg3d_b200_p2p_release(void);
+/* push = 0: pull nbytes[i] from byte offset peer_off[i] of the neighbour's array (upper neighbour
+ * if from_upper[i]) to my_off[i] of mine; push = 1: write nbytes[i] from my_off[i] of mine to
+ * peer_off[i] of that neighbour's (posted stores over NVLink).  All ranks use the same mode. */
 int emg3d_b200_p2p_exchange(int slot, int n, const size_t* my_off, const size_t* peer_off,
-                            const size_t* nbytes, const int* from_upper);
+                            const size_t* nbytes, const int* from_upper, int push);
 int emg3d_b200_p2p_status(int* status);
 int emg3d_b200_p2p_shutdown(void);
 

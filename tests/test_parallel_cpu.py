@@ -429,3 +429,33 @@ def test_chained_line_solve_equals_the_global_solve():
             nxt = x[i]
         halo = x[p0]
     assert np.linalg.norm(x - want) < 1e-13 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize('nz,nranks,n_dist', [(16, 2, 1), (32, 4, 2), (64, 8, 2)])
+@pytest.mark.parametrize('low', [False, True])
+def test_push_plan_mirrors_the_pull_plans(nz, nranks, n_dist, low):
+    """Executing every rank's push plan moves exactly what executing every rank's pull plan
+    moves (virtual ranks, host arrays), for both directions of the shared fz layer."""
+    from emg3d_b200 import parallel
+    nx, ny = 5, 4
+    part = parallel.SlabPartition(nz, nranks, n_dist)
+    for level in range(n_dist):
+        rng = np.random.default_rng(level)
+        fields = []
+        for r in range(nranks):
+            lo, hi = part.local(level, r)
+            (px, py, pz), (ox, oy, oz) = parallel._comp_sizes(nx >> level or 1, ny >> level or 1, hi - lo)
+            fields.append(rng.standard_normal(oz + pz * (hi - lo)))
+        nxl, nyl = nx >> level or 1, ny >> level or 1
+        pulled = [f.copy() for f in fields]
+        for r in range(nranks):
+            for from_upper, mo, po, cnt in parallel.pull_plan(part, level, r, nxl, nyl, low):
+                q = r + 1 if from_upper else r - 1
+                pulled[r][mo:mo + cnt] = fields[q][po:po + cnt]
+        pushed = [f.copy() for f in fields]
+        for r in range(nranks):
+            for to_upper, mo, po, cnt in parallel.push_plan(part, level, r, nxl, nyl, low):
+                q = r + 1 if to_upper else r - 1
+                pushed[q][po:po + cnt] = fields[r][mo:mo + cnt]
+        for a, b in zip(pulled, pushed):
+            assert np.array_equal(a, b)
