@@ -404,7 +404,7 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src,
                 "traffic": recorded_traffic('gs_point_tile_kernel') if n == 256 else None,
-                "traffic_source": "profiles/r1_ncu_stalls.csv (ncu --set full, same workload); "
+                "traffic_source": "profiles/r2_ncu_full_summary.csv (ncu --set full of the shipped kernel, same workload, mean of 8 launches); "
                                   "algorithmic bytes per launch: %d" % int(bytes_per_launch),
                 "bytes_per_cell_sweep": bytes_per_cell_sweep,
                 "launch_ms": kms / klaunch,
