@@ -90,7 +90,11 @@ def main():
         dist.barrier()
         t0 = time.perf_counter()
         try:
-            e, info = eb.solve(model, sfield, comm=comm, return_info=True, **{k: v for k, v in kw.items() if k != 'warm'})
+            kws = {k: v for k, v in kw.items() if k not in ('warm', 'nosingle')}
+            if kw.get('nosingle'):                     # (the field stays on the GPUs)
+                e, info = None, eb.solve(model, sfield, comm=comm, return_info=True, return_field=False, **kws)
+            else:
+                e, info = eb.solve(model, sfield, comm=comm, return_info=True, **kws)
         except Exception as err:                       # noqa: BLE001
             if rank == 0:
                 print(json.dumps({'case': name, 'error': repr(err)}), flush=True)
@@ -99,6 +103,16 @@ def main():
             continue
         _lib.sync()
         dt = time.perf_counter() - t0
+        if kw.pop('nosingle', False):                  # the distributed solve alone (full-size runs)
+            if rank == 0:
+                hist = [float(f"{v:.3e}") for v in info['error_at_cycle'] / info['ref_error']]
+                print(json.dumps({'case': name, 'shape': [int(v) for v in grid.shape_cells], 'nranks': world,
+                                  'kw': kw, 'dist': {'it_mg': info['it_mg'], 'it_ssl': info['it_ssl'],
+                                                     'exit': info['exit_message'], 'wall_s': round(dt, 3),
+                                                     'rel_error': float(info['rel_error']), 'err_hist': hist}}),
+                      flush=True)
+            dist.barrier()
+            continue
         warm = None
         if kw.get('warm'):                             # second solve on a live solver: warm timings
             kw2 = {k: v for k, v in kw.items() if k != 'warm'}
