@@ -220,9 +220,21 @@ int emg3d_b200_malloc_scratch(void** dptr, size_t nbytes) {
     }
     *dptr = nullptr;
     cudaError_t me = cudaMallocAsync(dptr, nbytes ? nbytes : 16, g_stream);
-    if (me != cudaSuccess) {                                // pool exhausted: the evicting allocator
+    if (me != cudaSuccess) {
+        // out of memory: hand the pool's idle blocks back and let the evicting allocator make room
+        // (cached line factorisations are recomputed on demand), then try once more
         cudaGetLastError();
-        return fail("cudaMallocAsync", me);
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaStreamSynchronize(g_stream);
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        void* probe = nullptr;
+        if (malloc_evicting(&probe, nbytes ? nbytes : 16, nullptr, -1) == cudaSuccess) cudaFree(probe);
+        cudaGetLastError();
+        me = cudaMallocAsync(dptr, nbytes ? nbytes : 16, g_stream);
+        if (me != cudaSuccess) return fail("cudaMallocAsync", me);
     }
     return 0;
 }

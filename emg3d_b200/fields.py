@@ -285,6 +285,21 @@ def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
     return SourceField(grid, idx, vals[:-1], vals[-1], frequency)
 
 
+def receiver_coordinates(receiver):
+    """``(x, y, z, azimuth, elevation)`` of a receiver argument (fields.py:560-583): an object with
+    ``coordinates``, a list of such, or the tuple itself."""
+    if hasattr(receiver, 'coordinates'):
+        return receiver.coordinates
+    if hasattr(tuple(receiver)[0], 'coordinates'):
+        return tuple(np.array([r.coordinates for r in receiver], dtype=float).T)
+    if len(receiver) != 5:
+        raise ValueError(
+            "`receiver` needs to be in the form "
+            "(x, y, z, azimuth, elevation). "
+            f"Length of provided `receiver`: {len(receiver)}.")
+    return receiver
+
+
 def get_receiver(field, receiver, method='cubic'):
     """Field (response) at receiver coordinates (emg3d/fields.py:522-615).
 
@@ -296,17 +311,7 @@ def get_receiver(field, receiver, method='cubic'):
     the interpolation runs on the GPU (csrc/interp.cu), only the responses come back.
     """
     from emg3d_b200 import _lib, maps
-    if hasattr(receiver, 'coordinates'):
-        coordinates = receiver.coordinates
-    elif hasattr(tuple(receiver)[0], 'coordinates'):
-        coordinates = tuple(np.array([r.coordinates for r in receiver], dtype=float).T)
-    else:
-        coordinates = receiver
-        if len(coordinates) != 5:
-            raise ValueError(
-                "`receiver` needs to be in the form "
-                "(x, y, z, azimuth, elevation). "
-                f"Length of provided `receiver`: {len(coordinates)}.")
+    coordinates = receiver_coordinates(receiver)
     if method not in ('cubic', 'linear'):
         raise ValueError(f"get_receiver: method must be 'cubic' or 'linear'; provided: {method!r}.")
     grid = field.grid

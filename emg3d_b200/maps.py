@@ -166,8 +166,8 @@ class _Sampler:
                                                     self.data.ptr))
                 _lib.check(lib.emg3d_b200_spline_filter3(self.cplx, *m, self.data.ptr, 1))
             elif mode == 'constant':
-                if self.lo != (0, 0, 0) or getattr(d_values, '_scratch', False) or tuple(self.shape) != tuple(shape):
-                    self.data = d_values                 # (the compact copy made above)
+                if tuple(self.shape) != tuple(int(n) for n in shape):
+                    self.data = d_values                 # (the compact copy made above: filtered in place)
                 else:
                     self.data = _lib.DeviceArray(int(np.prod(self.shape)), self.dtype, scratch=True)
                     _lib.check(lib.emg3d_b200_d2d(self.data.ptr, d_values.ptr, self.data.nbytes))

@@ -1165,8 +1165,7 @@ def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
             # field is gathered on ONE device (NVLink), sampled there, the responses shared
             full = dmg.gather_to_root()
             coords = np.broadcast_arrays(*[np.atleast_1d(np.asarray(c, dtype=float)) for c in
-                                           (receivers.coordinates if hasattr(receivers, 'coordinates')
-                                            else receivers)[:3]])
+                                           fields.receiver_coordinates(receivers)[:3]])
             d_r = _lib.DeviceArray(2 * coords[0].size, np.float64)
             d_r.zero()
             if full is not None:
