@@ -596,6 +596,7 @@ class DistributedMultigrid:
         self.p2p_push = os.environ.get('EMG3D_B200_P2P_PUSH', '1') != '0'
         self._sums = _lib.DeviceArray(8, np.float64)
         self._krylov_pool = []
+        self._rec = self._seg = None                     # graph segments being recorded (_descend)
         self._sums.zero()
 
     def chain(self, pattern):
@@ -954,13 +955,14 @@ class DistributedMultigrid:
     def _descend(self, var, ch, child, level, new_cycmax):
         """Everything between restriction to and prolongation from `child`.
 
-        Below the finest level a visit is a fixed sequence of launches (smoothers,
-        transfer kernels, halo-exchange kernels, the gather and the replicated coarse
-        sub-cycle; no norms, no host decisions), so the visit of level 1 can be captured
-        into ONE CUDA graph per rank and replayed (EMG3D_B200_DIST_GRAPHS=1; off by default:
-        with the NCCL gather of the replicated levels inside the captured region the replay
-        hung on 2 B200s in r1; the replicated coarse levels still replay the single-GPU graphs
-        of solver._subcycle).
+        Below the finest level a visit is a fixed sequence of launches (smoothers, transfer
+        kernels, halo-exchange kernels -- no norms, no host decisions) around the gather + replicated
+        coarse sub-cycle.  With ``EMG3D_B200_DIST_GRAPHS=1`` the visit of level 1 is recorded on its
+        second execution as a list of SEGMENTS: every stretch of launches between two gathers
+        becomes one CUDA graph, the gather (NCCL send / recv, not capturable together with the
+        peer-memory flags: that hung in r1) and the replicated sub-cycle (which replays its own
+        single-GPU graphs) stay eager; later visits replay the list.  The kernels of levels 1-2
+        are shorter than the 10-15 us of host time an eager launch from Python costs.
         """
         def run():
             if level < ch.n_dist:
@@ -972,27 +974,56 @@ class DistributedMultigrid:
         solver = self._solver
         import os
         if not (level == 1 and solver.GRAPHS and os.environ.get('EMG3D_B200_DIST_GRAPHS', '0') == '1'
-                and var.verb <= 3
+                and var.verb <= 3 and self._rec is None
                 and not getattr(var, '_capturing', False)):
             return run()
         key = (int(new_cycmax), var.cycle, int(var.sc_dir), int(var.lr_dir), solver._order(var),
                int(var.nu_pre), int(var.nu_post), int(var.nu_coarse), tuple(var.clevel))
         g = self._graphs.get(key)
-        if g is None:
+        if g is None:                      # first visit: eager (builds caches, registers arrays)
             self._graphs[key] = False
             return run()
-        if g is False:
-            var._capturing = True
+        if g is False:                     # second visit: record the segments while executing them
+            self._rec = []
+            self._seg_begin(var)
             try:
-                with self._lib.Graph() as g:
-                    run()
+                run()
             finally:
-                var._capturing = False
-            self._graphs[key] = g
-        g.launch()
+                self._seg_end(var)
+                items, self._rec = self._rec, None
+            self._graphs[key] = items
+            return
+        for item in g:                     # replay
+            if isinstance(item, tuple):
+                self._coarse_body(var, *item)
+            else:
+                item.launch()
+
+    def _seg_begin(self, var):
+        var._capturing = True
+        self._seg = self._lib.Graph()
+        self._seg.__enter__()
+
+    def _seg_end(self, var):
+        """Close the open segment, keep it and run it (captured launches have not executed)."""
+        seg, self._seg = self._seg, None
+        var._capturing = False
+        if seg is not None:
+            seg.__exit__(None, None, None)
+            self._rec.append(seg)
+            seg.launch()
 
     def _coarse_replicated(self, var, ch, top, level, new_cycmax):
         """Gather the coarse source, solve the coarse sub-cycle redundantly, keep our slab."""
+        if self._rec is not None:          # recording: this part stays eager, between two segments
+            self._seg_end(var)
+            self._rec.append((ch, top, level, new_cycmax))
+            self._coarse_body(var, ch, top, level, new_cycmax)
+            self._seg_begin(var)
+            return
+        self._coarse_body(var, ch, top, level, new_cycmax)
+
+    def _coarse_body(self, var, ch, top, level, new_cycmax):
         isz = self.dtype.itemsize
         lib = self._lib.load()
         copies, sends, recvs = ch.gather
