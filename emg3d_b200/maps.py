@@ -6,8 +6,8 @@ functions of ``emg3d/maps.py`` that sit next to the hot path, backed by the CUDA
 reference (emg3d/maps.py)                  here
 =========================================  ======================================================
 ``interpolate`` (232-369)                  :func:`interpolate`, same arguments; methods
-                                           ``'volume'``, ``'cubic'``, ``'linear'`` on the device
-                                           (``'nearest'`` is an index lookup, NumPy)
+                                           ``'volume'``, ``'cubic'``, ``'linear'``, ``'nearest'``
+                                           on the device
 ``interp_spline_3d`` (500-553)             :func:`interp_spline_3d`
 ``interp_volume_average`` (556-617)        :func:`interp_volume_average`, same argument list
 ``_volume_average_weights`` (620-665)      :func:`_volume_average_weights` (O(n) per axis, NumPy)
@@ -376,25 +376,32 @@ def interpolate(grid, values, xi, method='linear', extrapolate=True, log=False, 
                     raise ValueError("One of the requested xi is out of bounds")
         res = sample_points(values, points, new_points, 'linear', fill=fill, tensor=is_grid).download()
     elif method == 'nearest':
-        if isinstance(values, DeviceView):
-            raise NotImplementedError("method='nearest' takes host arrays")
-        idx = []
+        # nearest grid index per axis (O(points) bookkeeping, SciPy's rule: the upper neighbour from
+        # a normalised distance > 0.5 on), then a gather on the device: the linear kernel evaluated
+        # AT a grid index returns that sample
+        fill = kwargs.pop('fill_value', None if extrapolate else 0.0)
+        kwargs.pop('bounds_error', None)
+        if kwargs:
+            raise NotImplementedError(f"nearest interpolation: unknown keywords {sorted(kwargs)}.")
+        coords = []
         for pts, new in zip(points, new_points):
             pts, new = np.asarray(pts, float), np.asarray(new, float)
             i = np.clip(np.searchsorted(pts, new) - 1, 0, max(pts.size - 2, 0))
             if pts.size > 1:
                 i = i + ((new - pts[i]) / (pts[i + 1] - pts[i]) > 0.5)
-            idx.append(np.clip(i, 0, pts.size - 1))
-        res = values[np.ix_(*idx)].ravel('F') if is_grid else values[tuple(idx)]
-        if not extrapolate:
-            out = np.zeros(res.shape, dtype=bool)
-            if is_grid:
-                masks = [(np.asarray(n) < p[0]) | (np.asarray(n) > p[-1]) for p, n in zip(points, new_points)]
-                out = (masks[0][:, None, None] | masks[1][None, :, None] | masks[2][None, None, :]).ravel('F')
-            else:
-                for p, n in zip(points, new_points):
-                    out |= (n < p[0]) | (n > p[-1])
-            res = np.where(out, kwargs.get('fill_value', 0.0), res)
+            c = np.clip(i, 0, pts.size - 1).astype(float)
+            if fill is not None:
+                c = np.where((new < pts[0]) | (new > pts[-1]), np.nan, c)
+            coords.append(c)
+        d_val, vshape, dtype = _device_view(values)
+        sampler = _Sampler(d_val, vshape, dtype, 'linear')
+        d_c = [_lib.DeviceArray.from_host(np.ascontiguousarray(c), scratch=True) for c in coords]
+        npts = int(np.prod(out_shape)) if is_grid else coords[0].size
+        d_out = _lib.DeviceArray(npts, dtype, scratch=True)
+        sampler(d_c, d_out, tuple(len(c) for c in coords) if is_grid else None,
+                fill=0.0 if fill is None else fill)
+        _lib.sync()
+        res = d_out.download()
     else:
         raise ValueError(f"Method '{method}' is not defined")
 

@@ -98,36 +98,6 @@ def test_source_field_is_sparse_and_equals_the_dense_reference(golden):
     assert k > 0
 
 
-def test_nearest_interpolation_and_point_bookkeeping_match_scipy():
-    """Host-only parts of maps.interpolate: where an array lives (nodes / cell centres per axis,
-    maps.py:371-497), `method='nearest'` against SciPy's RegularGridInterpolator with both
-    extrapolation settings, and the argument errors of the reference."""
-    import emg3d_b200 as eb
-    from scipy.interpolate import RegularGridInterpolator
-    rng = np.random.default_rng(1)
-    grid = eb.TensorMesh([rng.uniform(1, 3, 7), rng.uniform(1, 3, 5), rng.uniform(1, 3, 6)], (-4., 2., 0.))
-    for shape, pts in [(grid.shape_edges_x, (grid.cell_centers_x, grid.nodes_y, grid.nodes_z)),
-                       (grid.shape_edges_z, (grid.nodes_x, grid.nodes_y, grid.cell_centers_z)),
-                       (grid.shape_faces_y, (grid.cell_centers_x, grid.nodes_y, grid.cell_centers_z)),
-                       (tuple(grid.shape_cells), (grid.cell_centers_x, grid.cell_centers_y, grid.cell_centers_z))]:
-        vals = rng.standard_normal(shape)
-        got_pts, _, _, _ = eb.maps._points_from_grids(grid, shape, (0., 3., 1.), 'nearest')
-        for a, b in zip(got_pts, pts):
-            assert np.array_equal(a, b)
-        xi = np.stack([rng.uniform(p[0] - 1, p[-1] + 1, 50) for p in pts], axis=1)
-        for extrapolate in (True, False):
-            want = RegularGridInterpolator(pts, vals, method='nearest', bounds_error=False,
-                                           fill_value=None if extrapolate else 0.0)(xi)
-            got = eb.maps.interpolate(grid, vals, xi, method='nearest', extrapolate=extrapolate)
-            assert np.array_equal(got, want), (shape, extrapolate)
-    with pytest.raises(ValueError, match='must be a 3D ndarray living on'):
-        eb.maps.interpolate(grid, np.zeros((3, 3, 3)), (0., 0., 0.), method='nearest')
-    with pytest.raises(ValueError, match="only implemented for TensorMesh"):
-        eb.maps.interpolate(grid, np.zeros(grid.shape_cells), (0., 0., 0.), method='volume')
-    with pytest.raises(ValueError, match="is not defined"):
-        eb.maps.interpolate(grid, np.zeros(grid.shape_cells), (0., 0., 0.), method='quintic')
-
-
 def test_sample_box_covers_the_reach_of_the_prefilter():
     from emg3d_b200 import maps
     shape = (300, 40, 200)
