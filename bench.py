@@ -222,7 +222,7 @@ def run_reference(args):
     The reference's own parallel mode is a process pool of independent solves
     (emg3d/_multiprocessing.py:33-65), one per core; the kernels are single-threaded.  A step
     = one plain V(2,2)-cycle per core, all cores at once, on a bounded sibling of the workload
-    (128^3 when the run has at most 10 steps + warm-ups, else 96^3: about 4-12 s per step);
+    (128^3, 96^3, 64^3 ... : the largest that keeps the K + W steps within about four minutes);
     throughput = cell-sweeps of all cores / time of the slowest.  Workers are forked AFTER the
     oracle library is loaded, pinned to one core each and warmed on the same size."""
     rank = int(os.environ.get('RANK', '0'))
@@ -237,7 +237,10 @@ def run_reference(args):
     except AttributeError:
         cores_avail = list(range(os.cpu_count() or 1))
     cores = len(cores_avail)
-    n = 128 if args.steps + args.warmup <= 10 else 96
+    # sibling size: the largest whose run of K + W steps stays within about four minutes (one
+    # all-core step costs ~ 12 s at 128^3, ~ 6 s at 96^3 on the boxes seen so far)
+    rounds = max(1, args.steps + args.warmup)
+    n = next((m for m, sec in ((128, 12.0), (96, 6.0), (64, 2.0), (48, 1.0)) if rounds * sec <= 240), 32)
     if args.size < 128:
         n = min(n, args.size)
     one = cpu_baseline(n, repeats=1)                  # one thread, same size, machine otherwise idle
