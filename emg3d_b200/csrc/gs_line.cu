@@ -197,6 +197,10 @@ __device__ __forceinline__ void sweep_line_direct(const Model<T>& m, int tp, int
 
 
 // ---- kernels ---------------------------------------------------------------
+#ifndef EMG_LINE_THREADS
+#define EMG_LINE_THREADS 64       // lines (threads) per block of the thread-per-line sweep kernel
+#endif
+
 // xin / xout: [slot][10] factors handed across a z-slab cut (see factor_line), or null
 template <typename T, int D>
 __global__ void __launch_bounds__(64)
@@ -210,7 +214,7 @@ line_factor_kernel(Model<T> m, T* fac, LineSlots ls, int c, const T* xin, T* xou
 
 // lines t0 .. t1 - 1 of colour class c (the whole class, or one batch of it)
 template <typename T, int D, int PH>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(EMG_LINE_THREADS)
 gs_line_color_kernel(Model<T> m, const T* fac, LineSlots ls, T* e, const T* s, int c, int t0, int t1) {
     int tp, tq;
     const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,7 +358,7 @@ static void gs_dir(const Model<T>& m, const T* fac, const T* fac2, T* e, const T
                     launch_gs_line_seg_color<T>(m, D, fac2, e, s, c, st);
                     continue;
                 }
-                const int threads = 64;
+                const int threads = EMG_LINE_THREADS;
                 const int t0 = (int)((int64_t)ls.cnt[c] * batch / nbatch);
                 const int t1 = (int)((int64_t)ls.cnt[c] * (batch + 1) / nbatch);
                 if (t1 <= t0) continue;

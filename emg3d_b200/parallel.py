@@ -706,7 +706,7 @@ class DistributedMultigrid:
         copies, sends, recvs = gather_plan(self.part0, 0, self.rank, nx, ny)
         if self.rank == root:
             n = sum(c for _, _, c in copies) + sum(c for _, _, c in recvs)
-            full = self._lib.DeviceArray(n, self.dtype)
+            full = self._lib.DeviceArray(n, self.dtype, scratch=True)     # (pool memory: no cudaMalloc / cudaFree per solve)
             lib = self._lib.load()
             for loff, goff, cnt in copies:
                 self._lib.check(lib.emg3d_b200_d2d(full.ptr + goff * isz, src.ptr + loff * isz, cnt * isz))
@@ -1197,7 +1197,7 @@ def solve_distributed(model, sfield, comm, sslsolver=True, semicoarsening=True,
             full = dmg.gather_to_root()
             coords = np.broadcast_arrays(*[np.atleast_1d(np.asarray(c, dtype=float)) for c in
                                            fields.receiver_coordinates(receivers)[:3]])
-            d_r = _lib.DeviceArray(2 * coords[0].size, np.float64)
+            d_r = _lib.DeviceArray(2 * coords[0].size, np.float64, scratch=True)
             d_r.zero()
             if full is not None:
                 resp = fields.get_receiver(fields.DeviceField(model.grid, full, dmg.dtype, sfield._frequency),
