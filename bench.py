@@ -752,7 +752,7 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
                     "call": "DistributedMultigrid.upload_source(sparse) + .solve(cycle='V', maxit=1) + the field "
                             "slab of every rank downloaded to pinned host memory"}
 
-    n_dist = dmg.n_dist
+    n_dist, dmg_push = dmg.n_dist, bool(dmg.p2p_push)
     dmg.close()
     del dmg
     barrier()
@@ -767,7 +767,9 @@ def run_distributed(args, rank, world, local_rank, dist, barrier, max_over_ranks
             "config": workload_config(args.size, world, args.order),
             "run": {"distributed_levels": int(n_dist),
                     "halo_transport": ("one peer-memory kernel per exchange (CUDA IPC mapping of the "
-                                       "neighbours' slabs, remote loads over NVLink, flag handshake)"
+                                       "neighbours' slabs, " + ("posted remote stores" if dmg_push else
+                                                                "remote loads")
+                                       + " over NVLink, flag handshake)"
                                        if comm.p2p else "ncclSend/ncclRecv over NVLink"),
                     "norms": "all-reduced (NCCL)"},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "e2e_full_field": e2e_full,
