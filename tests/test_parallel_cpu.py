@@ -459,3 +459,90 @@ def test_push_plan_mirrors_the_pull_plans(nz, nranks, n_dist, low):
                 pushed[q][po:po + cnt] = fields[r][mo:mo + cnt]
         for a, b in zip(pulled, pushed):
             assert np.array_equal(a, b)
+
+
+def _split_local(loc, nx, ny, nzl):
+    """F-ordered 3-D views (fx, fy, fz) of a local 1-D field with nzl cells along z."""
+    shp = ((nx, ny + 1, nzl + 1), (nx + 1, ny, nzl + 1), (nx + 1, ny + 1, nzl))
+    out, i0 = [], 0
+    for s_ in shp:
+        n = int(np.prod(s_))
+        out.append(loc[i0:i0 + n].reshape(s_, order='F'))
+        i0 += n
+    return out
+
+
+@pytest.mark.parametrize('nranks', [2, 4])
+def test_exact_halves_across_slabs_equal_the_single_sweep_on_the_oracle(nranks):
+    """The exact halo variant (DistributedMultigrid.smoothing) emulated on the CPU with the real
+    plans and the C oracle as the smoother: every rank relaxes the nodes of one global z-parity on
+    its z-window, the halos are exchanged (the shared fz layer from the lower rank after the half
+    that relaxed the lower rank's top plane), then the other parity -- the assembled field equals
+    one multicolour sweep of the whole grid, for descending and ascending sweeps."""
+    import oracle
+    oracle.build()
+    nx, ny, nz = 4, 3, 16
+    rng = np.random.default_rng(9)
+    hs = [rng.uniform(1, 2, n) for n in (nx, ny, nz)]
+    cplx = lambda shape: np.asfortranarray(rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    eta = [cplx((nx, ny, nz)) * 0.1 - 1j for _ in range(3)]
+    zeta = np.asfortranarray(rng.uniform(1, 2, (nx, ny, nz)))
+    ne = field_sizes(nx, ny, nz)
+    e0 = rng.standard_normal(ne) + 1j * rng.standard_normal(ne)
+    s = rng.standard_normal(ne) + 1j * rng.standard_normal(ne)
+    ex, ey, ez = _split_local(e0, nx, ny, nz)              # PEC: tangential boundary edges are zero
+    ex[:, [0, -1], :] = 0; ex[:, :, [0, -1]] = 0
+    ey[[0, -1], :, :] = 0; ey[:, :, [0, -1]] = 0
+    ez[[0, -1], :, :] = 0; ez[:, [0, -1], :] = 0
+    part = parallel.SlabPartition(nz, nranks, 1)
+
+    def classes(back, pz):
+        return [c for c in (range(7, -1, -1) if back else range(8)) if (c >> 2) & 1 == pz]
+
+    def nodes_of(c, planes):
+        px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+        return [(ix, iy, iz) for iz in planes if 1 <= iz < nz and (iz - 1) & 1 == pz
+                for iy in range(1 + py, ny, 2) for ix in range(1 + px, nx, 2)]
+
+    for back in (True, False):
+        # --- one sweep of the whole grid
+        ref = e0.copy()
+        seq = [n for pz in ((1, 0) if back else (0, 1)) for c in classes(back, pz) for n in nodes_of(c, range(nz + 1))]
+        oracle.gs_sequence(0, *_split_local(ref, nx, ny, nz), *_split_local(s, nx, ny, nz), *eta, zeta, *hs,
+                           np.array(seq, dtype=np.int32))
+        # --- the same on slabs
+        locs = [local_from_global(part, 0, r, nx, ny, e0, owned_only=False) for r in range(nranks)]
+        srcs = [local_from_global(part, 0, r, nx, ny, s, owned_only=False) for r in range(nranks)]
+        for pz in ((1, 0) if back else (0, 1)):
+            for r in range(nranks):
+                lo, hi = part.local(0, r)
+                p0, p1 = part.owned(0, r)
+                z0 = 0 if r == 0 else p0 - lo - 1           # the window: one halo plane below
+                w0 = lo + z0                                # global plane of window plane 0
+                win = [a[:, :, z0:] for a in _split_local(locs[r], nx, ny, hi - lo)]
+                swin = [a[:, :, z0:] for a in _split_local(srcs[r], nx, ny, hi - lo)]
+                sl = slice(w0, hi)
+                rows = [(ix, iy, iz - w0) for c in classes(back, pz) for (ix, iy, iz) in nodes_of(c, range(p0, p1))]
+                if rows:
+                    oracle.gs_sequence(0, *win, *swin, *[np.asfortranarray(a[:, :, sl]) for a in eta],
+                                       np.asfortranarray(zeta[:, :, sl]), hs[0], hs[1], hs[2][sl],
+                                       np.array(rows, dtype=np.int32))
+            # boundaries of the ownership blocks are even planes: the plane below an interface is
+            # odd, i.e. of class bit 0 -- after that half the shared layer travels upwards
+            plans = [parallel.exchange_plan(part, 0, r, nx, ny, shared_from_lower=(pz == 0)) for r in range(nranks)]
+            new = [a.copy() for a in locs]
+            for src in range(nranks):
+                for dst in range(nranks):
+                    sends = [(o, n) for s_, p, o, n in plans[src] if s_ and p == dst]
+                    recvs = [(o, n) for s_, p, o, n in plans[dst] if not s_ and p == src]
+                    for (so, n), (ro, _) in zip(sends, recvs):
+                        new[dst][ro:ro + n] = locs[src][so:so + n]
+            locs = new
+        out = np.full(ne, np.nan + 0j)
+        for r in range(nranks):
+            copies, _, _ = parallel.gather_plan(part, 0, r, nx, ny)
+            for loff, goff, n in copies:
+                out[goff:goff + n] = locs[r][loff:loff + n]
+        assert not np.isnan(out).any()
+        assert np.linalg.norm(out - ref) <= 1e-14 * np.linalg.norm(ref), (nranks, back)
+        assert np.linalg.norm(ref - e0) > 0.1 * np.linalg.norm(e0)      # the sweep did something
