@@ -472,11 +472,12 @@ def _split_local(loc, nx, ny, nzl):
     return out
 
 
+@pytest.mark.parametrize('ldir', [0, 1, 2])
 @pytest.mark.parametrize('nranks', [2, 4])
-def test_exact_halves_across_slabs_equal_the_single_sweep_on_the_oracle(nranks):
+def test_exact_halves_across_slabs_equal_the_single_sweep_on_the_oracle(nranks, ldir):
     """The exact halo variant (DistributedMultigrid.smoothing) emulated on the CPU with the real
-    plans and the C oracle as the smoother: every rank relaxes the nodes of one global z-parity on
-    its z-window, the halos are exchanged (the shared fz layer from the lower rank after the half
+    plans and the C oracle as the smoother (point, x-line and y-line relaxation): every rank relaxes
+    the blocks of one global z-parity on its z-window, the halos are exchanged (the shared fz layer from the lower rank after the half
     that relaxed the lower rank's top plane), then the other parity -- the assembled field equals
     one multicolour sweep of the whole grid, for descending and ascending sweeps."""
     import oracle
@@ -496,19 +497,27 @@ def test_exact_halves_across_slabs_equal_the_single_sweep_on_the_oracle(nranks):
     ez[[0, -1], :, :] = 0; ez[:, [0, -1], :] = 0
     part = parallel.SlabPartition(nz, nranks, 1)
 
+    # point smoother: 8 node colours, bit 2 = z-parity; x- / y-lines: 4 colours of the transverse
+    # node indices (y or x, and z), bit 1 = z-parity.  Blocks are (ix, iy, iz) resp. (t1, iz).
+    ncls, zbit = (8, 2) if ldir == 0 else (4, 1)
+
     def classes(back, pz):
-        return [c for c in (range(7, -1, -1) if back else range(8)) if (c >> 2) & 1 == pz]
+        return [c for c in (range(ncls - 1, -1, -1) if back else range(ncls)) if (c >> zbit) & 1 == pz]
 
     def nodes_of(c, planes):
-        px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1
-        return [(ix, iy, iz) for iz in planes if 1 <= iz < nz and (iz - 1) & 1 == pz
-                for iy in range(1 + py, ny, 2) for ix in range(1 + px, nx, 2)]
+        if ldir == 0:
+            px, py, pz = c & 1, (c >> 1) & 1, (c >> 2) & 1
+            return [(ix, iy, iz) for iz in planes if 1 <= iz < nz and (iz - 1) & 1 == pz
+                    for iy in range(1 + py, ny, 2) for ix in range(1 + px, nx, 2)]
+        pp, pz = c & 1, c >> 1
+        n1 = ny if ldir == 1 else nx                       # transverse axis next to z
+        return [(a, iz) for iz in planes if 1 <= iz < nz and (iz - 1) & 1 == pz for a in range(1 + pp, n1, 2)]
 
     for back in (True, False):
         # --- one sweep of the whole grid
         ref = e0.copy()
         seq = [n for pz in ((1, 0) if back else (0, 1)) for c in classes(back, pz) for n in nodes_of(c, range(nz + 1))]
-        oracle.gs_sequence(0, *_split_local(ref, nx, ny, nz), *_split_local(s, nx, ny, nz), *eta, zeta, *hs,
+        oracle.gs_sequence(ldir, *_split_local(ref, nx, ny, nz), *_split_local(s, nx, ny, nz), *eta, zeta, *hs,
                            np.array(seq, dtype=np.int32))
         # --- the same on slabs
         locs = [local_from_global(part, 0, r, nx, ny, e0, owned_only=False) for r in range(nranks)]
@@ -522,9 +531,9 @@ def test_exact_halves_across_slabs_equal_the_single_sweep_on_the_oracle(nranks):
                 win = [a[:, :, z0:] for a in _split_local(locs[r], nx, ny, hi - lo)]
                 swin = [a[:, :, z0:] for a in _split_local(srcs[r], nx, ny, hi - lo)]
                 sl = slice(w0, hi)
-                rows = [(ix, iy, iz - w0) for c in classes(back, pz) for (ix, iy, iz) in nodes_of(c, range(p0, p1))]
+                rows = [(*n[:-1], n[-1] - w0) for c in classes(back, pz) for n in nodes_of(c, range(p0, p1))]
                 if rows:
-                    oracle.gs_sequence(0, *win, *swin, *[np.asfortranarray(a[:, :, sl]) for a in eta],
+                    oracle.gs_sequence(ldir, *win, *swin, *[np.asfortranarray(a[:, :, sl]) for a in eta],
                                        np.asfortranarray(zeta[:, :, sl]), hs[0], hs[1], hs[2][sl],
                                        np.array(rows, dtype=np.int32))
             # boundaries of the ownership blocks are even planes: the plane below an interface is
