@@ -26,13 +26,15 @@ conventions as on one GPU.
 * **Halo exchange** = one peer-memory kernel per exchange (CUDA IPC mapping of the
   neighbours' arrays, remote loads over NVLink, flag handshake; csrc/comm.cu), NCCL
   send/recv groups as the fallback.
-* **Norms and dot products** are sums over owned edges, all-reduced with NCCL; BiCGSTAB and
-  CGS run around the distributed cycle through the backend-neutral drivers of solver.py.
+* **Norms and dot products** are sums over owned edges, all-reduced with NCCL; BiCGSTAB, CGS
+  and GCROT(m,k) run around the distributed cycle through the backend-neutral drivers of
+  solver.py (GCROT: driver checked against SciPy on a NumPy backend, tests/test_krylov_cpu.py;
+  not yet run on GPUs).
 * **Coarse levels are replicated**: below the distributed levels the restricted residual is
   all-gathered and every rank runs the remaining coarse sub-cycle redundantly with the
   single-GPU driver; each rank keeps its slab of the correction.
 
-Multicolour order only (``order='color'``); GCROT(m,k) is not distributed.
+Multicolour order only (``order='color'``).
 
 The index arithmetic (:class:`SlabPartition`, :func:`exchange_plan`,
 :func:`gather_plan`, :func:`hierarchy_plan`) is pure Python and is tested on CPU with two
@@ -1092,8 +1094,8 @@ class DistributedMultigrid:
             sslsolver = False if sslsolver is True else sslsolver
             semicoarsening = False if semicoarsening is True else semicoarsening
             linerelaxation = False if linerelaxation is True else linerelaxation
-        if sslsolver not in (False, True, 'bicgstab', 'cgs'):
-            raise ValueError("distributed Krylov wrappers: 'bicgstab' (True) and 'cgs'. "
+        if sslsolver not in (False, True, 'bicgstab', 'cgs', 'gcrotmk'):
+            raise ValueError("distributed Krylov wrappers: 'bicgstab' (True), 'cgs' and 'gcrotmk'. "
                              f"Provided: {sslsolver!r}.")
         kwargs.pop('return_info', None)
         var = solver.MGParameters(verb=verb, sslsolver=sslsolver, semicoarsening=semicoarsening,

@@ -974,6 +974,8 @@ def _krylov(lv, s, e, var, ops=None):
             i = _bicgstab(ops, s, e, var, record)
         elif var.sslsolver == 'cgs':
             i = _cgs(ops, s, e, var, record)
+        elif lv is None or os.environ.get('EMG3D_B200_GCROT', 'host') == 'device':
+            i = _gcrotmk(ops, s, e, var, record)
         else:
             i = _scipy_krylov(lv, s, e, var, record)
     except _ConvergenceError:
@@ -1129,9 +1131,144 @@ def _cgs(ops, b, x, var, callback):
     return var.ssl_maxit
 
 
+def _gcrotmk(ops, b, x, var, callback, m=20, k=None):
+    """Flexible GCROT(m,k) on the device(s), right-preconditioned by multigrid.
+
+    The outer iteration, the inner FGMRES/Arnoldi process with its projection against the
+    carried ``C`` vectors, the 'oldest' truncation, the stopping rule (true residual recomputed
+    before convergence is declared) and the callback at the start of every outer iteration are
+    those of ``scipy.sparse.linalg.gcrotmk`` (SciPy 1.18, ``_isolve/_gcrotmk.py``) as the
+    reference calls it at solver.py:763-765 (``m=20``, ``k=m``, no recycled ``CU``, ``rtol=tol``,
+    ``atol=1e-30``, ``maxiter=ssl_maxit``).  Vectors live on the device(s); only the small
+    Hessenberg problem (QR update, least squares) is solved on the host.  Returns SciPy's
+    ``info`` code (0 converged, else the number of outer iterations done).
+    """
+    from scipy.linalg import LinAlgError, lstsq, qr_insert
+    k = m if k is None else k
+    free = []                                 # work vectors are recycled between outer iterations
+
+    def new():
+        return free.pop() if free else ops.new()
+
+    def scal(a, v):                           # v *= a  (0 * b + a * v: no aliased operands)
+        ops.axpby(0.0, b, a, v)
+
+    def axpy(a, v, w):                        # w += a v
+        ops.axpby(a, v, 1.0, w)
+
+    b_norm = ops.norm(b)
+    if b_norm == 0:
+        x.copy_from(b)
+        return 0
+    dtype = np.dtype(complex) if isinstance(ops.dot(b, b), complex) else np.dtype(float)
+    beta_tol = max(1e-30, float(var.tol) * b_norm)
+    eps = np.finfo(float).eps
+
+    def true_residual(r):                     # r = b - A x
+        ops.matvec(x, r)
+        ops.axpby(1.0, b, -1.0, r)
+
+    r = new()
+    if ops.norm(x) > 0:
+        true_residual(r)
+    else:
+        r.copy_from(b)
+
+    def fgmres(v0, mm, atol, cs):
+        """L A Z = C B + V H with H kept as Q R; returns Q, R, B, vs, zs, y."""
+        vs, zs = [v0], []
+        B = np.zeros((len(cs), mm), dtype=dtype)
+        Q, R = np.ones((1, 1), dtype=dtype), np.zeros((1, 0), dtype=dtype)
+        breakdown = False
+        for j in range(mm):
+            z, w = new(), new()
+            ops.psolve(vs[-1], z, var)
+            ops.matvec(z, w)
+            w_norm = ops.norm(w)
+            for i, c in enumerate(cs):        # (1 - C C^H) A z
+                B[i, j] = alpha = ops.dot(c, w)
+                axpy(-alpha, c, w)
+            hcur = np.zeros(j + 2, dtype=dtype)
+            for i, v in enumerate(vs):        # modified Gram-Schmidt against V
+                hcur[i] = alpha = ops.dot(v, w)
+                axpy(-alpha, v, w)
+            h_last = ops.norm(w)
+            hcur[j + 1] = h_last
+            with np.errstate(over='ignore', divide='ignore'):
+                alpha = np.float64(1.0) / np.float64(h_last)
+            if np.isfinite(alpha):
+                scal(float(alpha), w)
+            if not (h_last > eps * w_norm):   # w in the span of the previous vectors, or nan
+                breakdown = True
+            vs.append(w)
+            zs.append(z)
+            Q2 = np.zeros((j + 2, j + 2), dtype=dtype, order='F')
+            Q2[:j + 1, :j + 1] = Q
+            Q2[j + 1, j + 1] = 1
+            R2 = np.zeros((j + 2, j), dtype=dtype, order='F')
+            R2[:j + 1, :] = R
+            Q, R = qr_insert(Q2, R2, hcur, j, which='col', overwrite_qru=True, check_finite=False)
+            if abs(Q[0, -1]) < atol or breakdown:
+                break
+        if not np.isfinite(R[j, j]):
+            free.extend(vs + zs)
+            raise LinAlgError()
+        y = lstsq(R[:j + 1, :j + 1], Q[0, :j + 1].conj())[0]
+        return Q, R, B[:, :j + 1], vs, zs, y
+
+    CU = []
+    for j_outer in range(var.ssl_maxit):
+        callback(x)
+        beta = ops.norm(r)
+        if beta <= beta_tol and (j_outer > 0 or CU):
+            true_residual(r)                  # recomputed: the recurrence residual drifts
+            beta = ops.norm(r)
+        if beta <= beta_tol:
+            return 0
+        ml = m + max(k - len(CU), 0)
+        v0 = new()
+        v0.copy_from(r)
+        scal(1.0 / beta, v0)
+        try:
+            Q, R, B, vs, zs, y = fgmres(v0, ml, beta_tol / beta, [c for c, _ in CU])
+        except LinAlgError:                   # over/underflow, nan from the operator
+            return j_outer + 1
+        y = y * beta
+        # new outer pair:  ux = (Z - U B) y,  cx = V H y = A ux  (zs[0], vs[0] are reused)
+        ux = zs[0]
+        scal(y[0], ux)
+        for z, yc in zip(zs[1:], y[1:]):
+            axpy(yc, z, ux)
+        for (_, u), byc in zip(CU, B.dot(y)):
+            axpy(-byc, u, ux)
+        with np.errstate(invalid='ignore'):
+            hy = Q.dot(R.dot(y))
+        cx = vs[0]
+        scal(hy[0], cx)
+        for v, hyc in zip(vs[1:], hy[1:]):
+            axpy(hyc, v, cx)
+        free.extend(vs[1:] + zs[1:])
+        with np.errstate(over='ignore', divide='ignore'):
+            alpha = np.float64(1.0) / np.float64(ops.norm(cx))
+        if not np.isfinite(alpha):            # cannot update: skip this pair
+            free.extend((cx, ux))
+            continue
+        scal(float(alpha), cx)
+        scal(float(alpha), ux)
+        gamma = ops.dot(cx, r)
+        axpy(-gamma, cx, r)
+        axpy(gamma, ux, x)
+        while len(CU) >= k and CU:            # truncate='oldest'
+            free.extend(CU.pop(0))
+        CU.append((cx, ux))
+    return var.ssl_maxit
+
+
 def _scipy_krylov(lv, s, e, var, callback):
-    """GCROT(m,k): SciPy drives, the GPU applies A and the preconditioner (full vectors cross
-    PCIe per application; BiCGSTAB and CGS are device-resident, see above)."""
+    """GCROT(m,k) driven by SciPy on the host: the GPU applies A and the preconditioner, full
+    vectors cross PCIe per application.  The single-GPU default for ``sslsolver='gcrotmk'``
+    (validated on the B200); ``EMG3D_B200_GCROT=device`` selects the device-resident
+    :func:`_gcrotmk` instead, which is also what a multi-GPU solve runs."""
     lib = _lib.load()
     n = lv.n_edges
     d_in, d_out = lv.new_field(False), lv.new_field(False)
