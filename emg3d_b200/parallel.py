@@ -28,8 +28,8 @@ conventions as on one GPU.
   send/recv groups as the fallback.
 * **Norms and dot products** are sums over owned edges, all-reduced with NCCL; BiCGSTAB, CGS
   and GCROT(m,k) run around the distributed cycle through the backend-neutral drivers of
-  solver.py (GCROT: driver checked against SciPy on a NumPy backend, tests/test_krylov_cpu.py;
-  not yet run on GPUs).
+  solver.py (GCROT: driver checked against SciPy and reference solves on CPU backends,
+  tests/test_krylov_cpu.py, and on one B200; not yet run on several GPUs).
 * **Coarse levels are replicated**: below the distributed levels the restricted residual is
   all-gathered and every rank runs the remaining coarse sub-cycle redundantly with the
   single-GPU driver; each rank keeps its slab of the correction.

@@ -974,7 +974,7 @@ def _krylov(lv, s, e, var, ops=None):
             i = _bicgstab(ops, s, e, var, record)
         elif var.sslsolver == 'cgs':
             i = _cgs(ops, s, e, var, record)
-        elif lv is None or os.environ.get('EMG3D_B200_GCROT', 'host') == 'device':
+        elif lv is None or os.environ.get('EMG3D_B200_GCROT', 'device') != 'host':
             i = _gcrotmk(ops, s, e, var, record)
         else:
             i = _scipy_krylov(lv, s, e, var, record)
@@ -1266,9 +1266,9 @@ def _gcrotmk(ops, b, x, var, callback, m=20, k=None):
 
 def _scipy_krylov(lv, s, e, var, callback):
     """GCROT(m,k) driven by SciPy on the host: the GPU applies A and the preconditioner, full
-    vectors cross PCIe per application.  The single-GPU default for ``sslsolver='gcrotmk'``
-    (validated on the B200); ``EMG3D_B200_GCROT=device`` selects the device-resident
-    :func:`_gcrotmk` instead, which is also what a multi-GPU solve runs."""
+    vectors cross PCIe per application.  Kept as a cross-check of the device-resident
+    :func:`_gcrotmk` (the default; also what a multi-GPU solve runs): ``EMG3D_B200_GCROT=host``
+    selects it (tests/test_gpu_solver_gcrot.py runs both against the reference)."""
     lib = _lib.load()
     n = lv.n_edges
     d_in, d_out = lv.new_field(False), lv.new_field(False)

@@ -254,7 +254,7 @@ def test_efield_argument_and_return_conventions(eb, golden, capsys):
 def test_krylov_variants_and_failures(eb, golden, capsys):
     c = solve_case(golden('solves'), 'res_bic_')
     grid, model, sfield = build(eb, c)
-    # cgs and gcrotmk run through SciPy with the GPU as matvec / preconditioner
+    # cgs and gcrotmk: device-resident restatements of SciPy's solvers
     e, info = eb.solve(model, sfield, plain=True, sslsolver='cgs', return_info=True, order='lex')
     assert info['exit'] == 0 and (info['it_ssl'], info['it_mg']) == (3, 6)   # as the reference
     assert rel_err(e.field, c['efield']) < 1e-4
