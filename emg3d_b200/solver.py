@@ -11,7 +11,8 @@ reference (``emg3d/solver.py``): :func:`solve`, :func:`solve_source`,
 * the grid hierarchy (coarse grids, summed coefficients, restriction weights,
   interpolation tables, line factorisations) is built once per solve and cached,
   where the reference rebuilds it at every visit (solver.py:888-931, 975-1007);
-* BiCGSTAB runs on the device with the recurrence of SciPy's implementation;
+* BiCGSTAB, CGS and GCROT(m,k) run on the device(s) with the recurrences of SciPy's
+  implementations (only GCROT's small Hessenberg problem is solved on the host);
 * ``order='color'`` (default) smooths in multicolour order, ``order='lex'``
   reproduces the reference's lexicographic Gauss-Seidel sweeps.
 
