@@ -28,8 +28,8 @@ conventions as on one GPU.
   send/recv groups as the fallback.
 * **Norms and dot products** are sums over owned edges, all-reduced with NCCL; BiCGSTAB, CGS
   and GCROT(m,k) run around the distributed cycle through the backend-neutral drivers of
-  solver.py (GCROT: driver checked against SciPy and reference solves on CPU backends,
-  tests/test_krylov_cpu.py, and on one B200; not yet run on several GPUs).
+  solver.py (tools/dist_check.py, tools/dist_gcrot_check.py: same iteration counts and fields
+  as on one GPU).
 * **Coarse levels are replicated**: below the distributed levels the restricted residual is
   all-gathered and every rank runs the remaining coarse sub-cycle redundantly with the
   single-GPU driver; each rank keeps its slab of the correction.
