@@ -419,7 +419,6 @@ class _DLevel:
         # sweep.  The deeper halo planes below only exist to keep the local grids
         # nested under coarsening; no kernel result ever depends on them.
         lo, hi = part.local(level, rank)
-        p0, _ = part.owned(level, rank)
         p0, p1 = part.owned(level, rank)
         z0 = 0 if rank == 0 else p0 - 1 - lo
         self.win = lv.handle if z0 == 0 else lv.handle.window(z0, hi - lo - z0)
@@ -594,7 +593,6 @@ class DistributedMultigrid:
         self.s = lv0.new_field()
         self.e = lv0.new_field()
         self.upload_source(sfield)
-        import os
         self.p2p_push = os.environ.get('EMG3D_B200_P2P_PUSH', '1') != '0'
         self._sums = _lib.DeviceArray(8, np.float64)
         self._krylov_pool = []
