@@ -118,6 +118,8 @@ _SIGNATURES = {
                                          c_int, c_void_p]),
     'emg3d_b200_host_gauss_seidel': (c_int, [c_int] * 6 + [c_void_p] * 13 + [c_int]),
     'emg3d_b200_host_solve': (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    'emg3d_b200_host_restrict': (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     'emg3d_b200_comm_unique_id': (c_int, [c_void_p]),
     'emg3d_b200_comm_init': (c_int, [c_void_p, c_int, c_int]),
     'emg3d_b200_comm_size': (c_int, [POINTER(c_int), POINTER(c_int)]),

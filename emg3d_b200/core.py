@@ -168,31 +168,35 @@ def interpolation_table(nodes, cnodes):
 
 
 def restrict(crx, cry, crz, rx, ry, rz, wx, wy, wz, sc_dir):
-    """Restrict the fine residual to the coarse grid (core.py:1620-2001)."""
-    from emg3d_b200 import solver   # local import: solver imports this module
+    """Restrict the fine residual to the coarse grid (core.py:1620-2001), host arrays in and out
+    through ``emg3d_b200_host_restrict``."""
     dt = np.dtype(rx.dtype)
     r = [_farr(v, dt, n) for v, n in ((rx, 'rx'), (ry, 'ry'), (rz, 'rz'))]
     cr = [_farr(v, dt, n, True) for v, n in ((crx, 'crx'), (cry, 'cry'), (crz, 'crz'))]
     fshape = (r[1].shape[0] - 1, r[0].shape[1] - 1, r[0].shape[2] - 1)
+    if int(sc_dir) not in SC_FLAGS:
+        raise ValueError(f"sc_dir must be 0 .. 6; provided: {sc_dir!r}.")
     cflag = SC_FLAGS[int(sc_dir)]
     cshape = tuple(n // 2 if f else n for n, f in zip(fshape, cflag))
-    fine = _lib.LevelHandle([np.ones(n) for n in fshape])
-    coarse = _lib.LevelHandle([np.ones(n) for n in cshape])
-    weights = [None] * 9
+    want = ((cshape[0], cshape[1] + 1, cshape[2] + 1), (cshape[0] + 1, cshape[1], cshape[2] + 1),
+            (cshape[0] + 1, cshape[1] + 1, cshape[2]))
+    for v, shp, name in zip(cr, want, ('crx', 'cry', 'crz')):
+        if v.shape != shp:
+            raise ValueError(f"{name}: shape {v.shape}, expected {shp} for sc_dir={sc_dir}.")
+    keep, wp = [], (_lib.c_void_p * 9)()
     for a, w in enumerate((wx, wy, wz)):
-        if cflag[a]:
-            weights[3 * a:3 * a + 3] = [np.asarray(v, dtype=np.float64) for v in w]
-    dummy = [(np.zeros(n + 1, np.int32), np.zeros(n + 1)) for n in fshape]
-    coarse.link(fine, cflag, weights, [d[0] for d in dummy], [d[1] for d in dummy])
-    solver._set_dtype(coarse, dt)
-    d_r = _lib.DeviceArray.from_host(np.concatenate([v.ravel('F') for v in r]))
-    d_c = _lib.DeviceArray(sum(v.size for v in cr), dt)
-    _lib.check(_lib.load().emg3d_b200_restrict(coarse.ptr, d_r.ptr, d_c.ptr))
-    out = d_c.download()
-    i0 = 0
-    for v in cr:
-        v[...] = out[i0:i0 + v.size].reshape(v.shape, order='F')
-        i0 += v.size
+        for k in range(3):
+            if cflag[a]:
+                arr = np.ascontiguousarray(w[k], dtype=np.float64)
+                if arr.size != cshape[a] + 1:
+                    raise ValueError(f"restriction weights of axis {a}: length {arr.size}, "
+                                     f"expected {cshape[a] + 1}.")
+                keep.append(arr)
+                wp[3 * a + k] = arr.ctypes.data
+            else:
+                wp[3 * a + k] = None
+    _lib.check(_lib.load().emg3d_b200_host_restrict(
+        int(dt.kind == 'c'), *fshape, int(sc_dir), *[_p(v) for v in cr], *[_p(v) for v in r], wp))
 
 
 def blocks_to_amat(amat, bvec, middle, left, rhs, im, nc):

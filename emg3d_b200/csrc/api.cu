@@ -1175,6 +1175,51 @@ int emg3d_b200_host_solve(int is_cplx, int n, void* amat, void* bvec) {
     return emg3d_b200_d2h(bvec, b.p, (size_t)n * el);
 }
 
+// core.restrict (core.py:1620-1621; call site solver.py:937-938) on host arrays: (nx, ny, nz) are the
+// FINE cell counts, weights[3 a + {0, 1, 2}] = wl, w0, wr of axis a (core.restrict_weights), NULL where
+// sc_dir leaves the axis alone.  Two bare levels (unit widths: the restriction only uses the weights)
+// are linked for the call.
+int emg3d_b200_host_restrict(int is_cplx, int nx, int ny, int nz, int sc_dir, void* crx, void* cry, void* crz,
+                             const void* rx, const void* ry, const void* rz, const double* const* weights) {
+    NEED_INIT();
+    static const int flags[7][3] = {{1, 1, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (sc_dir < 0 || sc_dir > 6) return fail_msg("host_restrict: sc_dir must be 0 .. 6");
+    if (!weights) return fail_msg("host_restrict: weights missing");
+    const int* cf = flags[sc_dir];
+    const int nf[3] = {nx, ny, nz};
+    int nc[3], nmax = 1;
+    for (int a = 0; a < 3; ++a) {
+        if (nf[a] < 1) return fail_msg("host_restrict: need at least 1 cell per axis");
+        if (cf[a] && (nf[a] % 2 || nf[a] < 2))
+            return fail_msg("host_restrict: a coarsened axis needs an even number of cells");
+        if (cf[a] && !(weights[3 * a] && weights[3 * a + 1] && weights[3 * a + 2]))
+            return fail_msg("host_restrict: weights of a coarsened axis missing");
+        nc[a] = cf[a] ? nf[a] / 2 : nf[a];
+        if (nf[a] > nmax) nmax = nf[a];
+    }
+    struct Owned {
+        emg3d_b200_level* p = nullptr;
+        ~Owned() { emg3d_b200_level_destroy(p); }
+    } fine, coarse;                                       // (coarse is destroyed first)
+    std::vector<double> ones((size_t)nmax, 1.0), frac0((size_t)nmax + 1, 0.0);
+    std::vector<int> lo0((size_t)nmax + 1, 0);            // prolongation tables: unused here
+    int rc;
+    if ((rc = emg3d_b200_level_create(&fine.p, nx, ny, nz, ones.data(), ones.data(), ones.data()))) return rc;
+    if ((rc = emg3d_b200_level_create(&coarse.p, nc[0], nc[1], nc[2], ones.data(), ones.data(), ones.data())))
+        return rc;
+    const int* lo[3] = {lo0.data(), lo0.data(), lo0.data()};
+    const double* fr[3] = {frac0.data(), frac0.data(), frac0.data()};
+    if ((rc = emg3d_b200_level_link(coarse.p, fine.p, cf, weights, lo, fr))) return rc;
+    if ((rc = emg3d_b200_level_set_model(coarse.p, is_cplx, nullptr, nullptr, nullptr, nullptr))) return rc;
+    const size_t el = is_cplx ? sizeof(cplx) : sizeof(double);
+    DevBuf r, c;
+    if (r.alloc((size_t)n_edges(fine.p->d) * el) || c.alloc((size_t)n_edges(coarse.p->d) * el))
+        return fail_msg("host_restrict: out of device memory");
+    if ((rc = field_io(true, is_cplx, fine.p->d, r.p, (void*)rx, (void*)ry, (void*)rz))) return rc;
+    if ((rc = emg3d_b200_restrict(coarse.p, r.p, c.p))) return rc;
+    return field_io(false, is_cplx, coarse.p->d, c.p, crx, cry, crz);
+}
+
 int emg3d_b200_host_gauss_seidel(int is_cplx, int ldir, int order, int nx, int ny, int nz, void* ex, void* ey,
                                  void* ez, const void* sx, const void* sy, const void* sz,
                                  const void* eta_x, const void* eta_y, const void* eta_z,

@@ -266,6 +266,14 @@ int emg3d_b200_host_gauss_seidel(int cplx, int ldir, int order, int nx, int ny, 
                                  const void* sz, const void* eta_x, const void* eta_y,
                                  const void* eta_z, const double* zeta, const double* hx,
                                  const double* hy, const double* hz, int nu);
+/* core.restrict(crx, cry, crz, rx, ry, rz, wx, wy, wz, sc_dir) (core.py:1620-1621; call site
+ * solver.py:937-938) on host arrays.  (nx, ny, nz): FINE cell counts; the coarse arrays have the
+ * shapes sc_dir implies (0: x, y, z halved; 1: y, z; 2: x, z; 3: x, y; 4: x; 5: y; 6: z;
+ * solver.py:891-897).  weights[3 a + {0, 1, 2}] = (wl, w0, wr) of axis a as returned by
+ * core.restrict_weights, length n_coarse_nodes(a); NULL for an axis that is not coarsened. */
+int emg3d_b200_host_restrict(int cplx, int nx, int ny, int nz, int sc_dir, void* crx, void* cry,
+                             void* crz, const void* rx, const void* ry, const void* rz,
+                             const double* const* weights);
 
 /* ---- interpolation on either side of a solve; device pointers ---------
  *

@@ -292,6 +292,12 @@ def test_restrict_golden(core, golden):
             w = [tuple(gt[q + f'w{a}']) for a in 'xyz']
             core.restrict(*split_field(cshape, cs), *split_field(shape, gt[p + 'r'].copy()), *w, sc)
             assert rel_err(cs, gt[q + 'cs']) < 1e-13, (k, sc)
+    # argument checks of the host-array entry (coarse arrays of the wrong shape, bad sc_dir)
+    fine = split_field(shape, gt[p + 'r'].copy())
+    with pytest.raises(ValueError, match='expected'):
+        core.restrict(*split_field(shape, np.zeros_like(gt[p + 'r'])), *fine, *w, 0)
+    with pytest.raises(ValueError, match='sc_dir'):
+        core.restrict(*split_field(cshape, cs), *fine, *w, 7)
 
 
 def test_solver_wrappers_golden(golden):
