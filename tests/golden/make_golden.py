@@ -22,6 +22,7 @@ not on the hot path); ``_refstubs/`` provides two-line stand-ins.  Outputs:
                   grid-to-grid interpolation of fields and models
 
     gcrot.npz     GCROT(m,k) solves with the source scaled to norm one (see make_gcrot)
+    cgs.npz       CGS solves
 
 The fixtures travel to the GPU box; the reference does not.
 """
@@ -422,11 +423,31 @@ def make_gcrot():
     np.savez_compressed(os.path.join(HERE, 'gcrot.npz'), **out)
 
 
+def make_cgs():
+    """CGS solves (the third ``sslsolver`` of the reference, solver.py:763-765)."""
+    out = {}
+    reg = emg3d.load('/root/reference/tests/data/regression.npz', verb=0)
+    dat = reg['res']
+    model = emg3d.Model(**dat['input_model'])
+    src = dat['input_source']
+    sfield = emg3d.get_source_field(**src)
+    _store_solve(out, 'res_cgs_', model.grid, model, sfield,
+                 dict(plain=True, sslsolver='cgs'), src['frequency'])
+    cfg = recipes.config('config2', 32)
+    grid = emg3d.TensorMesh(cfg['h'], cfg['origin'])
+    model = emg3d.Model(grid, **cfg['model'])
+    sfield = emg3d.get_source_field(grid, cfg['source'], cfg['frequency'])
+    _store_solve(out, 'config2_cgs_', grid, model, sfield,
+                 dict(sslsolver='cgs', semicoarsening=True, linerelaxation=True, cycle='V'),
+                 cfg['frequency'])
+    np.savez_compressed(os.path.join(HERE, 'cgs.npz'), **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot']
+    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs']
     for w in which:
         globals()['make_' + w]()
-    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot'):
+    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs'):
         fn = os.path.join(HERE, f + '.npz')
         if os.path.exists(fn):
             print(f, os.path.getsize(fn) // 1024, 'KiB')

@@ -1,8 +1,9 @@
-"""GCROT(m,k) around the multigrid cycle against the reference (tests/golden/gcrot.npz).
+"""GCROT(m,k) and CGS around the multigrid cycle against the reference (tests/golden/gcrot.npz,
+cgs.npz).
 
-Two drivers of the same algorithm: SciPy on the host with the GPU as operator and preconditioner
-(the default) and the device-resident restatement (``EMG3D_B200_GCROT=device``; its driver code is
-pinned against SciPy on a NumPy backend in tests/test_krylov_cpu.py).  ``order='lex'`` reproduces
+Two GCROT drivers of the same algorithm: the device-resident restatement (the default; its driver
+code is pinned against SciPy on a NumPy backend in tests/test_krylov_cpu.py) and SciPy on the host
+with the GPU as operator and preconditioner (``EMG3D_B200_GCROT=host``).  ``order='lex'`` reproduces
 the reference's Gauss-Seidel sweeps, so both must give the reference's iteration counts, exit
 message and field:
 
@@ -15,8 +16,8 @@ The reference only converges with GCROT when the source has a norm around one (i
 measures divergence against the norm of the original source, GCROT hands it unit vectors); the
 as-is 'res' source reports DIVERGED in both, which test_gpu_solver.py covers.
 
-This file sorts last among the gpu tests on purpose: the device-resident driver was written after
-the round's GPU budget was spent and runs on a B200 for the first time in the driver's own run.
+The GCROT cases ran on a B200 in round 2 (6 passed); this file sorts last among the gpu tests on
+purpose: the CGS cases were added after the round's GPU budget was spent.
 """
 import numpy as np
 import pytest
@@ -40,6 +41,23 @@ def eb():
 def test_gcrotmk_matches_reference(eb, golden, prefix, driver, monkeypatch, capsys):
     monkeypatch.setenv('EMG3D_B200_GCROT', driver)
     c = solve_case(golden('gcrot'), prefix)
+    grid = eb.TensorMesh([c['hx'], c['hy'], c['hz']], c['origin'])
+    model = eb.Model(grid, **c['model'])
+    sfield = eb.Field(grid, c['sfield'].copy(), frequency=c['frequency'])
+    efield, info = eb.solve(model, sfield, return_info=True, order='lex', **c['kwargs'])
+    capsys.readouterr()
+    assert info['exit_message'] == c['exit_message']
+    assert (info['it_ssl'], info['it_mg']) == (c['it_ssl'], c['it_mg'])
+    assert np.abs(info['error_at_cycle'] - c['error_at_cycle']).max() <= 1e-8 * c['ref_error']
+    assert rel_err(efield.field, c['efield']) <= 1e-8
+
+
+@pytest.mark.parametrize('prefix', ['res_cgs_', 'config2_cgs_'])
+def test_cgs_matches_reference(eb, golden, prefix, capsys):
+    """Device-resident CGS against CGS solves of the reference (tests/golden/cgs.npz); the same
+    driver around the oracle's multigrid reproduces them to 2e-14 (tests/test_krylov_cpu.py).
+    (Added after the round's GPU budget was spent: first run on a B200 is the driver's.)"""
+    c = solve_case(golden('cgs'), prefix)
     grid = eb.TensorMesh([c['hx'], c['hy'], c['hz']], c['origin'])
     model = eb.Model(grid, **c['model'])
     sfield = eb.Field(grid, c['sfield'].copy(), frequency=c['frequency'])

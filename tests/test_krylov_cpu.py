@@ -230,7 +230,7 @@ def krylov_over_oracle(c):
 
 @pytest.mark.parametrize('file,prefix', [
     ('gcrot', 'res_gcrot_'), ('gcrot', 'res_gcrot_noprec_'), ('gcrot', 'config2_gcrot_'),
-    ('solves', 'res_bic_'), ('solves', 'lap_bic_')])
+    ('solves', 'res_bic_'), ('solves', 'lap_bic_'), ('cgs', 'res_cgs_'), ('cgs', 'config2_cgs_')])
 def test_driver_with_multigrid_matches_reference(golden, file, prefix):
     from conftest import rel_err
     from helpers import solve_case
