@@ -247,25 +247,111 @@ class SourceField(Field):
         return Field(self.grid, self._dense.copy(), self._frequency)
 
 
-def get_source_field(grid, source, frequency, strength=1.0, length=1.0):
-    """Source term ``-s mu_0 J_s`` of an electric dipole on the edges.
+def _square_loop(center, azimuth, elevation, area):
+    """Closed square loop (5 points) of ``area`` m^2 perpendicular to a dipole: what stands in for
+    a magnetic dipole (emg3d/electrodes.py:796-822; the loop's area takes the dipole's length)."""
+    half_diag = np.sqrt(area / 2)
+    hor = _rotation(azimuth + 90.0, 0.0) * half_diag
+    ver = _rotation(azimuth, elevation + 90.0) * half_diag
+    return np.asarray(center, dtype=float) + np.stack([hor, ver, -hor, -ver, hor])
 
-    Mirrors the electric-dipole branch of emg3d.fields.get_source_field
-    (emg3d/fields.py:386-519).  ``source`` is ``(x, y, z, azimuth, elevation)``
-    (a dipole of ``length`` metres centred there; emg3d/electrodes.py:752-755),
-    ``(x0, x1, y0, y1, z0, z1)``, or an array of shape ``(n, 3)`` of wire
-    points.  Magnetic sources and point sources are outside the hot path.
+
+def _dipole_angles(points):
+    """(azimuth, elevation, length) of an electrode pair (emg3d/electrodes.py:758-793)."""
+    dx, dy, dz = points[1] - points[0]
+    return (np.degrees(np.arctan2(dy, dx)), np.degrees(np.arctan2(dz, np.hypot(dx, dy))),
+            float(np.linalg.norm([dx, dy, dz])))
+
+
+def _point_vector(grid, coordinates):
+    """Point dipole ``(x, y, z, azimuth, elevation)`` by the adjoint of trilinear interpolation
+    (emg3d/fields.py:662-745): per component the eight edges around the point get the trilinear
+    weights (in the last cell of an axis: weight one), times the direction cosine.  Returns
+    ``{flat index: value}``."""
+    coo = np.asarray(coordinates, dtype=float)
+    nodes = (grid.nodes_x, grid.nodes_y, grid.nodes_z)
+    if any(coo[a] < nodes[a][0] or coo[a] > nodes[a][-1] for a in range(3)):
+        raise ValueError(f"Provided source outside grid: {coordinates}.")
+    centers = (grid.cell_centers_x, grid.cell_centers_y, grid.cell_centers_z)
+    shapes = (grid.shape_edges_x, grid.shape_edges_y, grid.shape_edges_z)
+    offs = (0, grid.n_edges_x, grid.n_edges_x + grid.n_edges_y)
+    srcdir = _rotation(coo[3], coo[4])
+    out = {}
+    for c in range(3):
+        axes = []                                            # per axis: [(index, weight), (index1, weight1)]
+        for a in range(3):
+            cc = centers[a] if a == c else nodes[a]
+            n = shapes[c][a]
+            i0 = max(0, int(np.searchsorted(cc, coo[a], side='right')) - 1)
+            if i0 == n - 1:
+                axes.append(((i0, 1.0), (i0, 1.0)))
+            else:
+                r = (coo[a] - cc[i0]) / (cc[i0 + 1] - cc[i0])
+                axes.append(((i0, 1.0 - r), (i0 + 1, r)))
+        for iz, wz in axes[2]:
+            for iy, wy in axes[1]:
+                for ix, wx in axes[0]:
+                    flat = offs[c] + ix + shapes[c][0] * (iy + shapes[c][1] * iz)
+                    out[flat] = wx * wy * wz * srcdir[c]     # (assigned, not added: as the reference)
+    return out
+
+
+def get_source_field(grid, source, frequency, strength=1.0, length=1.0, electric=True):
+    """Source term ``-s mu_0 J_s`` on the edges (emg3d/fields.py:386-519).
+
+    ``source``: ``(x, y, z, azimuth, elevation)`` (a dipole of ``length`` metres centred there;
+    emg3d/electrodes.py:752-755), ``(x0, x1, y0, y1, z0, z1)`` or ``[[x0, y0, z0], [x1, y1, z1]]``
+    (a finite dipole), an array of shape ``(n, 3)``, n > 2 (a wire) -- or a source object of the
+    reference (``emg3d.TxElectricDipole``, ``TxMagneticDipole``, ``TxElectricWire``,
+    ``TxElectricPoint``: anything with ``points`` / ``coordinates`` and ``strength``).
+    ``electric=False``: a magnetic dipole, represented like in the reference by a square loop of
+    electric wire perpendicular to it whose area is the dipole's length.  Dipoles and wires are
+    distributed onto the edges by their length fraction per cell, point sources by the adjoint of
+    trilinear interpolation.  ``frequency=None`` returns the real, frequency-independent vector.
+    Magnetic POINT sources need ``discretize`` in the reference and are outside this path.
     Returns a :class:`SourceField`: same values as the reference's dense field, held sparsely.
     """
-    src = np.asarray(source, dtype=float)
-    if src.size == 5:
-        half = _rotation(src[3], src[4]) * length / 2
-        pts = np.array([src[:3] - half, src[:3] + half])
-    elif src.size == 6 and src.ndim == 1:
-        pts = np.array([[src[0], src[2], src[4]], [src[1], src[3], src[5]]])
+    point = None
+    if hasattr(source, 'points') and hasattr(source, 'strength'):      # a Tx* object
+        kind = type(source).__name__
+        strength = source.strength
+        if kind == 'TxMagneticPoint':
+            raise NotImplementedError("magnetic point sources (they need `discretize` in the "
+                                      "reference) are outside this path")
+        if kind == 'TxElectricPoint':
+            point = np.asarray(source.coordinates, dtype=float)
+        pts = np.asarray(source.points, dtype=float).reshape(-1, 3)
     else:
-        pts = src.reshape(-1, 3)
-    total = {}
+        src = np.asarray(source, dtype=float).squeeze()
+        if src.size == 5:
+            if electric:
+                half = _rotation(src[3], src[4]) * length / 2
+                pts = np.array([src[:3] - half, src[:3] + half])
+            else:
+                pts = _square_loop(src[:3], src[3], src[4], length)
+        elif src.size == 6:
+            pts = src.reshape((2, 3), order='F') if src.ndim == 1 else src.reshape(2, 3)
+            if np.allclose(pts[0], pts[1]):
+                raise ValueError(
+                    "The two electrodes are identical, use the format "
+                    "(x, y, z, azimuth, elevation) instead. "
+                    f"Provided coordinates: {src}.")
+            if not electric:
+                azimuth, elevation, dlen = _dipole_angles(pts)
+                pts = _square_loop(pts.sum(0) / 2, azimuth, elevation, dlen)
+        elif src.size > 6 and src.size % 3 == 0:
+            pts = src.reshape(-1, 3)
+        else:
+            raise ValueError(
+                "Coordinates are wrong defined. They must be defined either "
+                "as a point, (x, y, z, azimuth, elevation), or as two points, "
+                "(x1, x2, y1, y2, z1, z2) or [[x1, y1, z1], [x2, y2, z2]]. "
+                f"Provided coordinates: {src}.")
+    if point is not None:
+        total = _point_vector(grid, point)
+        pts = pts[:0]
+    else:
+        total = {}
     for a, b in zip(pts[:-1], pts[1:]):
         for flat, v in _segment_vector(grid, a, b).items():
             total[flat] = total.get(flat, 0.0) + v

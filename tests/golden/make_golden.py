@@ -23,6 +23,7 @@ not on the hot path); ``_refstubs/`` provides two-line stand-ins.  Outputs:
 
     gcrot.npz     GCROT(m,k) solves with the source scaled to norm one (see make_gcrot)
     cgs.npz       CGS solves
+    sources.npz   source assembly: magnetic dipoles, wires, electric points, source objects
 
 The fixtures travel to the GPU box; the reference does not.
 """
@@ -423,6 +424,61 @@ def make_gcrot():
     np.savez_compressed(os.path.join(HERE, 'gcrot.npz'), **out)
 
 
+def make_sources():
+    """Source assembly beyond electric dipoles (emg3d/fields.py:386-519): magnetic dipoles (square
+    loops), wires, electric point sources, strengths, the frequency-independent vector."""
+    out = {}
+    hx = recipes.widths(8, 1.2, 30.)
+    hy = recipes.widths(6, 1.1, 40.)
+    hz = recipes.widths(10, 1.3, 20.)
+    origin = (-hx.sum() / 2, -hy.sum() / 2 + 3., -hz.sum() / 2 - 7.)
+    grid = emg3d.TensorMesh([hx, hy, hz], origin)
+    out['hx'], out['hy'], out['hz'], out['origin'] = hx, hy, hz, np.array(origin)
+    wire = np.array([[-40., -30., -50.], [-10., 12., -20.], [25., 12., 33.], [60., -44., 33.]])
+    top = (grid.nodes_x[-1], grid.nodes_y[-1], grid.nodes_z[-1])
+    cases = [
+        # name, source as passed to the reference, kwargs
+        ('mag5', (12.3, -20.1, 5.5, 30., 20.), dict(electric=False, strength=2.5, length=30.)),
+        ('mag5z', (0., 0., 0., 0., 90.), dict(electric=False)),
+        ('mag6', (-40., 40., -10., 10., -20., 30.), dict(electric=False, strength=0.5)),
+        ('mag23', np.array([[-20., 5., -33.], [10., 5., -33.]]), dict(electric=False)),
+        ('dip23', np.array([[-20., 5., -33.], [10., 25., -3.]]), dict(strength=3.0)),
+        ('wire', wire, dict(strength=1.5)),
+        ('cstr', (12.3, -20.1, 5.5, 30., 20.), dict(strength=2 - 3j, length=12.)),
+    ]
+    for name, src, kw in cases:
+        out[f'{name}_source'] = np.asarray(src, dtype=float)
+        out[f'{name}_kwargs'] = json.dumps({k: ([v.real, v.imag] if isinstance(v, complex) else v)
+                                            for k, v in kw.items()})
+        for freq in (1.0, -2.5, None):
+            if freq is not None and freq < 0 and isinstance(kw.get('strength'), complex):
+                continue                                   # (complex strength: frequency domain only)
+            if freq is None and isinstance(kw.get('strength'), complex):
+                continue
+            sf = emg3d.get_source_field(grid, src, freq, **kw)
+            out[f'{name}_f{freq}'] = np.asarray(sf.field)
+    # source objects: points (trilinear adjoint), incl. the last cell / the grid corner
+    objs = [
+        ('pt', emg3d.TxElectricPoint((12.3, -20.1, 5.5, 30., 20.), strength=1.5)),
+        ('pt_node', emg3d.TxElectricPoint((grid.nodes_x[3], grid.nodes_y[2], grid.nodes_z[4], -70., 15.))),
+        ('pt_top', emg3d.TxElectricPoint((*top, 45., 45.), strength=2.0)),
+        ('pt_low', emg3d.TxElectricPoint((grid.nodes_x[0], grid.nodes_y[0], grid.nodes_z[0], 10., -30.))),
+        ('obj_wire', emg3d.TxElectricWire(wire, strength=4.0)),
+        ('obj_mag', emg3d.TxMagneticDipole((5., 6., -7., 20., -40.), strength=3.0, length=50.)),
+        ('obj_dip', emg3d.TxElectricDipole((-40., 40., -10., 10., -20., 30.), strength=0.25)),
+    ]
+    for name, obj in objs:
+        out[f'{name}_class'] = type(obj).__name__
+        out[f'{name}_points'] = np.asarray(obj.points, dtype=float)
+        out[f'{name}_coordinates'] = np.asarray(obj.coordinates, dtype=float)
+        out[f'{name}_strength'] = float(obj.strength)
+        for freq in (1.0, -2.5, None):
+            out[f'{name}_f{freq}'] = np.asarray(emg3d.get_source_field(grid, obj, freq).field)
+    out['cases'] = json.dumps([c[0] for c in cases])
+    out['objects'] = json.dumps([o[0] for o in objs])
+    np.savez_compressed(os.path.join(HERE, 'sources.npz'), **out)
+
+
 def make_cgs():
     """CGS solves (the third ``sslsolver`` of the reference, solver.py:763-765)."""
     out = {}
@@ -444,10 +500,10 @@ def make_cgs():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs']
+    which = sys.argv[1:] or ['kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs', 'sources']
     for w in which:
         globals()['make_' + w]()
-    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs'):
+    for f in ('kernels', 'transfer', 'solves', 'host', 'hfield', 'maps', 'gcrot', 'cgs', 'sources'):
         fn = os.path.join(HERE, f + '.npz')
         if os.path.exists(fn):
             print(f, os.path.getsize(fn) // 1024, 'KiB')

@@ -91,6 +91,58 @@ def test_source_field_matches_reference(golden):
             assert rel_err(sf.field, want) < 1e-12, (k, freq)
 
 
+def test_source_assembly_beyond_electric_dipoles(golden):
+    """Magnetic dipoles (square loops), finite dipoles, wires, complex strength, the frequency-
+    independent vector, electric point sources and source OBJECTS with the reference's attributes
+    (emg3d/fields.py:386-519, electrodes.py) against the reference's outputs."""
+    import json
+    import emg3d_b200 as eb
+    gs = golden('sources')
+    grid = eb.TensorMesh([gs['hx'], gs['hy'], gs['hz']], gs['origin'])
+
+    def check(sf, want, what):
+        assert sf.field.dtype == want.dtype, what
+        assert rel_err(sf.field, want) < 1e-12, what
+
+    for name in json.loads(str(gs['cases'])):
+        kw = json.loads(str(gs[f'{name}_kwargs']))
+        if isinstance(kw.get('strength'), list):
+            kw['strength'] = complex(*kw['strength'])
+        for freq in (1.0, -2.5, None):
+            key = f'{name}_f{freq}'
+            if key not in gs.files:
+                continue
+            sf = eb.get_source_field(grid, gs[f'{name}_source'], freq, **kw)
+            idx, val, bg = sf.sparse
+            dense = np.full(grid.n_edges, bg, dtype=val.dtype)
+            dense[idx] = val
+            assert np.array_equal(dense, sf.field)
+            assert idx.size < 400                          # a handful of edges, not a dense array
+            check(sf, gs[key], key)
+    for name in json.loads(str(gs['objects'])):
+        cls = type(str(gs[f'{name}_class']), (), {})       # same class name, same attributes
+        obj = cls()
+        obj.points, obj.coordinates = gs[f'{name}_points'], gs[f'{name}_coordinates']
+        obj.strength = float(gs[f'{name}_strength'])
+        for freq in (1.0, -2.5, None):
+            check(eb.get_source_field(grid, obj, freq), gs[f'{name}_f{freq}'], (name, freq))
+    # argument checks of the reference
+    with pytest.raises(ValueError, match='Coordinates are wrong defined'):
+        eb.get_source_field(grid, (1., 2., 3., 4.), 1.0)
+    with pytest.raises(ValueError, match='The two electrodes are identical'):
+        eb.get_source_field(grid, (1., 1., 2., 2., 3., 3.), 1.0)
+    with pytest.raises(ValueError, match='outside grid'):
+        eb.get_source_field(grid, (1e6, 0., 0., 0., 0.), 1.0)
+    pt = type('TxElectricPoint', (), {})()
+    pt.points, pt.coordinates, pt.strength = np.zeros((1, 3)), (1e6, 0., 0., 0., 0.), 1.0
+    with pytest.raises(ValueError, match='outside grid'):
+        eb.get_source_field(grid, pt, 1.0)
+    mp = type('TxMagneticPoint', (), {})()
+    mp.points, mp.coordinates, mp.strength = np.zeros((1, 3)), (0., 0., 0., 0., 0.), 1.0
+    with pytest.raises(NotImplementedError, match='magnetic point'):
+        eb.get_source_field(grid, mp, 1.0)
+
+
 def test_source_field_of_bench_configs(golden):
     """The source vectors of the golden solves are reproduced by our builder."""
     import emg3d_b200 as eb
