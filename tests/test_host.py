@@ -302,12 +302,18 @@ def test_mgparameters():
     assert var._repr_clevel['message'] == "  :: Grid not optimal for MG solver ::"
     assert "   Coarsest grid  :   3 x   5 x   7     => 105 cells\n" in repr(var)
     assert "   semicoarsening : True [3]  " in repr(var)
-    for bad in (dict(semicoarsening=5), dict(linerelaxation=-9), dict(sslsolver='jacobi'),
-                dict(cycle='G'), dict(cycle=None, sslsolver=False), dict(shape_cells=(1, 2, 2))):
+    # the reference's messages (tests/test_solver.py:685-737)
+    for bad, msg in ((dict(semicoarsening=5), '`semicoarsening` must be one o'),
+                     (dict(linerelaxation=-9), '`linerelaxation` must be one o'),
+                     (dict(sslsolver='jacobi'), '`sslsolver` must be True'),
+                     (dict(sslsolver=4), '`sslsolver` must be True'),
+                     (dict(cycle='G'), '`cycle` must be one of'),
+                     (dict(cycle=None, sslsolver=False), 'At least `cycle` or `sslsolve'),
+                     (dict(shape_cells=(1, 2, 2)), 'Nr. of cells must be at least')):
         kw = dict(verb=0, sslsolver=False, semicoarsening=False, linerelaxation=False,
                   shape_cells=(8, 8, 8))
         kw.update(bad)
-        with pytest.raises(ValueError):
+        with pytest.raises(ValueError, match=msg):
             MGParameters(**kw)
 
 
